@@ -1,0 +1,551 @@
+// Neighbor-Joining / UPGMA agglomeration loops on one B200.
+//
+// Restates the `while N > 2` loop of cassiopeia/solver/DistanceSolver.py:185-205 with
+//   NJ   : find_cherry / compute_q   cassiopeia/solver/NeighborJoiningSolver.py:123-171
+//          update_dissimilarity_map  cassiopeia/solver/NeighborJoiningSolver.py:173-260
+//   UPGMA: find_cherry               cassiopeia/solver/UPGMASolver.py:118-138
+//          update_dissimilarity_map  cassiopeia/solver/UPGMASolver.py:140-238
+//
+// Data layout in HBM: the symmetric map D[cap, ld] (both triangles kept so every node's
+// row is contiguous), live nodes occupy slots [0, k).  A join of slots lo < hi writes the
+// merged node into slot lo and moves the node of the last live slot k-1 into slot hi
+// (swap compaction), so the per-iteration scan is always a dense k x k lower triangle.
+// The reference keeps rows in "delete i and j, append the new node last" order, i.e.
+// ascending node id (leaf p -> id p, t-th merged node -> id n+t), and np.argmin takes the
+// first minimum in row-major order; the order-free equivalent used here is the
+// lexicographic minimum of (value, id_lo, id_hi)  (hard part 1).
+//
+// Kernels per iteration (k is known on the host, the chosen pair only on the device):
+//   [strict NJ] rowsum_seq : R[c] = sequential float64 column sum in id order (== numba's
+//                            d.sum(axis=1), NeighborJoiningSolver.py:160)
+//   scan                   : fused Q + lexicographic arg-min over the live lower triangle,
+//                            128-bit streaming loads, R_j staged in shared memory, persistent
+//                            CTAs over (column block, row block) tiles; the last CTA to
+//                            finish reduces the per-CTA candidates and publishes the pair.
+//   merge                  : new row/column, swap compaction, id/size/row-sum maintenance.
+// HBM roofline: the scan reads every live unordered pair once, E*k(k-1)/2 bytes
+// (E = 4 fast, 8 strict); merge touches O(k) elements.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cas {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int TC = 2048;  // columns per tile (R_j block staged in shared memory: 16 KB)
+constexpr int MERGE_THREADS = 256;
+constexpr int MAX_SCAN_CTAS = 2048;
+
+struct Cand {
+  double q;
+  unsigned long long key;  // (id_lo << 32) | id_hi ; ~0 = empty
+  int si, sj;              // slots, si > sj (row, column of the lower triangle)
+};
+
+struct Sel {
+  int lo, hi;       // slots, lo < hi
+  int size_lo, size_hi;
+  double dij;
+  int id_lo, id_hi;
+};
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int N = 4; };
+template <> struct VecOf<double> { static constexpr int N = 2; };
+
+__device__ __forceinline__ void ld_stream(const float *p, float (&v)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_stream(const double *p, double (&v)[2]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+
+__device__ __forceinline__ unsigned long long make_key(int ida, int idb) {
+  unsigned lo = (unsigned)min(ida, idb), hi = (unsigned)max(ida, idb);
+  return ((unsigned long long)lo << 32) | hi;
+}
+
+// rare path: candidate ties (or beats) the thread's running best
+__device__ __forceinline__ void tie_path(double q, int i, int j, double &bq, int &bi, int &bj,
+                                         const int32_t *__restrict__ ids) {
+  if (q < bq || bi < 0) {
+    bq = q; bi = i; bj = j;
+    return;
+  }
+  unsigned long long kn = make_key(ids[i], ids[j]);
+  unsigned long long ko = make_key(ids[bi], ids[bj]);
+  if (kn < ko) { bi = i; bj = j; }
+}
+
+__device__ __forceinline__ bool cand_better(double qa, unsigned long long ka, double qb,
+                                            unsigned long long kb) {
+  // empty candidates carry key ~0 and q = +inf
+  return (qa < qb) || (qa == qb && ka < kb);
+}
+
+struct ScanArgs {
+  const void *D;
+  int64_t ld;
+  int k;        // live nodes
+  int tr;       // rows per tile
+  int nrb;      // row blocks  = ceil(k / tr)
+  int ncb;      // col blocks  = ceil(k / TC)
+  int ntiles;
+  const double *R;
+  const int32_t *ids;
+  const int32_t *sizes;
+  double tinv;  // 1/(k-2)
+  Cand *cand;
+  unsigned *counter;
+  Sel *sel;
+  int32_t *joins;
+  int t;  // iteration index
+};
+
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int U = 4;                  // independent 128-bit loads in flight per lane
+  constexpr int STEP = 32 * V;          // elements per warp-wide load
+  __shared__ __align__(16) double sR[NJ ? TC : 2];
+  __shared__ Cand sCand[SCAN_WARPS];
+  __shared__ bool sLast;
+
+  const T *__restrict__ D = static_cast<const T *>(a.D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = a.k;
+  double bq = INFINITY;
+  int bi = -1, bj = -1;
+  int staged_cb = -1;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    // linear tile -> (column block, row block); column-block major
+    int cb = 0, rem = tile;
+    for (;;) {
+      int first = (cb * TC + 1) / a.tr;  // first row block with an element right of c0
+      int cnt = max(a.nrb - first, 0);
+      if (rem < cnt) { rem += first; break; }
+      rem -= cnt;
+      ++cb;
+    }
+    const int rb = rem;
+    const int c0 = cb * TC;
+    const int c1 = min(c0 + TC, k);
+    if (NJ && cb != staged_cb) {
+      __syncthreads();  // previous tile's readers are done with sR
+      for (int x = threadIdx.x; x < c1 - c0; x += SCAN_THREADS) sR[x] = a.R[c0 + x];
+      staged_cb = cb;
+      __syncthreads();
+    }
+    const int r0 = rb * a.tr;
+    const int r1 = min(r0 + a.tr, k);
+    for (int i = r0 + warp; i < r1; i += SCAN_WARPS) {
+      const int jend = min(c1, i);  // columns [c0, jend) of row i lie below the diagonal
+      if (jend <= c0) continue;
+      const T *__restrict__ row = D + (int64_t)i * a.ld;
+      const double Ri = NJ ? a.R[i] : 0.0;
+      for (int jb = c0; jb < jend; jb += STEP * U) {
+        T v[U][V];
+        const bool whole = (jb + STEP * U <= jend);
+        if (whole) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) ld_stream(row + jb + u * STEP + lane * V, v[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = jb + u * STEP + lane * V;
+            if (j < jend) ld_stream(row + j, v[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = jb + u * STEP + lane * V;
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            if (whole || (j + e < jend)) {
+              double q = (double)v[u][e];
+              if (NJ) {
+                // q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) ), no FMA  (NeighborJoiningSolver.py:163-170)
+                q = __dsub_rn(q, __dmul_rn(a.tinv, __dadd_rn(Ri, sR[j + e - c0])));
+              }
+              if (q <= bq) tie_path(q, i, j + e, bq, bi, bj, a.ids);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // warp reduce on (q, key)
+  unsigned long long bkey = (bi >= 0) ? make_key(a.ids[bi], a.ids[bj]) : ~0ull;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double oq = __shfl_down_sync(0xffffffffu, bq, off);
+    unsigned long long ok = __shfl_down_sync(0xffffffffu, bkey, off);
+    int oi = __shfl_down_sync(0xffffffffu, bi, off);
+    int oj = __shfl_down_sync(0xffffffffu, bj, off);
+    if (cand_better(oq, ok, bq, bkey)) { bq = oq; bkey = ok; bi = oi; bj = oj; }
+  }
+  if (lane == 0) { sCand[warp].q = bq; sCand[warp].key = bkey; sCand[warp].si = bi; sCand[warp].sj = bj; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Cand c = sCand[0];
+    for (int w = 1; w < SCAN_WARPS; ++w)
+      if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
+    a.cand[blockIdx.x] = c;
+    __threadfence();
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);  // wraps back to 0
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  // the last CTA reduces all per-CTA candidates
+  Cand c;
+  c.q = INFINITY; c.key = ~0ull; c.si = -1; c.sj = -1;
+  for (int x = threadIdx.x; x < (int)gridDim.x; x += SCAN_THREADS) {
+    Cand o;  // written by other CTAs: read through L2
+    o.q = __ldcg(&a.cand[x].q);
+    o.key = __ldcg(&a.cand[x].key);
+    o.si = __ldcg(&a.cand[x].si);
+    o.sj = __ldcg(&a.cand[x].sj);
+    if (cand_better(o.q, o.key, c.q, c.key)) c = o;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double oq = __shfl_down_sync(0xffffffffu, c.q, off);
+    unsigned long long ok = __shfl_down_sync(0xffffffffu, c.key, off);
+    int oi = __shfl_down_sync(0xffffffffu, c.si, off);
+    int oj = __shfl_down_sync(0xffffffffu, c.sj, off);
+    if (cand_better(oq, ok, c.q, c.key)) { c.q = oq; c.key = ok; c.si = oi; c.sj = oj; }
+  }
+  __syncthreads();
+  if (lane == 0) sCand[warp] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c = sCand[0];
+    for (int w = 1; w < SCAN_WARPS; ++w)
+      if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
+    Sel s;
+    s.lo = min(c.si, c.sj);
+    s.hi = max(c.si, c.sj);
+    s.dij = (double)D[(int64_t)s.lo * a.ld + s.hi];
+    s.size_lo = a.sizes ? a.sizes[s.lo] : 1;
+    s.size_hi = a.sizes ? a.sizes[s.hi] : 1;
+    s.id_lo = a.ids[s.lo];
+    s.id_hi = a.ids[s.hi];
+    *a.sel = s;
+    a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
+    a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
+  }
+}
+
+struct MergeArgs {
+  void *D;
+  int64_t ld;
+  int k;
+  const Sel *sel;
+  double *R;          // fast NJ: maintained row sums (by slot); else unused
+  int32_t *ids;
+  int32_t *sizes;     // UPGMA
+  double *partial;    // [gridDim] per-CTA partial sums of the new row
+  unsigned *counter;
+  int new_id;
+  int maintain_R;     // fast NJ
+  // strict NJ: live slots in id order, double buffered
+  const int32_t *order_old; const int32_t *pos_old;
+  int32_t *order_new; int32_t *pos_new;
+};
+
+template <typename T> __device__ __forceinline__ T round_to(double v);
+template <> __device__ __forceinline__ float round_to<float>(double v) { return __double2float_rn(v); }
+template <> __device__ __forceinline__ double round_to<double>(double v) { return v; }
+
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
+  __shared__ double sPart[MERGE_THREADS / 32];
+  __shared__ bool sLast;
+  T *__restrict__ D = static_cast<T *>(a.D);
+  const Sel s = *a.sel;
+  const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1;
+  const int64_t ld = a.ld;
+  const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
+  double contrib = 0.0;
+
+  if (v < k) {
+    if (v == lo) {
+      D[(int64_t)lo * ld + lo] = (T)0;
+      a.ids[lo] = a.new_id;
+      if (a.sizes) a.sizes[lo] = s.size_lo + s.size_hi;
+    } else if (v == hi) {
+      D[(int64_t)hi * ld + hi] = (T)0;
+    } else {
+      const double da = (double)D[(int64_t)lo * ld + v];
+      const double db = (double)D[(int64_t)hi * ld + v];
+      double nv;
+      if (NJ) {
+        // 0.5 * ((d_vi + d_vj) - d_ij)   (NeighborJoiningSolver.py:254-258)
+        nv = __dmul_rn(0.5, __dsub_rn(__dadd_rn(da, db), s.dij));
+      } else {
+        // (s_i * d_vi + s_j * d_vj) / (s_i + s_j)   (UPGMASolver.py:231-234)
+        const double zi = (double)s.size_lo, zj = (double)s.size_hi;
+        nv = __ddiv_rn(__dadd_rn(__dmul_rn(zi, da), __dmul_rn(zj, db)),
+                       (double)(s.size_lo + s.size_hi));
+      }
+      const T nvs = round_to<T>(nv);
+      contrib = (double)nvs;
+      double Rv = 0.0;
+      if (a.maintain_R) Rv = __dadd_rn(__dsub_rn(__dsub_rn(a.R[v], da), db), contrib);
+      if (hi != last && v != last) {
+        // the node in the last live slot moves into slot hi
+        const T l = D[(int64_t)last * ld + v];
+        D[(int64_t)hi * ld + v] = l;
+        D[(int64_t)v * ld + hi] = l;
+      }
+      D[(int64_t)lo * ld + v] = nvs;
+      D[(int64_t)v * ld + lo] = nvs;
+      if (v == last && hi != last) {
+        D[(int64_t)hi * ld + lo] = nvs;
+        D[(int64_t)lo * ld + hi] = nvs;
+        D[(int64_t)hi * ld + hi] = (T)0;
+        a.ids[hi] = a.ids[last];
+        if (a.sizes) a.sizes[hi] = a.sizes[last];
+        if (a.maintain_R) a.R[hi] = Rv;
+      } else if (a.maintain_R) {
+        a.R[v] = Rv;
+      }
+    }
+    // strict NJ: rebuild the id-ordered list of live slots
+    if (a.order_old) {
+      const int p = v;  // thread p handles the p-th live node in id order
+      const int p_lo = a.pos_old[lo], p_hi = a.pos_old[hi];
+      if (p != p_lo && p != p_hi) {
+        int sl = a.order_old[p];
+        if (sl == last) sl = hi;
+        const int np = p - (p > p_lo ? 1 : 0) - (p > p_hi ? 1 : 0);
+        a.order_new[np] = sl;
+        a.pos_new[sl] = np;
+      }
+      if (p == 0) {
+        a.order_new[k - 2] = lo;  // merged node has the largest id: last
+        a.pos_new[lo] = k - 2;
+      }
+    }
+  }
+
+  if (!a.maintain_R) return;
+  // deterministic sum of the new row: fixed 256-wide chunks, shuffle tree, then sequential
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
+  if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int w = 0; w < MERGE_THREADS / 32; ++w) sum = __dadd_rn(sum, sPart[w]);
+    a.partial[blockIdx.x] = sum;
+    __threadfence();
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (sLast && threadIdx.x == 0) {
+    __threadfence();
+    double sum = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
+    a.R[lo] = sum;
+  }
+}
+
+// strict NJ: R[c] = ((0 + d[o_0][c]) + d[o_1][c]) + ... over live nodes in id order
+template <typename T>
+__global__ void __launch_bounds__(64) rowsum_seq_kernel(const T *__restrict__ D, int64_t ld, int k,
+                                                        const int32_t *__restrict__ order,
+                                                        double *__restrict__ R) {
+  const int c = blockIdx.x * 64 + threadIdx.x;
+  if (c >= k) return;
+  double s = 0.0;
+  int p = 0;
+  for (; p + 8 <= k; p += 8) {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = (double)D[(int64_t)order[p + u] * ld + c];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = __dadd_rn(s, x[u]);
+  }
+  for (; p < k; ++p) s = __dadd_rn(s, (double)D[(int64_t)order[p] * ld + c]);
+  R[c] = s;
+}
+
+// fast NJ: initial row sums, one warp per row, fixed lane-strided order + shuffle tree
+template <typename T>
+__global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ D, int64_t ld, int k,
+                                                          double *__restrict__ R) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= k) return;
+  const T *__restrict__ r = D + (int64_t)row * ld;
+  double s = 0.0;
+  for (int j = lane; j < k; j += 32) s = __dadd_rn(s, (double)r[j]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+  if (lane == 0) R[row] = s;
+}
+
+__global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *order, int32_t *pos,
+                                  unsigned *counters) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) {
+    ids[v] = v;
+    if (sizes) sizes[v] = 1;
+    if (order) { order[v] = v; pos[v] = v; }
+  }
+  if (v < 8) counters[v] = 0;
+}
+
+__global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2) {
+  if (threadIdx.x == 0) {
+    if (n >= 2) {
+      last2[0] = min(ids[0], ids[1]);
+      last2[1] = max(ids[0], ids[1]);
+    } else {
+      last2[0] = n >= 1 ? ids[0] : -1;
+      last2[1] = -1;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------
+
+struct AgglomWorkspace {
+  double *R;
+  int32_t *ids, *sizes;
+  int32_t *order[2], *pos[2];
+  Cand *cand;
+  Sel *sel;
+  double *partial;
+  unsigned *counters;
+  size_t bytes;
+};
+
+static AgglomWorkspace carve_workspace(void *base, int64_t n) {
+  Carver c(base);
+  AgglomWorkspace w;
+  w.R = c.take<double>(n);
+  w.ids = c.take<int32_t>(n);
+  w.sizes = c.take<int32_t>(n);
+  w.order[0] = c.take<int32_t>(n);
+  w.order[1] = c.take<int32_t>(n);
+  w.pos[0] = c.take<int32_t>(n);
+  w.pos[1] = c.take<int32_t>(n);
+  w.cand = c.take<Cand>(MAX_SCAN_CTAS);
+  w.sel = c.take<Sel>(4);
+  w.partial = c.take<double>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
+  w.counters = c.take<unsigned>(64);
+  w.bytes = c.used();
+  return w;
+}
+
+size_t agglom_workspace_bytes(int64_t n) { return carve_workspace(nullptr, n > 0 ? n : 1).bytes; }
+
+// choose rows-per-tile so that the persistent grid has a few tiles per CTA
+static inline void plan_scan(int k, int target_ctas, int &tr, int &nrb, int &ncb, int &ntiles) {
+  ncb = (k + TC - 1) / TC;
+  tr = 32;
+  for (;;) {
+    nrb = (k + tr - 1) / tr;
+    long long cnt = 0;
+    for (int cb = 0; cb < ncb; ++cb) {
+      int first = (cb * TC + 1) / tr;
+      if (nrb > first) cnt += nrb - first;
+    }
+    ntiles = (int)cnt;
+    if (ntiles >= 2 * target_ctas || tr == 8) break;
+    tr >>= 1;
+  }
+}
+
+template <typename T, bool NJ>
+static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iters, int32_t *joins,
+                      int32_t *last2, void *workspace, cudaStream_t stream) {
+  AgglomWorkspace w = carve_workspace(workspace, n);
+  const bool strict_nj = NJ && (mode == CAS_MODE_STRICT);
+  const bool fast_nj = NJ && (mode == CAS_MODE_FAST);
+  const int sms = sm_count();
+  const int target_ctas = sms * 4;
+
+  {
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks == 0) blocks = 1;
+    init_state_kernel<<<blocks, 256, 0, stream>>>((int)n, w.ids, NJ ? nullptr : w.sizes,
+                                                  strict_nj ? w.order[0] : nullptr,
+                                                  strict_nj ? w.pos[0] : nullptr, w.counters);
+    CAS_LAUNCH_CHECK();
+  }
+  if (fast_nj && n > 2) {
+    rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>((const T *)D, ld, (int)n, w.R);
+    CAS_LAUNCH_CHECK();
+  }
+  int64_t k_final = n;
+  for (int64_t t = 0; t + 2 < n; ++t) {
+    if (max_iters >= 0 && t >= max_iters) break;
+    const int k = (int)(n - t);
+    k_final = k - 1;
+    const int cur = (int)(t & 1);
+    if (strict_nj) {
+      rowsum_seq_kernel<T><<<(unsigned)((k + 63) / 64), 64, 0, stream>>>((const T *)D, ld, k,
+                                                                          w.order[cur], w.R);
+      CAS_LAUNCH_CHECK();
+    }
+    ScanArgs sa;
+    sa.D = D; sa.ld = ld; sa.k = k;
+    plan_scan(k, target_ctas, sa.tr, sa.nrb, sa.ncb, sa.ntiles);
+    sa.R = w.R; sa.ids = w.ids; sa.sizes = NJ ? nullptr : w.sizes;
+    sa.tinv = 1.0 / (double)(k - 2);
+    sa.cand = w.cand; sa.counter = w.counters + 0; sa.sel = w.sel; sa.joins = joins; sa.t = (int)t;
+    int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
+    if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
+    if (grid < 1) grid = 1;
+    scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+    CAS_LAUNCH_CHECK();
+
+    MergeArgs ma;
+    ma.D = D; ma.ld = ld; ma.k = k; ma.sel = w.sel; ma.R = w.R; ma.ids = w.ids;
+    ma.sizes = NJ ? nullptr : w.sizes; ma.partial = w.partial; ma.counter = w.counters + 1;
+    ma.new_id = (int)(n + t); ma.maintain_R = fast_nj ? 1 : 0;
+    ma.order_old = strict_nj ? w.order[cur] : nullptr;
+    ma.pos_old = strict_nj ? w.pos[cur] : nullptr;
+    ma.order_new = strict_nj ? w.order[cur ^ 1] : nullptr;
+    ma.pos_new = strict_nj ? w.pos[cur ^ 1] : nullptr;
+    merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
+    CAS_LAUNCH_CHECK();
+  }
+  last2_kernel<<<1, 32, 0, stream>>>(w.ids, (int)(k_final < 2 ? k_final : 2), last2);
+  CAS_LAUNCH_CHECK();
+  return CAS_OK;
+}
+
+int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
+                 int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
+                 size_t workspace_bytes, cudaStream_t stream) {
+  CAS_REQUIRE(n >= 1 && n < (int64_t)1 << 30, "n=%lld out of range", (long long)n);
+  CAS_REQUIRE(ld >= n && ld % 32 == 0, "ld=%lld must be >= n and a multiple of 32", (long long)ld);
+  CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
+  CAS_REQUIRE(mode == CAS_MODE_STRICT || mode == CAS_MODE_FAST, "bad mode %d", mode);
+  CAS_REQUIRE(!(mode == CAS_MODE_STRICT && dtype != CAS_F64), "strict mode requires a float64 map");
+  CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(n), "workspace too small for agglomeration");
+  CAS_REQUIRE(((uintptr_t)D & 15) == 0, "D must be 16-byte aligned");
+  if (algo == CAS_ALGO_NJ) {
+    if (dtype == CAS_F64) return agglom_run<double, true>(D, n, ld, mode, max_iters, joins, last2, workspace, stream);
+    return agglom_run<float, true>(D, n, ld, mode, max_iters, joins, last2, workspace, stream);
+  } else if (algo == CAS_ALGO_UPGMA) {
+    if (dtype == CAS_F64) return agglom_run<double, false>(D, n, ld, mode, max_iters, joins, last2, workspace, stream);
+    return agglom_run<float, false>(D, n, ld, mode, max_iters, joins, last2, workspace, stream);
+  }
+  set_error("bad algo %d", algo);
+  return CAS_ERR_INVALID;
+}
+
+}  // namespace cas

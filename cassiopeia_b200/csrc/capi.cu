@@ -1,0 +1,208 @@
+// C-ABI entry points of libcas_b200.so (declared in include/cas_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace cas {
+
+static thread_local char g_err[1024] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int64_t n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      cached = sms;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+// implemented in whd_exact.cu / whd_gemm.cu / agglom.cu
+size_t whd_exact_workspace_bytes(int64_t n, int32_t m, int32_t weighted);
+int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
+                  int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
+                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int whd_read_error_flag(const void *workspace, cudaStream_t stream, int *flag);
+size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted);
+int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
+                 int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
+                 void *workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t agglom_workspace_bytes(int64_t n);
+int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
+                 int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace cas
+
+using namespace cas;
+
+extern "C" {
+
+int cas_abi_version(void) { return CAS_ABI_VERSION; }
+
+const char *cas_last_error(void) { return g_err; }
+
+int64_t cas_last_launch_count(void) { return g_launches; }
+
+int cas_device_info(int32_t *sms, int32_t *cc_major, int32_t *cc_minor, size_t *free_bytes,
+                    size_t *total_bytes) {
+  int dev = 0;
+  CAS_CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CAS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (sms) *sms = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  size_t f = 0, t = 0;
+  CAS_CUDA_TRY(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return CAS_OK;
+}
+
+size_t cas_whd_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted,
+                               int32_t method) {
+  if (method == CAS_MAP_TENSOR) return whd_gemm_workspace_bytes(n, m, n_states, weighted);
+  return whd_exact_workspace_bytes(n, m, weighted);
+}
+
+int cas_whd_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
+                int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
+                int32_t method, void *workspace, size_t workspace_bytes, void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(cm && D && workspace, "null pointer argument");
+  CAS_REQUIRE(n >= 1 && m >= 1, "empty character matrix (n=%lld, m=%d)", (long long)n, m);
+  CAS_REQUIRE(0 <= row0 && row0 <= row1 && row1 <= n, "bad row block [%lld,%lld)",
+              (long long)row0, (long long)row1);
+  CAS_REQUIRE(ld >= n, "ld=%lld < n=%lld", (long long)ld, (long long)n);
+  CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
+  if (method == CAS_MAP_TENSOR)
+    return whd_gemm_map(cm, n, m, missing, w, n_states, D, ld, dtype, row0, row1, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+  CAS_REQUIRE(method == CAS_MAP_EXACT, "bad map method %d", method);
+  return whd_exact_map(cm, n, m, missing, w, n_states, D, ld, dtype, row0, row1, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t cas_agglom_workspace_bytes(int64_t n, int32_t algo, int32_t mode) {
+  (void)algo; (void)mode;
+  return agglom_workspace_bytes(n);
+}
+
+int cas_nj_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t mode, int64_t max_iters,
+                 int32_t *joins, int32_t *last2, void *workspace, size_t workspace_bytes,
+                 void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(D && joins && last2 && workspace, "null pointer argument");
+  return agglom_solve(D, n, ld, dtype, CAS_ALGO_NJ, mode, max_iters, joins, last2, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
+}
+
+int cas_upgma_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t mode,
+                    int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
+                    size_t workspace_bytes, void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(D && joins && last2 && workspace, "null pointer argument");
+  return agglom_solve(D, n, ld, dtype, CAS_ALGO_UPGMA, mode, max_iters, joins, last2, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
+}
+
+// RAII device buffer for the host-buffer entry point
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t missing,
+                   const double *w_host, int32_t n_states, int32_t algo, int32_t mode,
+                   int32_t map_method, int32_t *joins_host, int32_t *last2_host,
+                   double *timings_ms) {
+  reset_launch_count();
+  CAS_REQUIRE(cm_host && joins_host && last2_host, "null pointer argument");
+  CAS_REQUIRE(n >= 2 && m >= 1, "need at least two samples (n=%lld, m=%d)", (long long)n, m);
+  CAS_REQUIRE(algo == CAS_ALGO_NJ || algo == CAS_ALGO_UPGMA, "bad algo %d", algo);
+  const int dtype = (mode == CAS_MODE_STRICT) ? CAS_F64 : CAS_F32;
+  const size_t esz = dtype == CAS_F64 ? 8 : 4;
+  const int64_t ld = (int64_t)align_up((size_t)n, 32);
+  const bool weighted = w_host != nullptr;
+
+  cudaStream_t stream;
+  CAS_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{stream};
+  cudaEvent_t ev[5];
+  for (auto &e : ev) CAS_CUDA_TRY(cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); } } eg{ev};
+
+  DevBuf cm_d, w_d, D_d, ws_map, ws_loop, joins_d, last2_d;
+  const size_t njoin = n > 2 ? (size_t)(n - 2) : 0;
+  CAS_CUDA_TRY(cm_d.alloc((size_t)n * m * sizeof(int32_t)));
+  if (weighted) CAS_CUDA_TRY(w_d.alloc((size_t)m * (n_states + 1) * sizeof(double)));
+  CAS_CUDA_TRY(D_d.alloc((size_t)n * ld * esz));
+  const size_t wsm = cas_whd_workspace_bytes(n, m, n_states, weighted, map_method);
+  const size_t wsl = cas_agglom_workspace_bytes(n, algo, mode);
+  CAS_CUDA_TRY(ws_map.alloc(wsm));
+  CAS_CUDA_TRY(ws_loop.alloc(wsl));
+  CAS_CUDA_TRY(joins_d.alloc((njoin + 1) * 2 * sizeof(int32_t)));
+  CAS_CUDA_TRY(last2_d.alloc(2 * sizeof(int32_t)));
+
+  CAS_CUDA_TRY(cudaEventRecord(ev[0], stream));
+  CAS_CUDA_TRY(cudaMemcpyAsync(cm_d.p, cm_host, (size_t)n * m * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, stream));
+  if (weighted)
+    CAS_CUDA_TRY(cudaMemcpyAsync(w_d.p, w_host, (size_t)m * (n_states + 1) * sizeof(double),
+                                 cudaMemcpyHostToDevice, stream));
+  CAS_CUDA_TRY(cudaEventRecord(ev[1], stream));
+  int rc;
+  if (map_method == CAS_MAP_TENSOR)
+    rc = whd_gemm_map((const int32_t *)cm_d.p, n, m, missing, (const double *)w_d.p, n_states, D_d.p,
+                      ld, dtype, 0, n, ws_map.p, wsm, stream);
+  else
+    rc = whd_exact_map((const int32_t *)cm_d.p, n, m, missing, (const double *)w_d.p, n_states,
+                       D_d.p, ld, dtype, 0, n, ws_map.p, wsm, stream);
+  if (rc != CAS_OK) return rc;
+  CAS_CUDA_TRY(cudaEventRecord(ev[2], stream));
+  rc = agglom_solve(D_d.p, n, ld, dtype, algo, mode, -1, (int32_t *)joins_d.p,
+                    (int32_t *)last2_d.p, ws_loop.p, wsl, stream);
+  if (rc != CAS_OK) return rc;
+  CAS_CUDA_TRY(cudaEventRecord(ev[3], stream));
+  if (njoin)
+    CAS_CUDA_TRY(cudaMemcpyAsync(joins_host, joins_d.p, njoin * 2 * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaMemcpyAsync(last2_host, last2_d.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                               stream));
+  CAS_CUDA_TRY(cudaEventRecord(ev[4], stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize(stream));
+  int flag = 0;
+  if (map_method == CAS_MAP_EXACT) {
+    rc = whd_read_error_flag(ws_map.p, stream, &flag);
+    if (rc != CAS_OK) return rc;
+    CAS_REQUIRE(flag == 0, "character matrix holds a state outside [0, n_states] that is not the missing indicator");
+  }
+  if (timings_ms) {
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0.f;
+      CAS_CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      timings_ms[i] = ms;
+    }
+  }
+  return CAS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// Exact pairwise weighted-Hamming dissimilarity map on CUDA cores.
+//
+// Restates cassiopeia/solver/dissimilarity_functions.py:46-72 (per pair) and the pair
+// enumeration of cassiopeia/data/utilities.py:358-368, producing the square symmetric
+// map the reference obtains through scipy squareform (CassiopeiaTree.py:1935).
+//
+// Bit-exactness: the numerator is accumulated in float64 in character order exactly
+// as the reference does (`d += w[a] + w[b]`: the two weights are added first, then
+// added to d; an uncut state contributes weight 0.0 and x + 0.0 == x), the unweighted
+// numerator is an exact integer, and the only other rounding is the IEEE float64
+// division by the shared-present count.  No multiplications => nothing for the
+// compiler to contract; the adds use __dadd_rn anyway.
+//
+// Layout: the int32 character matrix is first packed (K1 `encode`) into 16-bit codes
+// [n, m_pad] (missing -> 0xFFFF) and, when weighted, a per-cell weight row
+// [n, m_pad] float64 (weight of the cell's own state, 0.0 for uncut/missing), so the
+// pair kernel needs no table lookups.  Pair kernel: 64x64 output tile per CTA,
+// 4x4 pairs per thread, characters staged through shared memory in chunks of 32.
+#include "common.cuh"
+
+namespace cas {
+
+constexpr int TILE = 64;      // pairs per CTA edge
+constexpr int CK = 32;        // characters per shared-memory chunk
+constexpr int CPAD = TILE + 4;  // u16 row pitch (8-byte aligned 4-code reads)
+constexpr int WPAD = TILE + 2;  // f64 row pitch (16-byte aligned 2-weight reads)
+constexpr uint16_t MISS = 0xFFFFu;
+
+__global__ void encode_kernel(const int32_t *__restrict__ cm, int64_t n, int m, int m_pad,
+                              int32_t missing, const double *__restrict__ w, int n_states,
+                              uint16_t *__restrict__ codes, double *__restrict__ wrow,
+                              int *__restrict__ err_flag) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = n * (int64_t)m_pad;
+  if (idx >= total) return;
+  int64_t r = idx / m_pad;
+  int c = (int)(idx - r * m_pad);
+  uint16_t code = MISS;
+  double wt = 0.0;
+  if (c < m) {
+    int32_t s = cm[r * m + c];
+    if (s == missing) {
+      code = MISS;
+    } else if (s < 0 || s > n_states) {
+      atomicExch(err_flag, 1);  // state outside [0, n_states]: host validation was skipped
+      code = MISS;
+    } else {
+      code = (uint16_t)s;
+      if (w != nullptr && s != 0) wt = w[(int64_t)c * (n_states + 1) + s];
+    }
+  }
+  codes[idx] = code;
+  if (wrow != nullptr) wrow[idx] = wt;
+}
+
+template <typename T>
+__device__ __forceinline__ T cvt_out(double v);
+template <>
+__device__ __forceinline__ double cvt_out<double>(double v) { return v; }
+template <>
+__device__ __forceinline__ float cvt_out<float>(double v) { return __double2float_rn(v); }
+
+// grid.x enumerates tiles.  tri != 0: lower-triangular tiles of the full map, mirrored.
+// tri == 0: all tiles of the row block [row0,row1) x [0,n).
+template <typename T, bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+whd_exact_kernel(const uint16_t *__restrict__ codes, const double *__restrict__ wrow, int64_t n,
+                 int m, int m_pad, T *__restrict__ D, int64_t ld, int64_t row0, int64_t row1,
+                 int tri, int tiles_x) {
+  __shared__ __align__(16) uint16_t sA[CK][CPAD];
+  __shared__ __align__(16) uint16_t sB[CK][CPAD];
+  __shared__ __align__(16) double sWA[WEIGHTED ? CK : 1][WPAD];
+  __shared__ __align__(16) double sWB[WEIGHTED ? CK : 1][WPAD];
+
+  int64_t tr, tc;  // tile row / col indices
+  if (tri) {
+    // linear index -> (tr, tc) with tc <= tr
+    int64_t t = blockIdx.x;
+    int64_t r = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    while (r * (r + 1) / 2 > t) --r;
+    tr = r;
+    tc = t - r * (r + 1) / 2;
+  } else {
+    tr = blockIdx.x / tiles_x;
+    tc = blockIdx.x % tiles_x;
+  }
+  const int64_t i0 = row0 + tr * TILE;  // first row (global index) of this tile
+  const int64_t j0 = tc * TILE;         // first column
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  double acc[4][4];
+  int npres[4][4];
+  int inum[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { acc[a][b] = 0.0; npres[a][b] = 0; inum[a][b] = 0; }
+
+  for (int c0 = 0; c0 < m; c0 += CK) {
+    // stage [64 rows x CK chars] of both operands, transposed to [char][row]
+    for (int e = threadIdx.x; e < TILE * CK; e += 256) {
+      int row = e / CK, c = e % CK;
+      int64_t gi = i0 + row, gj = j0 + row;
+      int cc = c0 + c;
+      uint16_t ca = MISS, cb = MISS;
+      double wa = 0.0, wb = 0.0;
+      if (cc < m_pad) {
+        if (gi < n) { ca = codes[gi * m_pad + cc]; if (WEIGHTED) wa = wrow[gi * m_pad + cc]; }
+        if (gj < n) { cb = codes[gj * m_pad + cc]; if (WEIGHTED) wb = wrow[gj * m_pad + cc]; }
+      }
+      sA[c][row] = ca;
+      sB[c][row] = cb;
+      if (WEIGHTED) { sWA[c][row] = wa; sWB[c][row] = wb; }
+    }
+    __syncthreads();
+    const int cend = min(CK, m - c0);
+    for (int c = 0; c < cend; ++c) {
+      uint16_t a[4], b[4];
+      *reinterpret_cast<uint2 *>(a) = *reinterpret_cast<const uint2 *>(&sA[c][ty * 4]);
+      *reinterpret_cast<uint2 *>(b) = *reinterpret_cast<const uint2 *>(&sB[c][tx * 4]);
+      double wa[4], wb[4];
+      if (WEIGHTED) {
+        *reinterpret_cast<double2 *>(&wa[0]) = *reinterpret_cast<const double2 *>(&sWA[c][ty * 4]);
+        *reinterpret_cast<double2 *>(&wa[2]) = *reinterpret_cast<const double2 *>(&sWA[c][ty * 4 + 2]);
+        *reinterpret_cast<double2 *>(&wb[0]) = *reinterpret_cast<const double2 *>(&sWB[c][tx * 4]);
+        *reinterpret_cast<double2 *>(&wb[2]) = *reinterpret_cast<const double2 *>(&sWB[c][tx * 4 + 2]);
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const bool pres = (a[x] != MISS) && (b[y] != MISS);
+          const bool neq = pres && (a[x] != b[y]);
+          npres[x][y] += pres ? 1 : 0;
+          if (WEIGHTED) {
+            // d += w(a) + w(b): weights summed first, then accumulated (reference order)
+            const double t = __dadd_rn(wa[x], wb[y]);
+            if (neq) acc[x][y] = __dadd_rn(acc[x][y], t);
+          } else {
+            if (neq) inum[x][y] += (a[x] != 0 ? 1 : 0) + (b[y] != 0 ? 1 : 0);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const bool mirror = tri && (tr != tc);
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int64_t gi = i0 + ty * 4 + x;
+    if (gi >= n || gi >= row1) continue;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int64_t gj = j0 + tx * 4 + y;
+      if (gj >= n) continue;
+      double v = 0.0;
+      if (npres[x][y] > 0) {
+        const double num = WEIGHTED ? acc[x][y] : (double)inum[x][y];
+        v = __ddiv_rn(num, (double)npres[x][y]);
+      }
+      if (gi == gj) v = 0.0;
+      const T o = cvt_out<T>(v);
+      D[(gi - row0) * ld + gj] = o;
+      if (mirror) D[(gj - row0) * ld + gi] = o;
+    }
+  }
+}
+
+static inline int pad_m(int m) { return (m + 7) / 8 * 8; }
+
+size_t whd_exact_workspace_bytes(int64_t n, int32_t m, int32_t weighted) {
+  Carver c(nullptr);
+  size_t total = (size_t)n * pad_m(m);
+  c.take<int>(64);
+  c.take<uint16_t>(total);
+  if (weighted) c.take<double>(total);
+  return c.used();
+}
+
+int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
+                  int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
+                  void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  CAS_REQUIRE(n_states >= 0 && n_states <= 65534, "n_states=%d outside [0, 65534]", n_states);
+  const bool weighted = (w != nullptr);
+  CAS_REQUIRE(workspace_bytes >= whd_exact_workspace_bytes(n, m, weighted),
+              "workspace too small for whd map");
+  Carver carve(workspace);
+  const int mp = pad_m(m);
+  int *err_flag = carve.take<int>(64);
+  uint16_t *codes = carve.take<uint16_t>((size_t)n * mp);
+  double *wrow = weighted ? carve.take<double>((size_t)n * mp) : nullptr;
+
+  CAS_CUDA_TRY(cudaMemsetAsync(err_flag, 0, sizeof(int), stream));
+  {
+    int64_t total = n * (int64_t)mp;
+    int64_t blocks = (total + 255) / 256;
+    encode_kernel<<<(unsigned)blocks, 256, 0, stream>>>(cm, n, m, mp, missing, w, n_states, codes,
+                                                        wrow, err_flag);
+    CAS_LAUNCH_CHECK();
+  }
+  const bool full = (row0 == 0 && row1 == n);
+  const int64_t tiles_r = (row1 - row0 + TILE - 1) / TILE;
+  const int64_t tiles_c = (n + TILE - 1) / TILE;
+  const int64_t ntiles = full ? tiles_r * (tiles_r + 1) / 2 : tiles_r * tiles_c;
+  CAS_REQUIRE(ntiles < (int64_t)2147483647, "too many tiles");
+  if (ntiles == 0) return CAS_OK;
+  dim3 grid((unsigned)ntiles);
+#define LAUNCH(T, W)                                                                          \
+  whd_exact_kernel<T, W><<<grid, 256, 0, stream>>>(codes, wrow, n, m, mp, (T *)D, ld, row0,  \
+                                                   row1, full ? 1 : 0, (int)tiles_c)
+  if (dtype == CAS_F64) {
+    if (weighted) LAUNCH(double, true); else LAUNCH(double, false);
+  } else {
+    if (weighted) LAUNCH(float, true); else LAUNCH(float, false);
+  }
+#undef LAUNCH
+  CAS_LAUNCH_CHECK();
+  return CAS_OK;
+}
+
+// device flag written by encode_kernel (first int of the workspace)
+int whd_read_error_flag(const void *workspace, cudaStream_t stream, int *flag) {
+  CAS_CUDA_TRY(cudaMemcpyAsync(flag, workspace, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize(stream));
+  return CAS_OK;
+}
+
+}  // namespace cas

@@ -1,0 +1,149 @@
+"""Thin device-side driver over the C ABI.
+
+PyTorch is used only for plumbing: it owns the device buffers (character matrix,
+weights, the n x ld dissimilarity map, scratch) and supplies the CUDA stream.
+All arithmetic happens in the hand-written kernels of ``libcas_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (CAS_ALGO_NJ, CAS_ALGO_UPGMA, CAS_F32, CAS_F64, CAS_MAP_EXACT, CAS_MAP_TENSOR,
+                   CAS_MODE_FAST, CAS_MODE_STRICT, B200LibraryError)
+
+_ALGO = {"nj": CAS_ALGO_NJ, "upgma": CAS_ALGO_UPGMA}
+_MODE = {"strict": CAS_MODE_STRICT, "fast": CAS_MODE_FAST}
+_METHOD = {"exact": CAS_MAP_EXACT, "tensor": CAS_MAP_TENSOR}
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise B200LibraryError("no CUDA device visible: the B200 kernels cannot run (no CPU fallback)")
+    return torch
+
+
+def padded_ld(n: int) -> int:
+    """Row pitch (elements) of a map with n columns: multiple of 32 => 128-byte aligned rows."""
+    return (int(n) + 31) // 32 * 32
+
+
+def _stream_ptr(torch) -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def device_info() -> dict:
+    L = _lib.load()
+    _torch()
+    sms, maj, mnr = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    fr, tot = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(L.cas_device_info(ctypes.byref(sms), ctypes.byref(maj), ctypes.byref(mnr),
+                                 ctypes.byref(fr), ctypes.byref(tot)), "cas_device_info")
+    return {"sm_count": sms.value, "cc": (maj.value, mnr.value), "free_bytes": fr.value,
+            "total_bytes": tot.value}
+
+
+def last_launch_count() -> int:
+    return int(_lib.load().cas_last_launch_count())
+
+
+def whd_map(cm, missing: int, weights: Optional[np.ndarray], n_states: int, dtype: str = "f64",
+            method: str = "exact", rows: Optional[Tuple[int, int]] = None, out=None):
+    """Pairwise weighted-Hamming map of an int32 [n, m] matrix of compact state codes.
+
+    cm may be a numpy array (copied to the device) or a CUDA int32 tensor.  Returns a
+    CUDA tensor of shape [rows, ld] (ld = padded_ld(n)); columns >= n are padding.
+    """
+    torch = _torch()
+    L = _lib.load()
+    if isinstance(cm, np.ndarray):
+        cm_t = torch.from_numpy(np.ascontiguousarray(cm, dtype=np.int32)).cuda()
+    else:
+        cm_t = cm.to(device="cuda", dtype=torch.int32).contiguous()
+    n, m = int(cm_t.shape[0]), int(cm_t.shape[1])
+    w_t = None
+    if weights is not None:
+        w_np = np.ascontiguousarray(weights, dtype=np.float64)
+        if w_np.shape != (m, n_states + 1):
+            raise ValueError(f"weights table must be [{m}, {n_states + 1}], got {w_np.shape}")
+        w_t = torch.from_numpy(w_np).cuda()
+    r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
+    ld = padded_ld(n)
+    tdtype = torch.float64 if dtype == "f64" else torch.float32
+    if out is None:
+        out = torch.empty((r1 - r0, ld), dtype=tdtype, device="cuda")
+        if ld != n:
+            out[:, n:].zero_()
+    else:
+        assert out.is_cuda and out.dtype == tdtype and out.shape[0] >= r1 - r0 and out.stride(0) == ld
+    code = _METHOD[method]
+    ws_bytes = int(L.cas_whd_workspace_bytes(n, m, int(n_states), 1 if w_t is not None else 0, code))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda")
+    rc = L.cas_whd_map(cm_t.data_ptr(), n, m, int(missing), w_t.data_ptr() if w_t is not None else None,
+                       int(n_states), out.data_ptr(), ld, CAS_F64 if dtype == "f64" else CAS_F32,
+                       r0, r1, code, ws.data_ptr(), ws_bytes, _stream_ptr(torch))
+    _lib.check(rc, "cas_whd_map")
+    if method == "exact":
+        # first int of the workspace: "state outside [0, n_states]" flag set by the encode kernel
+        flag = int(ws[:4].view(torch.int32).item())
+        if flag:
+            raise ValueError("character matrix holds a state outside [0, n_states] that is not the missing indicator")
+    else:
+        torch.cuda.current_stream().synchronize()
+    return out
+
+
+def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
+    """Runs the NJ / UPGMA loop on the device map D ([n, ld] CUDA tensor, destroyed).
+
+    Returns (joins [n-2, 2] int32 numpy in id space, last2 [2] int32 numpy).
+    """
+    torch = _torch()
+    L = _lib.load()
+    assert D.is_cuda and D.dim() == 2 and D.stride(1) == 1
+    ld = int(D.stride(0))
+    dtype = CAS_F64 if D.dtype == torch.float64 else CAS_F32
+    if D.dtype not in (torch.float64, torch.float32):
+        raise ValueError("map must be float32 or float64")
+    njoin = max(int(n) - 2, 0)
+    joins = torch.full((njoin + 1, 2), -1, dtype=torch.int32, device="cuda")
+    last2 = torch.full((2,), -1, dtype=torch.int32, device="cuda")
+    ws_bytes = int(L.cas_agglom_workspace_bytes(int(n), _ALGO[algo], _MODE[mode]))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    fn = L.cas_nj_solve if algo == "nj" else L.cas_upgma_solve
+    rc = fn(D.data_ptr(), int(n), ld, dtype, _MODE[mode], int(max_iters), joins.data_ptr(),
+            last2.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(torch))
+    _lib.check(rc, f"cas_{algo}_solve")
+    done = njoin if max_iters < 0 else min(njoin, int(max_iters))
+    joins_h = joins[:done].cpu().numpy()
+    last2_h = last2.cpu().numpy()
+    return joins_h, last2_h
+
+
+def solve_host(cm: np.ndarray, missing: int, weights: Optional[np.ndarray], n_states: int,
+               algo: str, mode: str, method: str = "exact"):
+    """End to end from HOST buffers through ``cas_solve_host`` (H2D/D2H inside the call).
+
+    Returns (joins, last2, timings_ms[h2d, map, loop, d2h]).
+    """
+    _torch()
+    L = _lib.load()
+    cm = np.ascontiguousarray(cm, dtype=np.int32)
+    n, m = cm.shape
+    w = None
+    if weights is not None:
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert w.shape == (m, n_states + 1)
+    joins = np.full((max(n - 2, 0) + 1, 2), -1, dtype=np.int32)
+    last2 = np.full(2, -1, dtype=np.int32)
+    tm = np.zeros(4, dtype=np.float64)
+    rc = L.cas_solve_host(cm.ctypes.data, n, m, int(missing), w.ctypes.data if w is not None else None,
+                          int(n_states), _ALGO[algo], _MODE[mode], _METHOD[method],
+                          joins.ctypes.data, last2.ctypes.data, tm.ctypes.data)
+    _lib.check(rc, "cas_solve_host")
+    return joins[: max(n - 2, 0)], last2, tm

@@ -1,0 +1,130 @@
+/*
+ * cas_b200.h -- C ABI of the B200-native distance-solver hot path.
+ *
+ * Drop-in boundary for YosefLab/Cassiopeia's DistanceSolver path.  Every entry
+ * point takes plain pointers and sizes (no torch / Python types) so it can be
+ * bound from ctypes (see INTEGRATION.md for the stub a Cassiopeia maintainer
+ * would add).  All `*_dev` pointers are device pointers owned by the caller
+ * (the Python host keeps them alive as torch tensors); `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Functions
+ * enqueue work asynchronously on `stream` unless they say otherwise, return 0
+ * on success and a negative code on failure; `cas_last_error()` then holds a
+ * human-readable message (thread-local).
+ *
+ * Reference interfaces replaced (paths relative to the Cassiopeia checkout):
+ *   cas_whd_map        <- cassiopeia/data/utilities.py:189-295 `compute_dissimilarity_map`
+ *                         with cassiopeia/solver/dissimilarity_functions.py:12-72
+ *                         `weighted_hamming_distance` (called from
+ *                         cassiopeia/data/CassiopeiaTree.py:1926)
+ *   cas_nj_solve       <- the `while N > 2` loop of cassiopeia/solver/DistanceSolver.py:185-205
+ *                         specialised by NeighborJoiningSolver.find_cherry / compute_q /
+ *                         update_dissimilarity_map (cassiopeia/solver/NeighborJoiningSolver.py:123-260)
+ *   cas_upgma_solve    <- same loop with UPGMASolver.find_cherry / update_dissimilarity_map
+ *                         (cassiopeia/solver/UPGMASolver.py:118-238)
+ *   cas_solve_host     <- DistanceSolver.solve's numeric part end to end
+ *                         (cassiopeia/solver/DistanceSolver.py:173-205) from HOST buffers
+ *   cas_sharded_*      <- no reference counterpart (the reference is single-host); row-block
+ *                         sharded variant of the two loops for n^2 maps larger than one GPU.
+ */
+#ifndef CAS_B200_H_
+#define CAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CAS_API __attribute__((visibility("default")))
+#else
+#define CAS_API
+#endif
+
+/* element type of the dissimilarity map */
+#define CAS_F32 0
+#define CAS_F64 1
+/* agglomeration rule */
+#define CAS_ALGO_NJ 0
+#define CAS_ALGO_UPGMA 1
+/* arithmetic mode of the loop:
+ *   STRICT: float64 map, NJ row sums re-accumulated every iteration sequentially in
+ *           id order, no FMA -- reproduces the reference join for join.
+ *   FAST  : float32 (or float64) map, NJ row sums maintained incrementally in float64. */
+#define CAS_MODE_STRICT 0
+#define CAS_MODE_FAST 1
+/* dissimilarity-map kernel:
+ *   EXACT : CUDA-core kernel, float64 accumulation in character order (bit-exact vs reference)
+ *   TENSOR: one-hot contraction on tcgen05 tensor cores (int8 unweighted / split-bf16 weighted) */
+#define CAS_MAP_EXACT 0
+#define CAS_MAP_TENSOR 1
+
+/* error codes */
+#define CAS_OK 0
+#define CAS_ERR_INVALID (-1)
+#define CAS_ERR_CUDA (-2)
+#define CAS_ERR_UNSUPPORTED (-3)
+#define CAS_ERR_WORKSPACE (-4)
+#define CAS_ERR_NCCL (-5)
+
+CAS_API int cas_abi_version(void);
+CAS_API const char *cas_last_error(void);
+
+/* sm_count, compute capability and free/total device memory of the current device */
+CAS_API int cas_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, size_t *free_bytes,
+                    size_t *total_bytes);
+
+/* ---- pairwise weighted-Hamming dissimilarity map -------------------------
+ * cm_dev   : [n, m] int32 character matrix, row-major.  States are
+ *            0 (uncut), 1..n_states (indels, compact codes) or `missing`.
+ * w_dev    : [m, n_states+1] float64 weights (w[c][0] ignored) or NULL for the
+ *            reference's unweighted costs (0/1/2).
+ * D_dev    : output, element (i, j) at D[(i-row0)*ld + j] for i in [row0,row1),
+ *            j in [0,n); dtype CAS_F32 / CAS_F64; diagonal 0.  When the block is
+ *            the whole matrix only lower-triangle tiles are computed and mirrored.
+ * workspace: cas_whd_workspace_bytes(...) bytes of device scratch.
+ */
+CAS_API size_t cas_whd_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted,
+                               int32_t method);
+CAS_API int cas_whd_map(const int32_t *cm_dev, int64_t n, int32_t m, int32_t missing, const double *w_dev,
+                int32_t n_states, void *D_dev, int64_t ld, int32_t dtype, int64_t row0,
+                int64_t row1, int32_t method, void *workspace_dev, size_t workspace_bytes,
+                void *stream);
+
+/* ---- agglomeration loops ---------------------------------------------------
+ * D_dev    : [n, ld] symmetric map (both triangles valid), destroyed.  ld % 32 == 0.
+ * joins_dev: [max(n-2,0), 2] int32 out; join t merges ids (lo, hi) into id n+t
+ *            (leaf at row p has id p).  Ties resolve to the lexicographically smallest
+ *            (value, id_lo, id_hi) == the reference's first row-major arg-min.
+ * last2_dev: [2] int32 out, ids of the two clusters left (ascending); only meaningful
+ *            when the loop ran to the end.
+ * max_iters: < 0 runs all n-2 joins; otherwise stops after that many (bounded samples,
+ *            single-step hooks, profiling).
+ */
+CAS_API size_t cas_agglom_workspace_bytes(int64_t n, int32_t algo, int32_t mode);
+CAS_API int cas_nj_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int32_t mode,
+                 int64_t max_iters, int32_t *joins_dev, int32_t *last2_dev, void *workspace_dev,
+                 size_t workspace_bytes, void *stream);
+CAS_API int cas_upgma_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int32_t mode,
+                    int64_t max_iters, int32_t *joins_dev, int32_t *last2_dev,
+                    void *workspace_dev, size_t workspace_bytes, void *stream);
+/* number of kernels the last cas_*_solve / cas_whd_map / cas_solve_host call on this
+ * thread launched (bench.py's gpu_launches) */
+CAS_API int64_t cas_last_launch_count(void);
+
+/* ---- end to end from HOST buffers (synchronous) ----------------------------
+ * Copies the character matrix (and weights) to the device, builds the map, runs the
+ * loop and copies the join list back.  timings_ms (optional, [4]) receives device
+ * times: h2d, map, loop, d2h. */
+CAS_API int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t missing,
+                   const double *w_host, int32_t n_states, int32_t algo, int32_t mode,
+                   int32_t map_method, int32_t *joins_host, int32_t *last2_host,
+                   double *timings_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAS_B200_H_ */
