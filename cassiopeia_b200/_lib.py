@@ -30,6 +30,8 @@ EXPORTS = (
     "cas_upgma_solve",
     "cas_last_launch_count",
     "cas_solve_host",
+    "cas_nj_q",
+    "cas_update_map",
 )
 
 
@@ -60,6 +62,10 @@ def _declare(L: ctypes.CDLL) -> None:
     for fn in (L.cas_nj_solve, L.cas_upgma_solve):
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, i64, i64, i32, i32, i64, vp, vp, vp, sz, vp]
+    L.cas_nj_q.restype = ctypes.c_int
+    L.cas_nj_q.argtypes = [vp, i64, i64, vp, vp, vp]
+    L.cas_update_map.restype = ctypes.c_int
+    L.cas_update_map.argtypes = [vp, i64, i64, i32, i64, i64, i64, i64, vp, i64, vp]
     L.cas_solve_host.restype = ctypes.c_int
     L.cas_solve_host.argtypes = [vp, i64, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]
 

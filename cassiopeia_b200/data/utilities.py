@@ -1,0 +1,64 @@
+"""GPU counterparts of cassiopeia/data/utilities.py on the hot path."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .. import engine, host_prep
+from ..mixins import DistanceSolverError
+from ..solver import dissimilarity_functions, solver_utilities
+
+
+def _require_gpu_function(dissimilarity_function: Optional[Callable]) -> None:
+    if dissimilarity_function is None or not dissimilarity_functions.is_gpu_kernel(dissimilarity_function):
+        raise DistanceSolverError(
+            "only `weighted_hamming_distance` is built as a CUDA kernel; for any other dissimilarity "
+            "function populate the tree with a precomputed dissimilarity map (there is no CPU fallback)"
+        )
+
+
+def device_map(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dict[int, float]]],
+               dtype: str = "f64", method: str = "exact"):
+    """[n, ld] CUDA tensor holding the full symmetric map of the int matrix `cm` (rows as given)."""
+    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing, weights)
+    return engine.whd_map(codes, missing_code, table, n_states, dtype=dtype, method=method)
+
+
+def compute_dissimilarity_map(cm: np.ndarray, C: int, dissimilarity_function: Callable,
+                              weights: Optional[Dict[int, Dict[int, float]]] = None,
+                              missing_state_indicator: int = -1, threads: int = 1) -> np.ndarray:
+    """Condensed float64 vector of the C*(C-1)/2 pairwise dissimilarities, row-major pair
+    order -- the contract of cassiopeia/data/utilities.py:189-295 (`threads` is ignored)."""
+    _require_gpu_function(dissimilarity_function)
+    cm = host_prep.as_int_matrix(cm)[:C]
+    if C < 2:
+        return np.zeros(0, dtype=np.float64)
+    D = device_map(cm, missing_state_indicator, weights, dtype="f64", method="exact")
+    full = D[:, :C].cpu().numpy()
+    iu = np.triu_indices(C, k=1)
+    return np.ascontiguousarray(full[iu])
+
+
+def dissimilarity_map_frame_inputs(character_matrix, priors, missing_state_indicator: int,
+                                   dissimilarity_function: Optional[Callable],
+                                   prior_transformation: str = "negative_log",
+                                   dtype: str = "f64", method: str = "exact",
+                                   to_host: bool = True) -> Tuple[List[str], object]:
+    """(row names in the reference's map order, full n x n map).
+
+    Restates cassiopeia/data/CassiopeiaTree.py:1914-1958: priors -> weights, the
+    de-duplication row order, the square map.  `to_host=False` keeps the map on the
+    device as an [n, ld] CUDA tensor (used by the solvers for large n)."""
+    _require_gpu_function(dissimilarity_function)
+    weights = None
+    if priors:
+        weights = solver_utilities.transform_priors(priors, prior_transformation)
+    cm = host_prep.as_int_matrix(character_matrix)
+    order = host_prep.reference_row_order(cm)
+    names = [character_matrix.index[i] for i in order.tolist()]
+    D = device_map(cm[order], missing_state_indicator, weights, dtype=dtype, method=method)
+    if to_host:
+        n = cm.shape[0]
+        return names, D[:, :n].cpu().numpy()
+    return names, D

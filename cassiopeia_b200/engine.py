@@ -147,3 +147,29 @@ def solve_host(cm: np.ndarray, missing: int, weights: Optional[np.ndarray], n_st
                           joins.ctypes.data, last2.ctypes.data, tm.ctypes.data)
     _lib.check(rc, "cas_solve_host")
     return joins[: max(n - 2, 0)], last2, tm
+
+
+def nj_q(D: np.ndarray) -> np.ndarray:
+    """Q-criterion matrix of a float64 [n, n] map (single-step hook, ``cas_nj_q``)."""
+    torch = _torch()
+    L = _lib.load()
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    n = D.shape[0]
+    d = torch.from_numpy(D).cuda()
+    q = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    rs = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(L.cas_nj_q(d.data_ptr(), n, n, q.data_ptr(), rs.data_ptr(), _stream_ptr(torch)), "cas_nj_q")
+    return q.cpu().numpy()
+
+
+def update_map(D: np.ndarray, i: int, j: int, algo: str, size_i: int = 1, size_j: int = 1) -> np.ndarray:
+    """(n-1) x (n-1) map after joining rows i and j (single-step hook, ``cas_update_map``)."""
+    torch = _torch()
+    L = _lib.load()
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    n = D.shape[0]
+    d = torch.from_numpy(D).cuda()
+    out = torch.empty((n - 1, n - 1), dtype=torch.float64, device="cuda")
+    _lib.check(L.cas_update_map(d.data_ptr(), n, n, _ALGO[algo], int(i), int(j), int(size_i), int(size_j),
+                                out.data_ptr(), n - 1, _stream_ptr(torch)), "cas_update_map")
+    return out.cpu().numpy()

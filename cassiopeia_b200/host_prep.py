@@ -1,0 +1,124 @@
+"""Host-side preparation of the dissimilarity-map inputs (numpy, O(n*m)).
+
+* ``reference_row_order``: the row order of the reference's map
+  (cassiopeia/data/CassiopeiaTree.py:1920-1951): unique rows in first-appearance order,
+  then, for every unique row in that order, its duplicates in original order.  Computing
+  the full map on the permuted matrix equals the reference's dedup-then-expand result
+  (duplicates are at distance 0 from each other and share all other distances).
+* ``compact_states``: remaps arbitrary integer state labels to the compact codes the
+  kernels take (0 = uncut, 1..n_states, missing indicator untouched) and builds the dense
+  ``[m, n_states+1]`` float64 weight table.  Equality of states is preserved, so
+  distances are unchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from .mixins import DistanceSolverError
+
+DIRECT_STATE_LIMIT = 4094  # raw labels in [0, limit] are used as codes without remapping
+
+
+def as_int_matrix(character_matrix) -> np.ndarray:
+    """DataFrame / ndarray -> contiguous int64 ndarray; ambiguous (object) states are rejected."""
+    arr = character_matrix.to_numpy() if hasattr(character_matrix, "to_numpy") else np.asarray(character_matrix)
+    if arr.dtype == object:
+        try:
+            arr = arr.astype(np.int64)
+        except (TypeError, ValueError) as e:
+            raise DistanceSolverError(
+                "ambiguous (tuple) character states are not supported by the B200 kernels"
+            ) from e
+    if not np.issubdtype(arr.dtype, np.integer):
+        if np.issubdtype(arr.dtype, np.floating) and np.all(np.isfinite(arr)) and np.all(arr == np.round(arr)):
+            arr = arr.astype(np.int64)
+        else:
+            raise DistanceSolverError("character matrix must hold integer states")
+    return np.ascontiguousarray(arr, dtype=np.int64)
+
+
+def reference_row_order(cm: np.ndarray) -> np.ndarray:
+    cm = np.ascontiguousarray(cm)
+    n = cm.shape[0]
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    if cm.shape[1] == 0:
+        first = np.zeros(n, dtype=np.int64)
+    else:
+        rows = cm.view(np.dtype((np.void, cm.dtype.itemsize * cm.shape[1]))).ravel()
+        _, first_idx, inverse = np.unique(rows, return_index=True, return_inverse=True)
+        first = first_idx[inverse.ravel()]  # first occurrence of each row's content
+    idx = np.arange(n, dtype=np.int64)
+    is_first = first == idx
+    uniq = idx[is_first]
+    dups = idx[~is_first]
+    # duplicates grouped by their unique row's first index (== unique-row order), then by own index
+    dups = dups[np.lexsort((dups, first[dups]))]
+    return np.concatenate([uniq, dups])
+
+
+def compact_states(cm: np.ndarray, missing: int,
+                   weights: Optional[Dict[int, Dict[int, float]]]) -> Tuple[np.ndarray, int, Optional[np.ndarray], int]:
+    """Returns (codes int32 [n, m], missing_code, weight_table or None, n_states).
+
+    Raises KeyError where the reference's numba dict lookup would: a weighted character
+    that shows at least two distinct present states must have a weight for each of its
+    non-zero states (a state is only looked up when it takes part in a mismatch,
+    dissimilarity_functions.py:56-69).
+    """
+    n, m = cm.shape
+    present = cm != missing
+    weighted = bool(weights)
+    vals = cm[present]
+    smin = int(vals.min()) if vals.size else 0
+    smax = int(vals.max()) if vals.size else 0
+    direct = smin >= 0 and smax <= DIRECT_STATE_LIMIT
+    if direct:
+        codes = cm.astype(np.int32)
+        n_states = max(smax, 1)
+        missing_code = int(missing)
+        if 0 <= missing_code <= n_states:
+            # the indicator collides with the code range: move it out of the way
+            missing_code = -1
+            codes = np.where(present, codes, -1).astype(np.int32)
+        elif not (-(2**31) <= missing_code < 2**31):
+            missing_code = -1
+            codes = np.where(present, codes, -1).astype(np.int32)
+        label_of = None
+    else:
+        codes = np.full((n, m), -1, dtype=np.int32)
+        missing_code = -1
+        label_of = []
+        n_states = 1
+        for c in range(m):
+            col = cm[:, c]
+            pres = present[:, c]
+            labels = np.unique(col[pres])
+            nz = labels[labels != 0]
+            lut_keys = np.concatenate([[0], nz])
+            code = np.searchsorted(nz, col[pres]) + 1
+            code = np.where(col[pres] == 0, 0, code)
+            codes[pres, c] = code
+            label_of.append(lut_keys)
+            n_states = max(n_states, len(nz))
+    table = None
+    if weighted:
+        table = np.zeros((m, n_states + 1), dtype=np.float64)
+        for c in range(m):
+            col = codes[:, c]
+            seen = np.unique(col[col != missing_code])
+            if seen.size < 2:
+                continue  # no mismatch possible at this character: never looked up
+            if c not in weights:
+                raise KeyError(c)
+            wc = weights[c]
+            for code in seen.tolist():
+                if code == 0:
+                    continue
+                label = code if label_of is None else int(label_of[c][code])
+                if label not in wc:
+                    raise KeyError(label)
+                table[c, code] = wc[label]
+    return np.ascontiguousarray(codes), missing_code, table, int(n_states)

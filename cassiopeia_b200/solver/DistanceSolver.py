@@ -1,0 +1,211 @@
+"""B200 distance-solver driver: same API and tree output as the reference's
+``DistanceSolver`` (cassiopeia/solver/DistanceSolver.py:29-463), numeric work on the GPU.
+
+``solve`` follows reference :127-231 step for step -- root handling and error cases of
+``setup_dissimilarity_map`` (:351-395), the join loop (:185-205), ``root_tree``, dropping
+the root row (:214-222), ``populate_tree`` / ``collapse_unifurcations`` /
+``collapse_mutationless_edges`` (:224-231) -- except that the dissimilarity map is built
+by the CUDA map kernel and the whole ``while N > 2`` loop runs in ``cas_nj_solve`` /
+``cas_upgma_solve``.  The join list comes back in id space and is replayed through the
+same graph-building calls the reference makes, in the same order, so child order and
+rooting match.
+
+Deviations (documented in DESIGN.md): the n x n map is stored on the tree as a DataFrame
+only when n <= ``materialize_limit`` (the reference always stores it, CassiopeiaTree.py:1958);
+asymmetric user-supplied maps and dissimilarity functions other than
+``weighted_hamming_distance`` without a precomputed map raise ``DistanceSolverError``
+(no CPU fallback).
+"""
+from __future__ import annotations
+
+import abc
+from typing import Callable, List, Optional, Tuple
+
+import networkx as nx
+import numpy as np
+import pandas as pd
+
+from .. import engine, host_prep
+from ..data import utilities as data_utilities
+from ..mixins import DistanceSolverError
+from . import dissimilarity_functions, solver_utilities
+
+B200_IMPLEMENTATIONS = ("b200_strict", "b200_fast")
+
+
+class DistanceSolver(abc.ABC):
+    #: store the map on the tree (pandas) only up to this many samples
+    materialize_limit = 8192
+    _algo = None  # "nj" | "upgma"
+
+    def __init__(self, dissimilarity_function: Optional[Callable] = dissimilarity_functions.weighted_hamming_distance,
+                 add_root: bool = False, prior_transformation: str = "negative_log", threads: int = 1):
+        if not hasattr(self, "_implementation"):
+            self._implementation = "b200_strict"
+        self.prior_transformation = prior_transformation
+        self.dissimilarity_function = dissimilarity_function
+        self.add_root = add_root
+        self.threads = threads
+        self._pending_device_map = None
+        self.last_join_list = None  # (joins, last2, names) of the most recent solve
+
+    # ----------------------------------------------------------- configuration
+    @property
+    def precision(self) -> str:
+        return "fast" if self._implementation == "b200_fast" else "strict"
+
+    @property
+    def _map_dtype(self) -> str:
+        return "f32" if self.precision == "fast" else "f64"
+
+    @property
+    def _map_method(self) -> str:
+        return getattr(self, "map_method", "exact")
+
+    # ------------------------------------------------------------ map handling
+    def _compute_device_map(self, cassiopeia_tree, character_matrix: pd.DataFrame):
+        """Map of `character_matrix` on the device, in the reference's row order; also stored
+        on the tree as a float64 DataFrame when small enough."""
+        n = character_matrix.shape[0]
+        names, D = data_utilities.dissimilarity_map_frame_inputs(
+            character_matrix, cassiopeia_tree.priors, cassiopeia_tree.missing_state_indicator,
+            self.dissimilarity_function, self.prior_transformation,
+            dtype=self._map_dtype, method=self._map_method, to_host=False)
+        if n <= self.materialize_limit:
+            if self._map_dtype == "f64":
+                host = D[:, :n].cpu().numpy()
+            else:
+                # the stored frame is float64 like the reference's; recompute exactly
+                _, host = data_utilities.dissimilarity_map_frame_inputs(
+                    character_matrix, cassiopeia_tree.priors, cassiopeia_tree.missing_state_indicator,
+                    self.dissimilarity_function, self.prior_transformation, dtype="f64", method="exact")
+            cassiopeia_tree.set_dissimilarity_map(pd.DataFrame(host, index=names, columns=names))
+        return names, D
+
+    def _upload_map(self, dissimilarity_map: pd.DataFrame):
+        import torch
+
+        names = list(dissimilarity_map.index)
+        arr = dissimilarity_map.to_numpy(dtype=np.float64)
+        n = arr.shape[0]
+        if arr.shape != (n, n):
+            raise DistanceSolverError("dissimilarity map must be square")
+        if not np.array_equal(arr, arr.T):
+            raise DistanceSolverError("the B200 solvers need a symmetric dissimilarity map")
+        ld = engine.padded_ld(n)
+        host = np.zeros((n, ld), dtype=np.float64 if self._map_dtype == "f64" else np.float32)
+        host[:, :n] = arr
+        return names, torch.from_numpy(host).cuda()
+
+    def setup_dissimilarity_map(self, cassiopeia_tree, layer: Optional[str] = None) -> None:
+        """Reference :351-395: implicit root, error cases, map creation if absent."""
+        self._pending_device_map = None
+        if cassiopeia_tree.root_sample_name is None:
+            if self.add_root:
+                self.setup_root_finder(cassiopeia_tree)
+            else:
+                raise DistanceSolverError(
+                    "Please specify an explicit root sample in the Cassiopeia Tree or specify the "
+                    "solver to add an implicit root")
+        if self._pending_device_map is None and cassiopeia_tree.get_dissimilarity_map() is None:
+            if self.dissimilarity_function is None:
+                raise DistanceSolverError(
+                    "Please specify a dissimilarity function or populate the CassiopeiaTree object "
+                    "with a dissimilarity map")
+            character_matrix = (cassiopeia_tree.layers[layer] if layer is not None
+                                else cassiopeia_tree.character_matrix)
+            self._pending_device_map = self._compute_device_map(cassiopeia_tree, character_matrix)
+
+    def get_dissimilarity_map(self, cassiopeia_tree, layer: Optional[str] = None) -> pd.DataFrame:
+        """Reference :94-125 (host frame; `solve` itself keeps the map on the device)."""
+        self.setup_dissimilarity_map(cassiopeia_tree, layer)
+        stored = cassiopeia_tree.get_dissimilarity_map()
+        if stored is None and self._pending_device_map is not None:
+            names, D = self._pending_device_map
+            n = len(names)
+            stored = pd.DataFrame(D[:, :n].double().cpu().numpy(), index=names, columns=names)
+        return stored
+
+    def _device_map(self, cassiopeia_tree, layer: Optional[str]) -> Tuple[List[str], object]:
+        self.setup_dissimilarity_map(cassiopeia_tree, layer)
+        if self._pending_device_map is not None:
+            pending, self._pending_device_map = self._pending_device_map, None
+            return pending
+        return self._upload_map(cassiopeia_tree.get_dissimilarity_map())
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, cassiopeia_tree, layer: Optional[str] = None, collapse_mutationless_edges: bool = False,
+              logfile: str = "stdout.log") -> None:
+        names, D = self._device_map(cassiopeia_tree, layer)
+        n = len(names)
+        joins, last2 = engine.agglomerate(D, n, self._algo, self.precision)
+        del D
+        self.last_join_list = (joins, last2, names)
+        self.finish_tree(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges)
+
+    def finish_tree(self, cassiopeia_tree, names: List[str], joins: np.ndarray, last2: np.ndarray,
+                    layer: Optional[str] = None, collapse_mutationless_edges: bool = False) -> None:
+        """Host tail of `solve`: replays an id-space join list (leaf at map row p has id p, the
+        t-th join creates id n+t) through the reference's graph-building sequence (:181-199),
+        roots the tree and populates `cassiopeia_tree` (:207-231)."""
+        node_name_generator = solver_utilities.node_name_generator()
+        n = len(names)
+        tree = nx.Graph()
+        tree.add_nodes_from(names)
+        label = list(names)
+        for a, b in np.asarray(joins).tolist():
+            new_node_name = next(node_name_generator)
+            label.append(new_node_name)
+            tree.add_node(new_node_name)
+            tree.add_edges_from([(new_node_name, label[a]), (new_node_name, label[b])])
+        if n >= 2:
+            remaining = [label[int(last2[0])], label[int(last2[1])]]
+        else:
+            remaining = list(names)
+
+        tree = self.root_tree(tree, cassiopeia_tree.root_sample_name, remaining)
+
+        # remove root from character matrix before populating tree (:214-222)
+        if cassiopeia_tree.root_sample_name in cassiopeia_tree.character_matrix.index:
+            cassiopeia_tree.character_matrix = cassiopeia_tree.character_matrix.drop(
+                index=cassiopeia_tree.root_sample_name)
+
+        cassiopeia_tree.populate_tree(tree, layer=layer)
+        cassiopeia_tree.collapse_unifurcations()
+        if collapse_mutationless_edges:
+            cassiopeia_tree.collapse_mutationless_edges(infer_ancestral_characters=True)
+
+    # ------------------------------------------------------- reference hooks
+    @abc.abstractmethod
+    def root_tree(self, tree: nx.Graph, root_sample: str, remaining_samples: List[str]) -> nx.DiGraph:
+        ...
+
+    @abc.abstractmethod
+    def setup_root_finder(self, cassiopeia_tree) -> None:
+        ...
+
+    def find_cherry(self, dissimilarity_map: np.ndarray) -> Tuple[int, int]:
+        """Positions (i < j) of the pair the rule joins first (one scan on the GPU)."""
+        import torch
+
+        arr = np.asarray(dissimilarity_map, dtype=np.float64)
+        n = arr.shape[0]
+        ld = engine.padded_ld(n)
+        host = np.zeros((n, ld), dtype=np.float64)
+        host[:, :n] = arr
+        joins, _ = engine.agglomerate(torch.from_numpy(host).cuda(), n, self._algo, "strict", max_iters=1)
+        return int(joins[0, 0]), int(joins[0, 1])
+
+    def update_dissimilarity_map(self, dissimilarity_map: pd.DataFrame, cherry: Tuple[str, str],
+                                 new_node: str) -> pd.DataFrame:
+        """Map after joining `cherry` into `new_node`: the two rows/columns are dropped and the
+        new node appended last (reference NeighborJoiningSolver.py:173-216 / UPGMASolver.py:140-193)."""
+        index = list(dissimilarity_map.index)
+        i, j = index.index(cherry[0]), index.index(cherry[1])
+        size_i, size_j = self._cluster_sizes(cherry, new_node)
+        arr = engine.update_map(dissimilarity_map.to_numpy(dtype=np.float64), i, j, self._algo, size_i, size_j)
+        names = [nm for p, nm in enumerate(index) if p != i and p != j] + [new_node]
+        return pd.DataFrame(arr, index=names, columns=names)
+
+    def _cluster_sizes(self, cherry, new_node) -> Tuple[int, int]:
+        return 1, 1

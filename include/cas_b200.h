@@ -111,6 +111,17 @@ CAS_API int cas_nj_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int3
 CAS_API int cas_upgma_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int32_t mode,
                     int64_t max_iters, int32_t *joins_dev, int32_t *last2_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);
+/* ---- single-step hooks (float64, reference operation order) -----------------
+ * cas_nj_q       : Q[n,n] (zero diagonal) of NeighborJoiningSolver.compute_q
+ *                  (cassiopeia/solver/NeighborJoiningSolver.py:142-171); rowsum_scratch = n doubles.
+ * cas_update_map : the (n-1)x(n-1) map after joining rows i and j -- the two rows/columns are
+ *                  dropped and the merged node appended last
+ *                  (NeighborJoiningSolver.py:218-260 / UPGMASolver.py:195-238). */
+CAS_API int cas_nj_q(const double *D_dev, int64_t n, int64_t ld, double *Q_dev, double *rowsum_scratch_dev,
+             void *stream);
+CAS_API int cas_update_map(const double *D_dev, int64_t n, int64_t ld, int32_t algo, int64_t i, int64_t j,
+                   int64_t size_i, int64_t size_j, double *out_dev, int64_t ld_out, void *stream);
+
 /* number of kernels the last cas_*_solve / cas_whd_map / cas_solve_host call on this
  * thread launched (bench.py's gpu_launches) */
 CAS_API int64_t cas_last_launch_count(void);
