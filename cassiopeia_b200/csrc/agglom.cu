@@ -98,6 +98,7 @@ struct ScanArgs {
   const int32_t *ids;
   const int32_t *sizes;
   double tinv;  // 1/(k-2)
+  const unsigned long long *rmax_bits;  // bits of max |row sum| seen so far (NJ screening bound)
   Cand *cand;
   unsigned *counter;
   Sel *sel;
@@ -105,18 +106,32 @@ struct ScanArgs {
   int t;  // iteration index
 };
 
+// Screening arithmetic.  The exact criterion of a pair is the reference's float64 expression
+//   q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) )          (NJ)        q = d_ij  (UPGMA)
+// Evaluating it for every element costs ~30 instructions per element and makes the scan
+// issue-bound (ncu, profiles/r1_scan_before.md).  Instead each element is screened in
+// float32: qf = fl32(d) - fl32(u_j) with u_j = (1/(k-2)) * rs_j staged in shared memory, against
+// a per-row threshold thr >= (best + u_i) + E, where E = 2^-20 * (max|u| + |best + u_i|)
+// bounds every rounding of the screen (proof in DESIGN.md "scan screening").  Only elements
+// that pass are re-evaluated with the exact float64 expression and the lexicographic
+// (value, id_lo, id_hi) rule, so the selected pair is identical to evaluating everything
+// exactly.
+__device__ __forceinline__ float screen_value(float d) { return d; }
+__device__ __forceinline__ float screen_value(double d) { return __double2float_rd(d); }
+
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;                  // independent 128-bit loads in flight per lane
   constexpr int STEP = 32 * V;          // elements per warp-wide load
-  __shared__ __align__(16) double sR[NJ ? TC : 2];
+  __shared__ __align__(16) float sU[NJ ? TC : 4];
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
 
   const T *__restrict__ D = static_cast<const T *>(a.D);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
+  const double umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
   double bq = INFINITY;
   int bi = -1, bj = -1;
   int staged_cb = -1;
@@ -135,8 +150,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
     const int c0 = cb * TC;
     const int c1 = min(c0 + TC, k);
     if (NJ && cb != staged_cb) {
-      __syncthreads();  // previous tile's readers are done with sR
-      for (int x = threadIdx.x; x < c1 - c0; x += SCAN_THREADS) sR[x] = a.R[c0 + x];
+      __syncthreads();  // previous tile's readers are done with sU
+      for (int x = threadIdx.x; x < TC; x += SCAN_THREADS)
+        sU[x] = (c0 + x < c1) ? __double2float_rn(__dmul_rn(a.tinv, a.R[c0 + x])) : 0.f;
       staged_cb = cb;
       __syncthreads();
     }
@@ -147,6 +163,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
       if (jend <= c0) continue;
       const T *__restrict__ row = D + (int64_t)i * a.ld;
       const double Ri = NJ ? a.R[i] : 0.0;
+      const double ui = NJ ? __dmul_rn(a.tinv, Ri) : 0.0;
+      // screening threshold of this row for the thread's current best
+      auto threshold = [&]() -> float {
+        if (bi < 0) return INFINITY;
+        if (!NJ) return __double2float_ru(bq);
+        const double B = bq + ui;
+        return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + 1e-300);
+      };
+      float thr = threshold();
       for (int jb = c0; jb < jend; jb += STEP * U) {
         T v[U][V];
         const bool whole = (jb + STEP * U <= jend);
@@ -157,21 +182,46 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int j = jb + u * STEP + lane * V;
-            if (j < jend) ld_stream(row + j, v[u]);
+            if (j < jend) {
+              ld_stream(row + j, v[u]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < V; ++e) v[u][e] = (T)INFINITY;
+            }
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = jb + u * STEP + lane * V;
+          float qf[V];
+          if (NJ) {
+            float su[V];
+            if (V == 4) *reinterpret_cast<float4 *>(su) = *reinterpret_cast<const float4 *>(&sU[j - c0]);
+            else *reinterpret_cast<float2 *>(su) = *reinterpret_cast<const float2 *>(&sU[j - c0]);
 #pragma unroll
-          for (int e = 0; e < V; ++e) {
-            if (whole || (j + e < jend)) {
-              double q = (double)v[u][e];
-              if (NJ) {
-                // q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) ), no FMA  (NeighborJoiningSolver.py:163-170)
-                q = __dsub_rn(q, __dmul_rn(a.tinv, __dadd_rn(Ri, sR[j + e - c0])));
+            for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(screen_value(v[u][e]), su[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) qf[e] = screen_value(v[u][e]);
+          }
+          float m = qf[0];
+#pragma unroll
+          for (int e = 1; e < V; ++e) m = fminf(m, qf[e]);
+          if (m <= thr) {
+            // rare: exact float64 evaluation of the elements that passed the screen
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              if (qf[e] <= thr && (whole || j + e < jend)) {
+                double q = (double)v[u][e];
+                if (NJ) {
+                  // q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) ), no FMA  (NeighborJoiningSolver.py:163-170)
+                  q = __dsub_rn(q, __dmul_rn(a.tinv, __dadd_rn(Ri, a.R[j + e])));
+                }
+                if (q <= bq || bi < 0) {
+                  tie_path(q, i, j + e, bq, bi, bj, a.ids);
+                  thr = threshold();
+                }
               }
-              if (q <= bq) tie_path(q, i, j + e, bq, bi, bj, a.ids);
             }
           }
         }
@@ -243,6 +293,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   }
 }
 
+// running maximum of |row sum| (non-negative doubles order like their bit patterns)
+__device__ __forceinline__ void warp_atomic_absmax(unsigned long long *dst, double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
+    b = o > b ? o : b;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(dst, b);
+}
+
 struct MergeArgs {
   void *D;
   int64_t ld;
@@ -255,6 +316,7 @@ struct MergeArgs {
   unsigned *counter;
   int new_id;
   int maintain_R;     // fast NJ
+  unsigned long long *rmax_bits;
   // strict NJ: live slots in id order, double buffered
   const int32_t *order_old; const int32_t *pos_old;
   int32_t *order_new; int32_t *pos_new;
@@ -337,6 +399,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
   }
 
   if (!a.maintain_R) return;
+  {
+    // keep the screening bound max|row sum| current (all lanes participate)
+    double mine = 0.0;
+    if (v < k && v != lo && v != hi) mine = (v == last && hi != last) ? a.R[hi] : a.R[v];
+    warp_atomic_absmax(a.rmax_bits, mine);
+  }
   // deterministic sum of the new row: fixed 256-wide chunks, shuffle tree, then sequential
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
@@ -356,6 +424,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     double sum = 0.0;
     for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
     a.R[lo] = sum;
+    atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
   }
 }
 
@@ -363,26 +432,30 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(64) rowsum_seq_kernel(const T *__restrict__ D, int64_t ld, int k,
                                                         const int32_t *__restrict__ order,
-                                                        double *__restrict__ R) {
+                                                        double *__restrict__ R,
+                                                        unsigned long long *rmax_bits) {
   const int c = blockIdx.x * 64 + threadIdx.x;
-  if (c >= k) return;
   double s = 0.0;
-  int p = 0;
-  for (; p + 8 <= k; p += 8) {
-    double x[8];
+  if (c < k) {
+    int p = 0;
+    for (; p + 8 <= k; p += 8) {
+      double x[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = (double)D[(int64_t)order[p + u] * ld + c];
+      for (int u = 0; u < 8; ++u) x[u] = (double)D[(int64_t)order[p + u] * ld + c];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s = __dadd_rn(s, x[u]);
+      for (int u = 0; u < 8; ++u) s = __dadd_rn(s, x[u]);
+    }
+    for (; p < k; ++p) s = __dadd_rn(s, (double)D[(int64_t)order[p] * ld + c]);
+    R[c] = s;
   }
-  for (; p < k; ++p) s = __dadd_rn(s, (double)D[(int64_t)order[p] * ld + c]);
-  R[c] = s;
+  warp_atomic_absmax(rmax_bits, s);
 }
 
 // fast NJ: initial row sums, one warp per row, fixed lane-strided order + shuffle tree
 template <typename T>
 __global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ D, int64_t ld, int k,
-                                                          double *__restrict__ R) {
+                                                          double *__restrict__ R,
+                                                          unsigned long long *rmax_bits) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= k) return;
@@ -391,11 +464,14 @@ __global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ 
   for (int j = lane; j < k; j += 32) s = __dadd_rn(s, (double)r[j]);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
-  if (lane == 0) R[row] = s;
+  if (lane == 0) {
+    R[row] = s;
+    atomicMax(rmax_bits, (unsigned long long)__double_as_longlong(fabs(s)));
+  }
 }
 
 __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *order, int32_t *pos,
-                                  unsigned *counters) {
+                                  unsigned *counters, unsigned long long *rmax_bits) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < n) {
     ids[v] = v;
@@ -403,6 +479,7 @@ __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *
     if (order) { order[v] = v; pos[v] = v; }
   }
   if (v < 8) counters[v] = 0;
+  if (v == 0) *rmax_bits = 0ull;
 }
 
 __global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2) {
@@ -427,6 +504,7 @@ struct AgglomWorkspace {
   Sel *sel;
   double *partial;
   unsigned *counters;
+  unsigned long long *rmax_bits;
   size_t bytes;
 };
 
@@ -444,6 +522,7 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.sel = c.take<Sel>(4);
   w.partial = c.take<double>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
   w.counters = c.take<unsigned>(64);
+  w.rmax_bits = c.take<unsigned long long>(8);
   w.bytes = c.used();
   return w;
 }
@@ -481,11 +560,12 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     if (blocks == 0) blocks = 1;
     init_state_kernel<<<blocks, 256, 0, stream>>>((int)n, w.ids, NJ ? nullptr : w.sizes,
                                                   strict_nj ? w.order[0] : nullptr,
-                                                  strict_nj ? w.pos[0] : nullptr, w.counters);
+                                                  strict_nj ? w.pos[0] : nullptr, w.counters,
+                                                  w.rmax_bits);
     CAS_LAUNCH_CHECK();
   }
   if (fast_nj && n > 2) {
-    rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>((const T *)D, ld, (int)n, w.R);
+    rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>((const T *)D, ld, (int)n, w.R, w.rmax_bits);
     CAS_LAUNCH_CHECK();
   }
   int64_t k_final = n;
@@ -496,7 +576,8 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     const int cur = (int)(t & 1);
     if (strict_nj) {
       rowsum_seq_kernel<T><<<(unsigned)((k + 63) / 64), 64, 0, stream>>>((const T *)D, ld, k,
-                                                                          w.order[cur], w.R);
+                                                                          w.order[cur], w.R,
+                                                                          w.rmax_bits);
       CAS_LAUNCH_CHECK();
     }
     ScanArgs sa;
@@ -504,6 +585,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     plan_scan(k, target_ctas, sa.tr, sa.nrb, sa.ncb, sa.ntiles);
     sa.R = w.R; sa.ids = w.ids; sa.sizes = NJ ? nullptr : w.sizes;
     sa.tinv = 1.0 / (double)(k - 2);
+    sa.rmax_bits = w.rmax_bits;
     sa.cand = w.cand; sa.counter = w.counters + 0; sa.sel = w.sel; sa.joins = joins; sa.t = (int)t;
     int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
     if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
@@ -514,7 +596,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     MergeArgs ma;
     ma.D = D; ma.ld = ld; ma.k = k; ma.sel = w.sel; ma.R = w.R; ma.ids = w.ids;
     ma.sizes = NJ ? nullptr : w.sizes; ma.partial = w.partial; ma.counter = w.counters + 1;
-    ma.new_id = (int)(n + t); ma.maintain_R = fast_nj ? 1 : 0;
+    ma.new_id = (int)(n + t); ma.maintain_R = fast_nj ? 1 : 0; ma.rmax_bits = w.rmax_bits;
     ma.order_old = strict_nj ? w.order[cur] : nullptr;
     ma.pos_old = strict_nj ? w.pos[cur] : nullptr;
     ma.order_new = strict_nj ? w.order[cur ^ 1] : nullptr;
