@@ -32,6 +32,15 @@ EXPORTS = (
     "cas_solve_host",
     "cas_nj_q",
     "cas_update_map",
+    "cas_sharded_local_rows",
+    "cas_sharded_local_capacity",
+    "cas_sharded_workspace_bytes",
+    "cas_whd_map_cyclic",
+    "cas_nccl_unique_id",
+    "cas_nccl_comm_create",
+    "cas_nccl_comm_destroy",
+    "cas_sharded_solve",
+    "cas_sharded_solve_emulated",
 )
 
 
@@ -66,6 +75,24 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_nj_q.argtypes = [vp, i64, i64, vp, vp, vp]
     L.cas_update_map.restype = ctypes.c_int
     L.cas_update_map.argtypes = [vp, i64, i64, i32, i64, i64, i64, i64, vp, i64, vp]
+    L.cas_sharded_local_rows.restype = i64
+    L.cas_sharded_local_rows.argtypes = [i64, i32, i32]
+    L.cas_sharded_local_capacity.restype = i64
+    L.cas_sharded_local_capacity.argtypes = [i64, i32]
+    L.cas_sharded_workspace_bytes.restype = sz
+    L.cas_sharded_workspace_bytes.argtypes = [i64, i32, i32]
+    L.cas_whd_map_cyclic.restype = ctypes.c_int
+    L.cas_whd_map_cyclic.argtypes = [vp, i64, i32, i32, vp, i32, vp, i64, i32, i32, i32, i32, vp, sz, vp]
+    L.cas_nccl_unique_id.restype = ctypes.c_int
+    L.cas_nccl_unique_id.argtypes = [vp]
+    L.cas_nccl_comm_create.restype = ctypes.c_int
+    L.cas_nccl_comm_create.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
+    L.cas_nccl_comm_destroy.restype = ctypes.c_int
+    L.cas_nccl_comm_destroy.argtypes = [vp]
+    L.cas_sharded_solve.restype = ctypes.c_int
+    L.cas_sharded_solve.argtypes = [vp, i64, i64, i32, i32, i64, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.cas_sharded_solve_emulated.restype = ctypes.c_int
+    L.cas_sharded_solve_emulated.argtypes = [vp, i64, i64, i32, i32, i64, i32, vp, vp, vp, sz, vp]
     L.cas_solve_host.restype = ctypes.c_int
     L.cas_solve_host.argtypes = [vp, i64, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]
 

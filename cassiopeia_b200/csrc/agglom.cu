@@ -25,66 +25,9 @@
 //   merge                  : new row/column, swap compaction, id/size/row-sum maintenance.
 // HBM roofline: the scan reads every live unordered pair once, E*k(k-1)/2 bytes
 // (E = 4 fast, 8 strict); merge touches O(k) elements.
-#include <math.h>
-
-#include "common.cuh"
+#include "agglom_common.cuh"
 
 namespace cas {
-
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_WARPS = SCAN_THREADS / 32;
-constexpr int TC = 2048;  // columns per tile (R_j block staged in shared memory: 16 KB)
-constexpr int MERGE_THREADS = 256;
-constexpr int MAX_SCAN_CTAS = 2048;
-
-struct Cand {
-  double q;
-  unsigned long long key;  // (id_lo << 32) | id_hi ; ~0 = empty
-  int si, sj;              // slots, si > sj (row, column of the lower triangle)
-};
-
-struct Sel {
-  int lo, hi;       // slots, lo < hi
-  int size_lo, size_hi;
-  double dij;
-  int id_lo, id_hi;
-};
-
-template <typename T> struct VecOf;
-template <> struct VecOf<float> { static constexpr int N = 4; };
-template <> struct VecOf<double> { static constexpr int N = 2; };
-
-__device__ __forceinline__ void ld_stream(const float *p, float (&v)[4]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
-}
-__device__ __forceinline__ void ld_stream(const double *p, double (&v)[2]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-               : "=d"(v[0]), "=d"(v[1]) : "l"(p));
-}
-
-__device__ __forceinline__ unsigned long long make_key(int ida, int idb) {
-  unsigned lo = (unsigned)min(ida, idb), hi = (unsigned)max(ida, idb);
-  return ((unsigned long long)lo << 32) | hi;
-}
-
-// rare path: candidate ties (or beats) the thread's running best
-__device__ __forceinline__ void tie_path(double q, int i, int j, double &bq, int &bi, int &bj,
-                                         const int32_t *__restrict__ ids) {
-  if (q < bq || bi < 0) {
-    bq = q; bi = i; bj = j;
-    return;
-  }
-  unsigned long long kn = make_key(ids[i], ids[j]);
-  unsigned long long ko = make_key(ids[bi], ids[bj]);
-  if (kn < ko) { bi = i; bj = j; }
-}
-
-__device__ __forceinline__ bool cand_better(double qa, unsigned long long ka, double qb,
-                                            unsigned long long kb) {
-  // empty candidates carry key ~0 and q = +inf
-  return (qa < qb) || (qa == qb && ka < kb);
-}
 
 struct ScanArgs {
   const void *D;
@@ -106,24 +49,8 @@ struct ScanArgs {
   int t;  // iteration index
 };
 
-// Screening arithmetic.  The exact criterion of a pair is the reference's float64 expression
-//   q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) )          (NJ)        q = d_ij  (UPGMA)
-// Evaluating it for every element costs ~30 instructions per element and makes the scan
-// issue-bound (ncu, profiles/r1_scan_before.md).  Instead each element is screened in
-// float32: qf = fl32(d) - fl32(u_j) with u_j = (1/(k-2)) * rs_j staged in shared memory, against
-// a per-row threshold thr >= (best + u_i) + E, where E = 2^-20 * (max|u| + |best + u_i|)
-// bounds every rounding of the screen (proof in DESIGN.md "scan screening").  Only elements
-// that pass are re-evaluated with the exact float64 expression and the lexicographic
-// (value, id_lo, id_hi) rule, so the selected pair is identical to evaluating everything
-// exactly.
-__device__ __forceinline__ float screen_value(float d) { return d; }
-__device__ __forceinline__ float screen_value(double d) { return __double2float_rd(d); }
-
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
-  constexpr int V = VecOf<T>::N;
-  constexpr int U = 4;                  // independent 128-bit loads in flight per lane
-  constexpr int STEP = 32 * V;          // elements per warp-wide load
   __shared__ __align__(16) float sU[NJ ? TC : 4];
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
@@ -163,88 +90,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
       if (jend <= c0) continue;
       const T *__restrict__ row = D + (int64_t)i * a.ld;
       const double Ri = NJ ? a.R[i] : 0.0;
-      const double ui = NJ ? __dmul_rn(a.tinv, Ri) : 0.0;
-      // screening threshold of this row for the thread's current best
-      auto threshold = [&]() -> float {
-        if (bi < 0) return INFINITY;
-        if (!NJ) return __double2float_ru(bq);
-        const double B = bq + ui;
-        return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + 1e-300);
-      };
-      float thr = threshold();
-      for (int jb = c0; jb < jend; jb += STEP * U) {
-        T v[U][V];
-        const bool whole = (jb + STEP * U <= jend);
-        if (whole) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) ld_stream(row + jb + u * STEP + lane * V, v[u]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = jb + u * STEP + lane * V;
-            if (j < jend) {
-              ld_stream(row + j, v[u]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < V; ++e) v[u][e] = (T)INFINITY;
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = jb + u * STEP + lane * V;
-          float qf[V];
-          if (NJ) {
-            float su[V];
-            if (V == 4) *reinterpret_cast<float4 *>(su) = *reinterpret_cast<const float4 *>(&sU[j - c0]);
-            else *reinterpret_cast<float2 *>(su) = *reinterpret_cast<const float2 *>(&sU[j - c0]);
-#pragma unroll
-            for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(screen_value(v[u][e]), su[e]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < V; ++e) qf[e] = screen_value(v[u][e]);
-          }
-          float m = qf[0];
-#pragma unroll
-          for (int e = 1; e < V; ++e) m = fminf(m, qf[e]);
-          if (m <= thr) {
-            // rare: exact float64 evaluation of the elements that passed the screen
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-              if (qf[e] <= thr && (whole || j + e < jend)) {
-                double q = (double)v[u][e];
-                if (NJ) {
-                  // q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) ), no FMA  (NeighborJoiningSolver.py:163-170)
-                  q = __dsub_rn(q, __dmul_rn(a.tinv, __dadd_rn(Ri, a.R[j + e])));
-                }
-                if (q <= bq || bi < 0) {
-                  tie_path(q, i, j + e, bq, bi, bj, a.ids);
-                  thr = threshold();
-                }
-              }
-            }
-          }
-        }
-      }
+      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj);
     }
   }
 
-  // warp reduce on (q, key)
-  unsigned long long bkey = (bi >= 0) ? make_key(a.ids[bi], a.ids[bj]) : ~0ull;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    double oq = __shfl_down_sync(0xffffffffu, bq, off);
-    unsigned long long ok = __shfl_down_sync(0xffffffffu, bkey, off);
-    int oi = __shfl_down_sync(0xffffffffu, bi, off);
-    int oj = __shfl_down_sync(0xffffffffu, bj, off);
-    if (cand_better(oq, ok, bq, bkey)) { bq = oq; bkey = ok; bi = oi; bj = oj; }
-  }
-  if (lane == 0) { sCand[warp].q = bq; sCand[warp].key = bkey; sCand[warp].si = bi; sCand[warp].sj = bj; }
-  __syncthreads();
+  Cand c = block_best(bq, bi, bj, a.ids, sCand);
   if (threadIdx.x == 0) {
-    Cand c = sCand[0];
-    for (int w = 1; w < SCAN_WARPS; ++w)
-      if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
     a.cand[blockIdx.x] = c;
     __threadfence();
     unsigned prev = atomicInc(a.counter, gridDim.x - 1);  // wraps back to 0
@@ -254,31 +105,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   if (!sLast) return;
   __threadfence();
   // the last CTA reduces all per-CTA candidates
-  Cand c;
-  c.q = INFINITY; c.key = ~0ull; c.si = -1; c.sj = -1;
-  for (int x = threadIdx.x; x < (int)gridDim.x; x += SCAN_THREADS) {
-    Cand o;  // written by other CTAs: read through L2
-    o.q = __ldcg(&a.cand[x].q);
-    o.key = __ldcg(&a.cand[x].key);
-    o.si = __ldcg(&a.cand[x].si);
-    o.sj = __ldcg(&a.cand[x].sj);
-    if (cand_better(o.q, o.key, c.q, c.key)) c = o;
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    double oq = __shfl_down_sync(0xffffffffu, c.q, off);
-    unsigned long long ok = __shfl_down_sync(0xffffffffu, c.key, off);
-    int oi = __shfl_down_sync(0xffffffffu, c.si, off);
-    int oj = __shfl_down_sync(0xffffffffu, c.sj, off);
-    if (cand_better(oq, ok, c.q, c.key)) { c.q = oq; c.key = ok; c.si = oi; c.sj = oj; }
-  }
-  __syncthreads();
-  if (lane == 0) sCand[warp] = c;
-  __syncthreads();
+  c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
   if (threadIdx.x == 0) {
-    c = sCand[0];
-    for (int w = 1; w < SCAN_WARPS; ++w)
-      if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
     Sel s;
     s.lo = min(c.si, c.sj);
     s.hi = max(c.si, c.sj);
@@ -291,17 +119,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
     a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
     a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
   }
-}
-
-// running maximum of |row sum| (non-negative doubles order like their bit patterns)
-__device__ __forceinline__ void warp_atomic_absmax(unsigned long long *dst, double x) {
-  unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x));
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
-    b = o > b ? o : b;
-  }
-  if ((threadIdx.x & 31) == 0) atomicMax(dst, b);
 }
 
 struct MergeArgs {
@@ -321,10 +138,6 @@ struct MergeArgs {
   const int32_t *order_old; const int32_t *pos_old;
   int32_t *order_new; int32_t *pos_new;
 };
-
-template <typename T> __device__ __forceinline__ T round_to(double v);
-template <> __device__ __forceinline__ float round_to<float>(double v) { return __double2float_rn(v); }
-template <> __device__ __forceinline__ double round_to<double>(double v) { return v; }
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {

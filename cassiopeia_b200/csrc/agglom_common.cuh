@@ -1,0 +1,224 @@
+// Device-side pieces shared by the single-GPU loop (agglom.cu) and the row-sharded loop (sharded.cu).
+#pragma once
+
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cas {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int TC = 2048;  // columns per tile (R_j block staged in shared memory: 16 KB)
+constexpr int MERGE_THREADS = 256;
+constexpr int MAX_SCAN_CTAS = 2048;
+
+struct Cand {
+  double q;
+  unsigned long long key;  // (id_lo << 32) | id_hi ; ~0 = empty
+  int si, sj;              // slots, si > sj (row, column of the lower triangle)
+};
+
+struct Sel {
+  int lo, hi;       // slots, lo < hi
+  int size_lo, size_hi;
+  double dij;
+  int id_lo, id_hi;
+};
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int N = 4; };
+template <> struct VecOf<double> { static constexpr int N = 2; };
+
+__device__ __forceinline__ void ld_stream(const float *p, float (&v)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_stream(const double *p, double (&v)[2]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+
+__device__ __forceinline__ unsigned long long make_key(int ida, int idb) {
+  unsigned lo = (unsigned)min(ida, idb), hi = (unsigned)max(ida, idb);
+  return ((unsigned long long)lo << 32) | hi;
+}
+
+// rare path: candidate ties (or beats) the thread's running best
+__device__ __forceinline__ void tie_path(double q, int i, int j, double &bq, int &bi, int &bj,
+                                         const int32_t *__restrict__ ids) {
+  if (q < bq || bi < 0) {
+    bq = q; bi = i; bj = j;
+    return;
+  }
+  unsigned long long kn = make_key(ids[i], ids[j]);
+  unsigned long long ko = make_key(ids[bi], ids[bj]);
+  if (kn < ko) { bi = i; bj = j; }
+}
+
+__device__ __forceinline__ bool cand_better(double qa, unsigned long long ka, double qb,
+                                            unsigned long long kb) {
+  // empty candidates carry key ~0 and q = +inf
+  return (qa < qb) || (qa == qb && ka < kb);
+}
+
+// Screening arithmetic.  The exact criterion of a pair is the reference's float64 expression
+//   q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) )          (NJ)        q = d_ij  (UPGMA)
+// Evaluating it for every element costs ~30 instructions per element and makes the scan
+// issue-bound (ncu, profiles/r1_scan_before.md).  Instead each element is screened in
+// float32: qf = fl32(d) - fl32(u_j) with u_j = (1/(k-2)) * rs_j staged in shared memory, against
+// a per-row threshold thr >= (best + u_i) + E, where E = 2^-20 * (max|u| + |best + u_i|)
+// bounds every rounding of the screen (proof in DESIGN.md "scan screening").  Only elements
+// that pass are re-evaluated with the exact float64 expression and the lexicographic
+// (value, id_lo, id_hi) rule, so the selected pair is identical to evaluating everything
+// exactly.
+__device__ __forceinline__ float screen_value(float d) { return d; }
+__device__ __forceinline__ float screen_value(double d) { return __double2float_rd(d); }
+
+// running maximum of |row sum| (non-negative doubles order like their bit patterns)
+__device__ __forceinline__ void warp_atomic_absmax(unsigned long long *dst, double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
+    b = o > b ? o : b;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(dst, b);
+}
+
+template <typename T> __device__ __forceinline__ T round_to(double v);
+template <> __device__ __forceinline__ float round_to<float>(double v) { return __double2float_rn(v); }
+template <> __device__ __forceinline__ double round_to<double>(double v) { return v; }
+
+
+// Scans columns [c0, jend) of one matrix row (slot i) with one warp: float32 screen against the
+// staged u_j block `sU`, exact float64 re-evaluation of the survivors.  (bq, bi, bj) is the
+// lane's running best (value, row slot, column slot).
+template <typename T, bool NJ>
+__device__ __forceinline__ void scan_row_segment(const T *__restrict__ row, int i, int c0, int jend,
+                                                 int lane, const float *sU, const double *__restrict__ R,
+                                                 double Ri, double tinv, double umax,
+                                                 const int32_t *__restrict__ ids, double &bq, int &bi,
+                                                 int &bj) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int U = 4;          // independent 128-bit loads in flight per lane
+  constexpr int STEP = 32 * V;  // elements per warp-wide load
+  const double ui = NJ ? __dmul_rn(tinv, Ri) : 0.0;
+  // screening threshold of this row for the lane's current best
+  auto threshold = [&]() -> float {
+    if (bi < 0) return INFINITY;
+    if (!NJ) return __double2float_ru(bq);
+    const double B = bq + ui;
+    return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + 1e-300);
+  };
+  float thr = threshold();
+  for (int jb = c0; jb < jend; jb += STEP * U) {
+    T v[U][V];
+    const bool whole = (jb + STEP * U <= jend);
+    if (whole) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) ld_stream(row + jb + u * STEP + lane * V, v[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = jb + u * STEP + lane * V;
+        if (j < jend) {
+          ld_stream(row + j, v[u]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[u][e] = (T)INFINITY;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + u * STEP + lane * V;
+      float qf[V];
+      if (NJ) {
+        float su[V];
+        if (V == 4) *reinterpret_cast<float4 *>(su) = *reinterpret_cast<const float4 *>(&sU[j - c0]);
+        else *reinterpret_cast<float2 *>(su) = *reinterpret_cast<const float2 *>(&sU[j - c0]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(screen_value(v[u][e]), su[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) qf[e] = screen_value(v[u][e]);
+      }
+      float m = qf[0];
+#pragma unroll
+      for (int e = 1; e < V; ++e) m = fminf(m, qf[e]);
+      if (m <= thr) {
+        // rare: exact float64 evaluation of the elements that passed the screen
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          if (qf[e] <= thr && (whole || j + e < jend)) {
+            double q = (double)v[u][e];
+            if (NJ) {
+              // q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) ), no FMA  (NeighborJoiningSolver.py:163-170)
+              q = __dsub_rn(q, __dmul_rn(tinv, __dadd_rn(Ri, R[j + e])));
+            }
+            if (q <= bq || bi < 0) {
+              tie_path(q, i, j + e, bq, bi, bj, ids);
+              thr = threshold();
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Reduces the lanes' bests to one candidate per CTA (thread 0 returns it).
+__device__ __forceinline__ Cand block_best(double bq, int bi, int bj, const int32_t *__restrict__ ids,
+                                           Cand *sCand) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long bkey = (bi >= 0) ? make_key(ids[bi], ids[bj]) : ~0ull;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double oq = __shfl_down_sync(0xffffffffu, bq, off);
+    unsigned long long ok = __shfl_down_sync(0xffffffffu, bkey, off);
+    int oi = __shfl_down_sync(0xffffffffu, bi, off);
+    int oj = __shfl_down_sync(0xffffffffu, bj, off);
+    if (cand_better(oq, ok, bq, bkey)) { bq = oq; bkey = ok; bi = oi; bj = oj; }
+  }
+  if (lane == 0) { sCand[warp].q = bq; sCand[warp].key = bkey; sCand[warp].si = bi; sCand[warp].sj = bj; }
+  __syncthreads();
+  Cand c = sCand[0];
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SCAN_WARPS; ++w)
+      if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
+  }
+  return c;
+}
+
+// All threads of one CTA reduce `count` candidates written by other CTAs / ranks (read through L2).
+__device__ __forceinline__ Cand reduce_candidates(const Cand *cand, int count, Cand *sCand) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Cand c;
+  c.q = INFINITY; c.key = ~0ull; c.si = -1; c.sj = -1;
+  for (int x = threadIdx.x; x < count; x += blockDim.x) {
+    Cand o;
+    o.q = __ldcg(&cand[x].q);
+    o.key = __ldcg(&cand[x].key);
+    o.si = __ldcg(&cand[x].si);
+    o.sj = __ldcg(&cand[x].sj);
+    if (cand_better(o.q, o.key, c.q, c.key)) c = o;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double oq = __shfl_down_sync(0xffffffffu, c.q, off);
+    unsigned long long ok = __shfl_down_sync(0xffffffffu, c.key, off);
+    int oi = __shfl_down_sync(0xffffffffu, c.si, off);
+    int oj = __shfl_down_sync(0xffffffffu, c.sj, off);
+    if (cand_better(oq, ok, c.q, c.key)) { c.q = oq; c.key = ok; c.si = oi; c.sj = oj; }
+  }
+  __syncthreads();
+  if (lane == 0) sCand[warp] = c;
+  __syncthreads();
+  c = sCand[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
+  return c;  // identical in every thread
+}
+
+}  // namespace cas

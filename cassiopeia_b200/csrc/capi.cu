@@ -37,7 +37,8 @@ int sm_count() {
 size_t whd_exact_workspace_bytes(int64_t n, int32_t m, int32_t weighted);
 int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
                   int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
-                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                  void *workspace, size_t workspace_bytes, cudaStream_t stream, int cyc_G = 0,
+                  int cyc_r = 0);
 int whd_read_error_flag(const void *workspace, cudaStream_t stream, int *flag);
 size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted);
 int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
@@ -98,6 +99,20 @@ int cas_whd_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const 
   CAS_REQUIRE(method == CAS_MAP_EXACT, "bad map method %d", method);
   return whd_exact_map(cm, n, m, missing, w, n_states, D, ld, dtype, row0, row1, workspace,
                        workspace_bytes, (cudaStream_t)stream);
+}
+
+int cas_whd_map_cyclic(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
+                       int32_t n_states, void *D_local, int64_t ld, int32_t dtype, int32_t rank,
+                       int32_t world, int32_t method, void *workspace, size_t workspace_bytes,
+                       void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(cm && D_local && workspace, "null pointer argument");
+  CAS_REQUIRE(n >= 1 && m >= 1 && ld >= n, "bad sizes");
+  CAS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d of %d", rank, world);
+  CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
+  CAS_REQUIRE(method == CAS_MAP_EXACT, "only CAS_MAP_EXACT builds block-cyclic shards");
+  return whd_exact_map(cm, n, m, missing, w, n_states, D_local, ld, dtype, 0, n, workspace,
+                       workspace_bytes, (cudaStream_t)stream, world, rank);
 }
 
 size_t cas_agglom_workspace_bytes(int64_t n, int32_t algo, int32_t mode) {

@@ -1,0 +1,622 @@
+// Row-sharded Neighbor-Joining / UPGMA loop for maps larger than one GPU.
+//
+// No reference counterpart (the reference is single-host); same arithmetic as the single-GPU
+// fast loop in agglom.cu, so 1-GPU and N-GPU runs produce the identical join list.
+//
+// Partition: slots are dealt to ranks in blocks of SHB = 64 rows, block-cyclically
+// (owner(s) = (s / 64) % G); a rank stores its rows contiguously in local-row order
+// (local(s) = (s / 64 / G) * 64 + s % 64), full length ld, so scans stay coalesced and the
+// triangular work is balanced.  Row sums R, ids and cluster sizes are replicated.
+//
+// One iteration at live size k (host knows k, the pair lives on the device):
+//   scan   : each rank scans the lower-triangle part of its own rows -> one candidate
+//   C1     : all-gather of the G candidates (24 B each); every rank reduces them identically
+//            (lexicographic (value, id_lo, id_hi): exact, order-free => root-free arg-min)
+//   cols   : each rank extracts, for its rows v, d(v,lo), d(v,hi), d(v,last) -- by symmetry these
+//            are the full rows lo, hi and last
+//   C2     : all-gather of those three vectors (3 * k values)
+//   merge  : every rank computes the merged row redundantly (bit-identical), updates the
+//            replicated R / ids / sizes, the two columns of its own rows and, if it owns them,
+//            rows lo and hi (swap compaction as in agglom.cu).
+// Collectives: NCCL all-gather on the caller's stream (dlopen'ed libnccl.so.2, the one torch
+// already loaded), or none at all in the single-process emulation used to test the kernels on
+// one GPU (all virtual ranks share the gather buffers).
+#include <dlfcn.h>
+#include <string.h>
+
+#include <vector>
+
+#include "agglom_common.cuh"
+
+namespace cas {
+
+constexpr int SHB = 64;  // rows per ownership block
+
+__host__ __device__ __forceinline__ int sh_owner(int slot, int G) { return (slot / SHB) % G; }
+__host__ __device__ __forceinline__ int sh_local(int slot, int G) {
+  return (slot / SHB / G) * SHB + slot % SHB;
+}
+__host__ __device__ __forceinline__ int sh_slot(int local, int r, int G) {
+  return ((local / SHB) * G + r) * SHB + local % SHB;
+}
+// number of local rows of rank r whose slot is < k
+__host__ __device__ __forceinline__ int sh_count(int k, int r, int G) {
+  const int nb = k / SHB, rem = k % SHB;
+  int rows = (nb / G + (r < nb % G ? 1 : 0)) * SHB;
+  if (rem > 0 && nb % G == r) rows += rem;
+  return rows;
+}
+// stride (rows) of one rank's chunk in the gather buffers at live size k
+__host__ __device__ __forceinline__ int sh_chunk(int k, int G) {
+  const int nblocks = (k + SHB - 1) / SHB;
+  return ((nblocks + G - 1) / G) * SHB;
+}
+
+struct ShScanArgs {
+  const void *Dloc;
+  int64_t ld;
+  int k, G, r;
+  int nlrb;   // local row blocks of 32 rows
+  int ncb, ntiles;
+  const double *R;
+  const int32_t *ids;
+  double tinv;
+  const unsigned long long *rmax_bits;
+  Cand *cand;       // per-CTA scratch
+  unsigned *counter;
+  Cand *out;        // this rank's slot in the candidate gather buffer
+};
+
+constexpr int SH_TR = 32;  // rows per scan tile (divides SHB, so a tile's slots are contiguous)
+
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) sh_scan_kernel(ShScanArgs a) {
+  __shared__ __align__(16) float sU[NJ ? TC : 4];
+  __shared__ Cand sCand[SCAN_WARPS];
+  __shared__ bool sLast;
+  const T *__restrict__ D = static_cast<const T *>(a.Dloc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = a.k;
+  const double umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
+  double bq = INFINITY;
+  int bi = -1, bj = -1;
+  int staged_cb = -1;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    int cb = 0, rem = tile;
+    for (;;) {
+      // first local row block holding a row with slot > c0 (rows with slot <= c0 have no
+      // element in this column block)
+      int first = sh_count(cb * TC + 1, a.r, a.G) / SH_TR;
+      int cnt = max(a.nlrb - first, 0);
+      if (rem < cnt) { rem += first; break; }
+      rem -= cnt;
+      ++cb;
+    }
+    const int c0 = cb * TC;
+    const int c1 = min(c0 + TC, k);
+    if (NJ && cb != staged_cb) {
+      __syncthreads();
+      for (int x = threadIdx.x; x < TC; x += SCAN_THREADS)
+        sU[x] = (c0 + x < c1) ? __double2float_rn(__dmul_rn(a.tinv, a.R[c0 + x])) : 0.f;
+      staged_cb = cb;
+      __syncthreads();
+    }
+    const int l0 = rem * SH_TR;
+    for (int lr = l0 + warp; lr < l0 + SH_TR; lr += SCAN_WARPS) {
+      const int i = sh_slot(lr, a.r, a.G);
+      if (i >= k) continue;
+      const int jend = min(c1, i);
+      if (jend <= c0) continue;
+      const T *__restrict__ row = D + (int64_t)lr * a.ld;
+      const double Ri = NJ ? a.R[i] : 0.0;
+      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj);
+    }
+  }
+
+  Cand c = block_best(bq, bi, bj, a.ids, sCand);
+  if (threadIdx.x == 0) {
+    a.cand[blockIdx.x] = c;
+    __threadfence();
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
+  if (threadIdx.x == 0) *a.out = c;
+}
+
+struct ShColsArgs {
+  const void *Dloc;
+  int64_t ld;
+  int k, G, r;
+  int chunk;             // rows per rank chunk in the gather buffer
+  const Cand *cand_all;  // [G] gathered candidates
+  void *mine;            // this rank's chunk: [3][chunk] values of type T
+  const int32_t *ids;
+  const int32_t *sizes;
+  Sel *sel;
+  int32_t *joins;
+  int t;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
+  __shared__ Cand sCand[8];
+  const Cand c = reduce_candidates(a.cand_all, a.G, sCand);
+  const int lo = min(c.si, c.sj), hi = max(c.si, c.sj), last = a.k - 1;
+  const T *__restrict__ D = static_cast<const T *>(a.Dloc);
+  T *__restrict__ out = static_cast<T *>(a.mine);
+  const int lr = blockIdx.x * 256 + threadIdx.x;
+  if (lr < sh_count(a.k, a.r, a.G)) {
+    const T *row = D + (int64_t)lr * a.ld;
+    out[lr] = row[lo];
+    out[a.chunk + lr] = row[hi];
+    out[2 * a.chunk + lr] = row[last];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    Sel s;
+    s.lo = lo; s.hi = hi;
+    s.dij = 0.0;  // filled from the gathered row in the merge kernel
+    s.size_lo = a.sizes ? a.sizes[lo] : 1;
+    s.size_hi = a.sizes ? a.sizes[hi] : 1;
+    s.id_lo = a.ids[lo];
+    s.id_hi = a.ids[hi];
+    *a.sel = s;
+    a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
+    a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
+  }
+}
+
+struct ShMergeArgs {
+  void *Dloc;
+  int64_t ld;
+  int k, G, r, chunk;
+  const void *gath;  // [G][3][chunk] values of type T
+  const Sel *sel;
+  double *R;
+  int32_t *ids;
+  int32_t *sizes;
+  double *partial;
+  unsigned *counter;
+  unsigned long long *rmax_bits;
+  int new_id;
+  int maintain_R;
+};
+
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) {
+  __shared__ double sPart[MERGE_THREADS / 32];
+  __shared__ bool sLast;
+  T *__restrict__ D = static_cast<T *>(a.Dloc);
+  const T *__restrict__ g = static_cast<const T *>(a.gath);
+  const Sel s = *a.sel;
+  const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1, G = a.G;
+  const int64_t ld = a.ld;
+  const int64_t cstride = 3 * (int64_t)a.chunk;
+  auto gathered = [&](int which, int slot) -> T {
+    return g[(int64_t)sh_owner(slot, G) * cstride + (int64_t)which * a.chunk + sh_local(slot, G)];
+  };
+  const double dij = (double)gathered(0, hi);  // d(hi, lo)
+  auto merged = [&](double da, double db) -> double {
+    if (NJ) return __dmul_rn(0.5, __dsub_rn(__dadd_rn(da, db), dij));
+    const double zi = (double)s.size_lo, zj = (double)s.size_hi;
+    return __ddiv_rn(__dadd_rn(__dmul_rn(zi, da), __dmul_rn(zj, db)), (double)(s.size_lo + s.size_hi));
+  };
+  const bool own_lo = sh_owner(lo, G) == a.r, own_hi = sh_owner(hi, G) == a.r;
+  T *row_lo = own_lo ? D + (int64_t)sh_local(lo, G) * ld : nullptr;
+  T *row_hi = own_hi ? D + (int64_t)sh_local(hi, G) * ld : nullptr;
+  // merged distance of the node that sits in the last slot (needed at (lo,hi) / (hi,lo))
+  T nv_last = (T)0;
+  if (hi != last) nv_last = round_to<T>(merged((double)gathered(0, last), (double)gathered(1, last)));
+
+  const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
+  double contrib = 0.0, mine = 0.0;
+  if (v < k) {
+    const bool own_v = sh_owner(v, G) == a.r;
+    T *row_v = own_v ? D + (int64_t)sh_local(v, G) * ld : nullptr;
+    if (v == lo) {
+      if (own_lo) row_lo[lo] = (T)0;
+      if (own_hi && hi != last) row_hi[lo] = nv_last;
+      a.ids[lo] = a.new_id;
+      if (a.sizes) a.sizes[lo] = s.size_lo + s.size_hi;
+    } else if (v == hi) {
+      if (own_hi) row_hi[hi] = (T)0;
+      if (own_lo && hi != last) row_lo[hi] = nv_last;
+    } else {
+      const double da = (double)gathered(0, v), db = (double)gathered(1, v);
+      const T nvs = round_to<T>(merged(da, db));
+      contrib = (double)nvs;
+      double Rv = 0.0;
+      if (a.maintain_R) Rv = __dadd_rn(__dsub_rn(__dsub_rn(a.R[v], da), db), contrib);
+      if (hi != last && v != last) {
+        const T l = gathered(2, v);
+        if (own_hi) row_hi[v] = l;
+        if (own_v) row_v[hi] = l;
+      }
+      if (own_lo) row_lo[v] = nvs;
+      if (own_v) row_v[lo] = nvs;
+      if (v == last && hi != last) {
+        a.ids[hi] = a.ids[last];
+        if (a.sizes) a.sizes[hi] = a.sizes[last];
+        if (a.maintain_R) { a.R[hi] = Rv; mine = Rv; }
+      } else if (a.maintain_R) {
+        a.R[v] = Rv;
+        mine = Rv;
+      }
+    }
+  }
+  if (!a.maintain_R) return;
+  warp_atomic_absmax(a.rmax_bits, mine);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
+  if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int w = 0; w < MERGE_THREADS / 32; ++w) sum = __dadd_rn(sum, sPart[w]);
+    a.partial[blockIdx.x] = sum;
+    __threadfence();
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (sLast && threadIdx.x == 0) {
+    __threadfence();
+    double sum = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
+    a.R[lo] = sum;
+    atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
+  }
+}
+
+// initial row sums of the local rows (same lane-strided order as rowsum_init_kernel)
+template <typename T>
+__global__ void __launch_bounds__(256) sh_rowsum_kernel(const T *__restrict__ D, int64_t ld, int k, int G,
+                                                        int r, double *__restrict__ mine) {
+  const int lr = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (lr >= sh_count(k, r, G)) return;
+  const T *__restrict__ row = D + (int64_t)lr * ld;
+  double s = 0.0;
+  for (int j = lane; j < k; j += 32) s = __dadd_rn(s, (double)row[j]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+  if (lane == 0) mine[lr] = s;
+}
+
+__global__ void sh_rscatter_kernel(const double *__restrict__ gath, int chunk, int k, int G,
+                                   double *__restrict__ R, unsigned long long *rmax_bits) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (v < k) {
+    s = gath[(int64_t)sh_owner(v, G) * chunk + sh_local(v, G)];
+    R[v] = s;
+  }
+  warp_atomic_absmax(rmax_bits, s);
+}
+
+__global__ void sh_init_kernel(int n, int32_t *ids, int32_t *sizes, unsigned *counters,
+                               unsigned long long *rmax_bits) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) { ids[v] = v; sizes[v] = 1; }
+  if (v < 8) counters[v] = 0;
+  if (v == 0) *rmax_bits = 0ull;
+}
+
+__global__ void sh_last2_kernel(const int32_t *ids, int32_t *last2) {
+  if (threadIdx.x == 0) {
+    last2[0] = min(ids[0], ids[1]);
+    last2[1] = max(ids[0], ids[1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen (so the library also loads on boxes without NCCL)
+
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+
+struct UniqueId128 { char bytes[128]; };
+typedef int (*CommInitRankFn)(void **, int, UniqueId128, int);
+
+static NcclApi g_nccl;
+static CommInitRankFn g_comm_init = nullptr;
+
+static int nccl_load() {
+  if (g_nccl.handle) return CAS_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *nm : names) {
+    h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+    return CAS_ERR_NCCL;
+  }
+  g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+  g_comm_init = (CommInitRankFn)dlsym(h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+  g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_comm_init || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+    set_error("libnccl lacks a required symbol");
+    return CAS_ERR_NCCL;
+  }
+  g_nccl.handle = h;
+  return CAS_OK;
+}
+
+#define CAS_NCCL_TRY(expr)                                                                  \
+  do {                                                                                      \
+    int _r = (expr);                                                                        \
+    if (_r != 0) {                                                                          \
+      set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+      return CAS_ERR_NCCL;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+constexpr int NCCL_INT8 = 0;  // ncclInt8 / ncclChar
+
+// ---------------------------------------------------------------------------------------------
+
+struct ShWorkspace {
+  double *R;
+  int32_t *ids, *sizes;
+  Cand *cand;
+  Cand *cand_all;
+  Sel *sel;
+  double *partial;
+  unsigned *counters;
+  unsigned long long *rmax_bits;
+  char *gath;  // max(G*3*chunk*esz, G*chunk*8) bytes
+  size_t gath_bytes;
+  size_t bytes;
+};
+
+static ShWorkspace sh_carve(void *base, int64_t n, int G, size_t esz) {
+  Carver c(base);
+  ShWorkspace w;
+  w.R = c.take<double>(n);
+  w.ids = c.take<int32_t>(n);
+  w.sizes = c.take<int32_t>(n);
+  w.cand = c.take<Cand>(MAX_SCAN_CTAS);
+  w.cand_all = c.take<Cand>(64);
+  w.sel = c.take<Sel>(4);
+  w.partial = c.take<double>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
+  w.counters = c.take<unsigned>(64);
+  w.rmax_bits = c.take<unsigned long long>(8);
+  const size_t chunk = (size_t)sh_chunk((int)n, G);
+  size_t per = 3 * chunk * esz;
+  if (per < chunk * 8) per = chunk * 8;
+  w.gath_bytes = per * G;
+  w.gath = c.take<char>(w.gath_bytes);
+  w.bytes = c.used();
+  return w;
+}
+
+struct ShRank {
+  void *D;
+  ShWorkspace w;
+  int r;
+};
+
+// Runs the loop for the local virtual ranks `ranks` (one in real multi-process mode, G in the
+// emulation).  comm == nullptr => emulation: the ranks share ranks[0]'s gather buffers.
+template <typename T, bool NJ>
+static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int64_t max_iters, void *comm,
+                  int32_t *joins, int32_t *last2, cudaStream_t stream) {
+  const int sms = sm_count();
+  const int target_ctas = sms * 4;
+  const bool emu = (comm == nullptr);
+  Cand *cand_all = ranks[0].w.cand_all;
+  char *gath = ranks[0].w.gath;
+  for (auto &rk : ranks) {
+    sh_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)n, rk.w.ids, rk.w.sizes,
+                                                                    rk.w.counters, rk.w.rmax_bits);
+    CAS_LAUNCH_CHECK();
+  }
+  if (NJ && n > 2) {
+    const int chunk = sh_chunk((int)n, G);
+    for (auto &rk : ranks) {
+      const int nloc = sh_count((int)n, rk.r, G);
+      double *mine = reinterpret_cast<double *>(emu ? gath : rk.w.gath) + (size_t)rk.r * chunk;
+      if (nloc > 0) {
+        sh_rowsum_kernel<T><<<(unsigned)((nloc + 7) / 8), 256, 0, stream>>>((const T *)rk.D, ld, (int)n, G,
+                                                                             rk.r, mine);
+        CAS_LAUNCH_CHECK();
+      }
+    }
+    if (!emu) {
+      ShRank &rk = ranks[0];
+      double *buf = reinterpret_cast<double *>(rk.w.gath);
+      CAS_NCCL_TRY(g_nccl.AllGather(buf + (size_t)rk.r * chunk, buf, (size_t)chunk * 8, NCCL_INT8, comm, stream));
+    }
+    for (auto &rk : ranks) {
+      const double *buf = reinterpret_cast<const double *>(emu ? gath : rk.w.gath);
+      sh_rscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(buf, chunk, (int)n, G, rk.w.R,
+                                                                          rk.w.rmax_bits);
+      CAS_LAUNCH_CHECK();
+    }
+  }
+  for (int64_t t = 0; t + 2 < n; ++t) {
+    if (max_iters >= 0 && t >= max_iters) break;
+    const int k = (int)(n - t);
+    const int chunk = sh_chunk(k, G);
+    const int ncb = (k + TC - 1) / TC;
+    // --- scan
+    for (auto &rk : ranks) {
+      ShScanArgs sa;
+      sa.Dloc = rk.D; sa.ld = ld; sa.k = k; sa.G = G; sa.r = rk.r;
+      const int nloc = sh_count(k, rk.r, G);
+      sa.nlrb = (nloc + SH_TR - 1) / SH_TR;
+      sa.ncb = ncb;
+      long long cnt = 0;
+      for (int cb = 0; cb < ncb; ++cb) {
+        int first = sh_count(cb * TC + 1, rk.r, G) / SH_TR;
+        if (sa.nlrb > first) cnt += sa.nlrb - first;
+      }
+      sa.ntiles = (int)cnt;
+      sa.R = rk.w.R; sa.ids = rk.w.ids; sa.tinv = 1.0 / (double)(k - 2); sa.rmax_bits = rk.w.rmax_bits;
+      sa.cand = rk.w.cand; sa.counter = rk.w.counters + 0;
+      sa.out = (emu ? cand_all : rk.w.cand_all) + rk.r;
+      int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
+      if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
+      if (grid < 1) grid = 1;
+      sh_scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+      CAS_LAUNCH_CHECK();
+    }
+    // --- C1: candidates
+    if (!emu) {
+      ShRank &rk = ranks[0];
+      CAS_NCCL_TRY(g_nccl.AllGather(rk.w.cand_all + rk.r, rk.w.cand_all, sizeof(Cand), NCCL_INT8, comm, stream));
+    }
+    // --- cols
+    for (auto &rk : ranks) {
+      ShColsArgs ca;
+      ca.Dloc = rk.D; ca.ld = ld; ca.k = k; ca.G = G; ca.r = rk.r; ca.chunk = chunk;
+      ca.cand_all = emu ? cand_all : rk.w.cand_all;
+      ca.mine = (emu ? gath : rk.w.gath) + (size_t)rk.r * 3 * chunk * sizeof(T);
+      ca.ids = rk.w.ids; ca.sizes = NJ ? nullptr : rk.w.sizes; ca.sel = rk.w.sel;
+      ca.joins = joins; ca.t = (int)t;
+      const int nloc = sh_count(k, rk.r, G);
+      sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
+      CAS_LAUNCH_CHECK();
+    }
+    // --- C2: rows lo, hi, last
+    if (!emu) {
+      ShRank &rk = ranks[0];
+      const size_t per = (size_t)3 * chunk * sizeof(T);
+      CAS_NCCL_TRY(g_nccl.AllGather(rk.w.gath + (size_t)rk.r * per, rk.w.gath, per, NCCL_INT8, comm, stream));
+    }
+    // --- merge
+    for (auto &rk : ranks) {
+      ShMergeArgs ma;
+      ma.Dloc = rk.D; ma.ld = ld; ma.k = k; ma.G = G; ma.r = rk.r; ma.chunk = chunk;
+      ma.gath = emu ? gath : rk.w.gath;
+      ma.sel = rk.w.sel; ma.R = rk.w.R; ma.ids = rk.w.ids; ma.sizes = NJ ? nullptr : rk.w.sizes;
+      ma.partial = rk.w.partial; ma.counter = rk.w.counters + 1; ma.rmax_bits = rk.w.rmax_bits;
+      ma.new_id = (int)(n + t); ma.maintain_R = NJ ? 1 : 0;
+      sh_merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
+      CAS_LAUNCH_CHECK();
+    }
+  }
+  if (n >= 2) {
+    sh_last2_kernel<<<1, 32, 0, stream>>>(ranks[0].w.ids, last2);
+    CAS_LAUNCH_CHECK();
+  }
+  return CAS_OK;
+}
+
+static int sh_dispatch(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int dtype, int algo,
+                       int64_t max_iters, void *comm, int32_t *joins, int32_t *last2, cudaStream_t stream) {
+  if (algo == CAS_ALGO_NJ) {
+    if (dtype == CAS_F64) return sh_run<double, true>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
+    return sh_run<float, true>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
+  }
+  if (dtype == CAS_F64) return sh_run<double, false>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
+  return sh_run<float, false>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
+}
+
+}  // namespace cas
+
+using namespace cas;
+
+extern "C" {
+
+int64_t cas_sharded_local_rows(int64_t n, int32_t rank, int32_t world) {
+  if (world < 1 || rank < 0 || rank >= world || n < 0) return -1;
+  return sh_count((int)n, rank, world);
+}
+
+int64_t cas_sharded_local_capacity(int64_t n, int32_t world) {
+  if (world < 1 || n < 0) return -1;
+  return sh_chunk((int)n, world);
+}
+
+size_t cas_sharded_workspace_bytes(int64_t n, int32_t world, int32_t dtype) {
+  return sh_carve(nullptr, n > 0 ? n : 1, world > 0 ? world : 1, dtype == CAS_F64 ? 8 : 4).bytes;
+}
+
+int cas_nccl_unique_id(void *out128) {
+  CAS_REQUIRE(out128, "null pointer argument");
+  int rc = nccl_load();
+  if (rc != CAS_OK) return rc;
+  CAS_NCCL_TRY(g_nccl.GetUniqueId(out128));
+  return CAS_OK;
+}
+
+int cas_nccl_comm_create(const void *id128, int32_t rank, int32_t world, void **comm_out) {
+  CAS_REQUIRE(id128 && comm_out, "null pointer argument");
+  int rc = nccl_load();
+  if (rc != CAS_OK) return rc;
+  UniqueId128 id;
+  memcpy(id.bytes, id128, 128);
+  void *comm = nullptr;
+  CAS_NCCL_TRY(g_comm_init(&comm, world, id, rank));
+  *comm_out = comm;
+  return CAS_OK;
+}
+
+int cas_nccl_comm_destroy(void *comm) {
+  if (!comm) return CAS_OK;
+  int rc = nccl_load();
+  if (rc != CAS_OK) return rc;
+  CAS_NCCL_TRY(g_nccl.CommDestroy(comm));
+  return CAS_OK;
+}
+
+static int sh_check(int64_t n, int64_t ld, int dtype, int algo, int world) {
+  CAS_REQUIRE(n >= 2 && n < (int64_t)1 << 30, "n=%lld out of range", (long long)n);
+  CAS_REQUIRE(ld >= n && ld % 32 == 0, "ld=%lld must be >= n and a multiple of 32", (long long)ld);
+  CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
+  CAS_REQUIRE(algo == CAS_ALGO_NJ || algo == CAS_ALGO_UPGMA, "bad algo %d", algo);
+  CAS_REQUIRE(world >= 1 && world <= 64, "world=%d out of range", world);
+  return CAS_OK;
+}
+
+int cas_sharded_solve(void *D_local, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int64_t max_iters,
+                      int32_t rank, int32_t world, void *nccl_comm, int32_t *joins, int32_t *last2,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(D_local && joins && last2 && workspace && nccl_comm, "null pointer argument");
+  int rc = sh_check(n, ld, dtype, algo, world);
+  if (rc != CAS_OK) return rc;
+  CAS_REQUIRE(rank >= 0 && rank < world, "bad rank %d", rank);
+  CAS_REQUIRE(workspace_bytes >= cas_sharded_workspace_bytes(n, world, dtype), "workspace too small");
+  rc = nccl_load();
+  if (rc != CAS_OK) return rc;
+  std::vector<ShRank> ranks(1);
+  ranks[0].D = D_local;
+  ranks[0].w = sh_carve(workspace, n, world, dtype == CAS_F64 ? 8 : 4);
+  ranks[0].r = rank;
+  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nccl_comm, joins, last2, (cudaStream_t)stream);
+}
+
+int cas_sharded_solve_emulated(void *const *D_locals, int64_t n, int64_t ld, int32_t dtype, int32_t algo,
+                               int64_t max_iters, int32_t world, int32_t *joins, int32_t *last2,
+                               void *const *workspaces, size_t workspace_bytes, void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(D_locals && joins && last2 && workspaces, "null pointer argument");
+  int rc = sh_check(n, ld, dtype, algo, world);
+  if (rc != CAS_OK) return rc;
+  CAS_REQUIRE(workspace_bytes >= cas_sharded_workspace_bytes(n, world, dtype), "workspace too small");
+  std::vector<ShRank> ranks(world);
+  for (int r = 0; r < world; ++r) {
+    CAS_REQUIRE(D_locals[r] && workspaces[r], "null shard pointer for rank %d", r);
+    ranks[r].D = D_locals[r];
+    ranks[r].w = sh_carve(workspaces[r], n, world, dtype == CAS_F64 ? 8 : 4);
+    ranks[r].r = r;
+  }
+  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nullptr, joins, last2, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -66,7 +66,7 @@ template <typename T, bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 whd_exact_kernel(const uint16_t *__restrict__ codes, const double *__restrict__ wrow, int64_t n,
                  int m, int m_pad, T *__restrict__ D, int64_t ld, int64_t row0, int64_t row1,
-                 int tri, int tiles_x) {
+                 int tri, int tiles_x, int cyc_G, int cyc_r) {
   __shared__ __align__(16) uint16_t sA[CK][CPAD];
   __shared__ __align__(16) uint16_t sB[CK][CPAD];
   __shared__ __align__(16) double sWA[WEIGHTED ? CK : 1][WPAD];
@@ -85,7 +85,10 @@ whd_exact_kernel(const uint16_t *__restrict__ codes, const double *__restrict__ 
     tr = blockIdx.x / tiles_x;
     tc = blockIdx.x % tiles_x;
   }
-  const int64_t i0 = row0 + tr * TILE;  // first row (global index) of this tile
+  // first row (global index) of this tile; block-cyclic shards (cyc_G > 0) own the 64-row
+  // blocks cyc_r, cyc_r + cyc_G, ... and store them contiguously in local order
+  const int64_t i0 = cyc_G > 0 ? (tr * cyc_G + cyc_r) * TILE : row0 + tr * TILE;
+  const int64_t o0 = cyc_G > 0 ? tr * TILE : tr * TILE;  // first output row of this tile
   const int64_t j0 = tc * TILE;         // first column
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
@@ -162,8 +165,8 @@ whd_exact_kernel(const uint16_t *__restrict__ codes, const double *__restrict__ 
       }
       if (gi == gj) v = 0.0;
       const T o = cvt_out<T>(v);
-      D[(gi - row0) * ld + gj] = o;
-      if (mirror) D[(gj - row0) * ld + gi] = o;
+      D[(o0 + ty * 4 + x) * ld + gj] = o;
+      if (mirror) D[gj * ld + gi] = o;
     }
   }
 }
@@ -181,7 +184,7 @@ size_t whd_exact_workspace_bytes(int64_t n, int32_t m, int32_t weighted) {
 
 int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
                   int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
-                  void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+                  void *workspace, size_t workspace_bytes, cudaStream_t stream, int cyc_G, int cyc_r) {
   CAS_REQUIRE(n_states >= 0 && n_states <= 65534, "n_states=%d outside [0, 65534]", n_states);
   const bool weighted = (w != nullptr);
   CAS_REQUIRE(workspace_bytes >= whd_exact_workspace_bytes(n, m, weighted),
@@ -200,8 +203,15 @@ int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
                                                         wrow, err_flag);
     CAS_LAUNCH_CHECK();
   }
-  const bool full = (row0 == 0 && row1 == n);
-  const int64_t tiles_r = (row1 - row0 + TILE - 1) / TILE;
+  const bool full = (row0 == 0 && row1 == n) && cyc_G <= 0;
+  int64_t tiles_r = (row1 - row0 + TILE - 1) / TILE;
+  if (cyc_G > 0) {
+    // 64-row blocks owned by cyc_r among ceil(n / 64)
+    const int64_t nblocks = (n + TILE - 1) / TILE;
+    tiles_r = nblocks > cyc_r ? (nblocks - cyc_r + cyc_G - 1) / cyc_G : 0;
+    row0 = 0;
+    row1 = n;
+  }
   const int64_t tiles_c = (n + TILE - 1) / TILE;
   const int64_t ntiles = full ? tiles_r * (tiles_r + 1) / 2 : tiles_r * tiles_c;
   CAS_REQUIRE(ntiles < (int64_t)2147483647, "too many tiles");
@@ -209,7 +219,7 @@ int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
   dim3 grid((unsigned)ntiles);
 #define LAUNCH(T, W)                                                                          \
   whd_exact_kernel<T, W><<<grid, 256, 0, stream>>>(codes, wrow, n, m, mp, (T *)D, ld, row0,  \
-                                                   row1, full ? 1 : 0, (int)tiles_c)
+                                                   row1, full ? 1 : 0, (int)tiles_c, cyc_G, cyc_r)
   if (dtype == CAS_F64) {
     if (weighted) LAUNCH(double, true); else LAUNCH(double, false);
   } else {

@@ -1,0 +1,232 @@
+"""Row-sharded NJ / UPGMA over several B200s (one process per GPU, NCCL over NVLink).
+
+The n x n map is dealt to the ranks in 64-row blocks, block-cyclically; every rank builds its
+own rows from the replicated character matrix (no exchange) and the loop exchanges, per
+iteration, the ranks' arg-min candidates and the three rows (lo, hi, last) with two NCCL
+all-gathers issued from the C++ host loop of ``cas_sharded_solve``.  ``torch.distributed`` is
+used only to hand the NCCL unique id to the other ranks.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import _lib, engine
+from ._lib import CAS_ALGO_NJ, CAS_ALGO_UPGMA, CAS_F32, CAS_F64, CAS_MAP_EXACT
+
+BLOCK = 64  # rows per ownership block (SHB in csrc/sharded.cu)
+
+
+# ---- partition arithmetic (mirrors sh_owner / sh_local / sh_count; tested on CPU) -------------
+def owner_of(slot: int, world: int) -> int:
+    return (slot // BLOCK) % world
+
+
+def local_of(slot: int, world: int) -> int:
+    return (slot // BLOCK // world) * BLOCK + slot % BLOCK
+
+
+def slot_of(local: int, rank: int, world: int) -> int:
+    return ((local // BLOCK) * world + rank) * BLOCK + local % BLOCK
+
+
+def local_rows(k: int, rank: int, world: int) -> int:
+    nb, rem = divmod(k, BLOCK)
+    rows = (nb // world + (1 if rank < nb % world else 0)) * BLOCK
+    if rem > 0 and nb % world == rank:
+        rows += rem
+    return rows
+
+
+def local_capacity(n: int, world: int) -> int:
+    nblocks = (n + BLOCK - 1) // BLOCK
+    return ((nblocks + world - 1) // world) * BLOCK
+
+
+def shard_rows(n: int, rank: int, world: int) -> np.ndarray:
+    """Global slots of this rank's local rows, in local order."""
+    return np.array([slot_of(l, rank, world) for l in range(local_rows(n, rank, world))], dtype=np.int64)
+
+
+# ---- device side ----------------------------------------------------------------------------
+def build_shard(cm_dev, missing: int, table, n_states: int, rank: int, world: int, dtype: str = "f32"):
+    """This rank's rows of the map, [local_capacity, ld], from the replicated character matrix."""
+    torch = engine._torch()
+    L = _lib.load()
+    n, m = int(cm_dev.shape[0]), int(cm_dev.shape[1])
+    ld = engine.padded_ld(n)
+    cap = local_capacity(n, world)
+    tdtype = torch.float64 if dtype == "f64" else torch.float32
+    D = torch.zeros((cap, ld), dtype=tdtype, device="cuda")
+    w_t = torch.from_numpy(np.ascontiguousarray(table, dtype=np.float64)).cuda() if table is not None else None
+    ws_bytes = int(L.cas_whd_workspace_bytes(n, m, int(n_states), 1 if w_t is not None else 0, CAS_MAP_EXACT))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda")
+    rc = L.cas_whd_map_cyclic(cm_dev.data_ptr(), n, m, int(missing), w_t.data_ptr() if w_t is not None else None,
+                              int(n_states), D.data_ptr(), ld, CAS_F64 if dtype == "f64" else CAS_F32,
+                              int(rank), int(world), CAS_MAP_EXACT, ws.data_ptr(), ws_bytes,
+                              engine._stream_ptr(torch))
+    _lib.check(rc, "cas_whd_map_cyclic")
+    return D
+
+
+def emulated_solve(codes: np.ndarray, missing: int, table, n_states: int, algo: str, world: int,
+                   dtype: str = "f32", max_iters: int = -1):
+    """All `world` virtual ranks in this process on the current GPU (no collective): the same
+    kernels as the multi-process path, used to check that sharding does not change the joins."""
+    torch = engine._torch()
+    L = _lib.load()
+    cm_dev = torch.from_numpy(np.ascontiguousarray(codes, dtype=np.int32)).cuda()
+    n = int(cm_dev.shape[0])
+    ld = engine.padded_ld(n)
+    code = CAS_F64 if dtype == "f64" else CAS_F32
+    shards = [build_shard(cm_dev, missing, table, n_states, r, world, dtype) for r in range(world)]
+    ws_bytes = int(L.cas_sharded_workspace_bytes(n, world, code))
+    wss = [torch.empty(ws_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    njoin = max(n - 2, 0)
+    joins = torch.full((njoin + 1, 2), -1, dtype=torch.int32, device="cuda")
+    last2 = torch.full((2,), -1, dtype=torch.int32, device="cuda")
+    dptr = (ctypes.c_void_p * world)(*[s.data_ptr() for s in shards])
+    wptr = (ctypes.c_void_p * world)(*[w.data_ptr() for w in wss])
+    rc = L.cas_sharded_solve_emulated(dptr, n, ld, code, CAS_ALGO_NJ if algo == "nj" else CAS_ALGO_UPGMA,
+                                      int(max_iters), int(world), joins.data_ptr(), last2.data_ptr(), wptr,
+                                      ws_bytes, engine._stream_ptr(torch))
+    _lib.check(rc, "cas_sharded_solve_emulated")
+    done = njoin if max_iters < 0 else min(njoin, max_iters)
+    return joins[:done].cpu().numpy(), last2.cpu().numpy()
+
+
+class NcclGroup:
+    """NCCL communicator owned by libcas_b200; the unique id travels over torch.distributed."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        L = _lib.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        buf = (ctypes.c_char * 128)()
+        if self.rank == 0:
+            _lib.check(L.cas_nccl_unique_id(buf), "cas_nccl_unique_id")
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=0)
+        ident = bytes(t.cpu().tolist())
+        self.handle = ctypes.c_void_p()
+        _lib.check(L.cas_nccl_comm_create(ident, self.rank, self.world, ctypes.byref(self.handle)),
+                   "cas_nccl_comm_create")
+
+    def close(self):
+        if self.handle:
+            _lib.load().cas_nccl_comm_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+def sharded_solve(shard, n: int, algo: str, group: NcclGroup, max_iters: int = -1):
+    """Runs the sharded loop on this rank's shard ([capacity, ld] CUDA tensor, destroyed).
+    Every rank returns the same (joins, last2)."""
+    torch = engine._torch()
+    L = _lib.load()
+    ld = int(shard.stride(0))
+    code = CAS_F64 if shard.dtype == torch.float64 else CAS_F32
+    ws_bytes = int(L.cas_sharded_workspace_bytes(int(n), group.world, code))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    njoin = max(int(n) - 2, 0)
+    joins = torch.full((njoin + 1, 2), -1, dtype=torch.int32, device="cuda")
+    last2 = torch.full((2,), -1, dtype=torch.int32, device="cuda")
+    rc = L.cas_sharded_solve(shard.data_ptr(), int(n), ld, code, CAS_ALGO_NJ if algo == "nj" else CAS_ALGO_UPGMA,
+                             int(max_iters), group.rank, group.world, group.handle, joins.data_ptr(),
+                             last2.data_ptr(), ws.data_ptr(), ws_bytes, engine._stream_ptr(torch))
+    _lib.check(rc, "cas_sharded_solve")
+    done = njoin if max_iters < 0 else min(njoin, int(max_iters))
+    return joins[:done].cpu().numpy(), last2.cpu().numpy()
+
+
+# ---- bench.py entry for --gpus N > 1 ------------------------------------------------------------
+def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
+    import torch
+    import torch.distributed as dist
+
+    import bench
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    group = NcclGroup()
+    dt = "f32"
+    codes, missing_code, table, n_states = bench.make_workload(args)
+    n = codes.shape[0]
+    cm_dev = torch.from_numpy(codes).cuda()
+    launches = [0]
+
+    def step():
+        shard = build_shard(cm_dev, missing_code, table, n_states, rank, world, dt)
+        launches[0] += engine.last_launch_count()
+        mid = torch.cuda.Event(enable_timing=True)
+        mid.record()
+        joins, last2 = sharded_solve(shard, n, "nj", group)
+        launches[0] += engine.last_launch_count()
+        return joins, last2, mid
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches[0] = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    mids, ends = [], []
+    for _ in range(args.steps):
+        joins, last2, mid = step()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        mids.append(mid)
+        ends.append(e)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop()
+    total_ms = ev0.elapsed_time(ev1)
+    loop_ms = float(np.mean([m.elapsed_time(e) for m, e in zip(mids, ends)]))
+    t = torch.tensor([total_ms, loop_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, loop_ms = float(t[0]), float(t[1])
+    # every rank must hold the same join list
+    h = torch.tensor([int(np.int64(joins.astype(np.int64).sum())), int(joins[-1, 0])], dtype=torch.int64, device="cuda")
+    hmax, hmin = h.clone(), h.clone()
+    dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+    assert torch.equal(hmax, hmin), "ranks disagree on the join list"
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_per_step = total_ms / args.steps
+        b_alg = scan_bytes(n, 4)
+        achieved = b_alg / (loop_ms * 1e-3) / 1e9
+        out = {
+            "metric": metric, "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": dt, "data": "synthetic",
+            "config": workload_config(args, world, "fast/exact-map"),
+            "clocks": clocks, "gpu_launches": int(launches[0]),
+            "roofline": {"bound": "hbm", "kernel": "sh_scan_kernel<float,NJ>", "achieved": achieved,
+                         "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
+                         "peak_source": peak_src + f" x {world} GPUs", "loop_ms": loop_ms,
+                         "collectives_per_iteration": "2 NCCL all-gathers (24 B x G candidates; 3 rows x k x 4 B)"},
+            "e2e": {"value": ms_per_step / 1e3, "unit": "s",
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(joins.nbytes + last2.nbytes),
+                    "note": "sharded path: character matrix replicated on the devices before the timed region; "
+                            "join list read back to the host every step"},
+        }
+        print(json.dumps(out), flush=True)
+    group.close()
+    dist.destroy_process_group()

@@ -111,6 +111,33 @@ CAS_API int cas_nj_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int3
 CAS_API int cas_upgma_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int32_t mode,
                     int64_t max_iters, int32_t *joins_dev, int32_t *last2_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);
+/* ---- row-sharded loop (n^2 map larger than one GPU; no reference counterpart) ----------
+ * Slots are dealt to ranks in 64-row blocks, block-cyclically; a rank stores its rows in local
+ * order, [cas_sharded_local_capacity(n, world), ld].  cas_whd_map_cyclic fills such a shard
+ * (every rank needs only the replicated character matrix: no exchange).  cas_sharded_solve runs
+ * the fast-mode loop with one NCCL all-gather of the ranks' candidates and one of the rows
+ * (lo, hi, last) per iteration; every rank receives the full, identical join list.
+ * cas_sharded_solve_emulated runs all `world` virtual ranks in one process on one GPU with no
+ * collective (shared gather buffers) -- the same kernels, used to test the sharded path. */
+CAS_API int64_t cas_sharded_local_rows(int64_t n, int32_t rank, int32_t world);
+CAS_API int64_t cas_sharded_local_capacity(int64_t n, int32_t world);
+CAS_API size_t cas_sharded_workspace_bytes(int64_t n, int32_t world, int32_t dtype);
+CAS_API int cas_whd_map_cyclic(const int32_t *cm_dev, int64_t n, int32_t m, int32_t missing,
+                       const double *w_dev, int32_t n_states, void *D_local_dev, int64_t ld,
+                       int32_t dtype, int32_t rank, int32_t world, int32_t method,
+                       void *workspace_dev, size_t workspace_bytes, void *stream);
+CAS_API int cas_nccl_unique_id(void *out128);
+CAS_API int cas_nccl_comm_create(const void *id128, int32_t rank, int32_t world, void **comm_out);
+CAS_API int cas_nccl_comm_destroy(void *comm);
+CAS_API int cas_sharded_solve(void *D_local_dev, int64_t n, int64_t ld, int32_t dtype, int32_t algo,
+                      int64_t max_iters, int32_t rank, int32_t world, void *nccl_comm,
+                      int32_t *joins_dev, int32_t *last2_dev, void *workspace_dev,
+                      size_t workspace_bytes, void *stream);
+CAS_API int cas_sharded_solve_emulated(void *const *D_locals_dev, int64_t n, int64_t ld, int32_t dtype,
+                               int32_t algo, int64_t max_iters, int32_t world, int32_t *joins_dev,
+                               int32_t *last2_dev, void *const *workspaces_dev,
+                               size_t workspace_bytes, void *stream);
+
 /* ---- single-step hooks (float64, reference operation order) -----------------
  * cas_nj_q       : Q[n,n] (zero diagonal) of NeighborJoiningSolver.compute_q
  *                  (cassiopeia/solver/NeighborJoiningSolver.py:142-171); rowsum_scratch = n doubles.
