@@ -88,13 +88,10 @@ def whd_map(cm, missing: int, weights: Optional[np.ndarray], n_states: int, dtyp
                        int(n_states), out.data_ptr(), ld, CAS_F64 if dtype == "f64" else CAS_F32,
                        r0, r1, code, ws.data_ptr(), ws_bytes, _stream_ptr(torch))
     _lib.check(rc, "cas_whd_map")
-    if method == "exact":
-        # first int of the workspace: "state outside [0, n_states]" flag set by the encode kernel
-        flag = int(ws[:4].view(torch.int32).item())
-        if flag:
-            raise ValueError("character matrix holds a state outside [0, n_states] that is not the missing indicator")
-    else:
-        torch.cuda.current_stream().synchronize()
+    # first int of the workspace: "state outside [0, n_states]" flag set by the encode kernels
+    flag = int(ws[:4].view(torch.int32).item())
+    if flag:
+        raise ValueError("character matrix holds a state outside [0, n_states] that is not the missing indicator")
     return out
 
 
