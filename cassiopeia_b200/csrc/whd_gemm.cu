@@ -4,25 +4,25 @@
 // whd_exact.cu (cassiopeia/solver/dissimilarity_functions.py:46-72 over all pairs).
 //
 // Unweighted ("plain Hamming", costs 0/1/2) -- kind::i8, int32 accumulation, EXACT:
-//   per cell one row of A and one of B, K = m*(S+3) int8 columns
-//     A = [ U | P | -2 X | 64 P ]      B = [ P | U | X | 64 P ]
+//   per cell one row of A and one of B, K = m*(S+2) int8 columns
+//     A = [ U | P | -2 X ]      B = [ P | U | X ]
 //   P = present, U = present & cut, X = one-hot over (character, cut state).  Then
-//     acc_ij = (U.P + P.U - 2 X.X) + 4096 * (P.P) = numerator + 4096 * shared_present
-//   (numerator <= 2m < 4096), so one accumulator yields both; D = num / den in IEEE
-//   arithmetic => bit-identical to the reference.
+//     acc_ij = U.P + P.U - 2 X.X = the integer numerator; the shared-present count is
+//   popcount(mask_i & mask_j) of the cells' presence bit masks in the epilogue; D = num / den
+//   in IEEE arithmetic => bit-identical to the reference.
 // Weighted (mutation priors) -- kind::f16 (bf16 x bf16 -> fp32), cancellation-free form
 //     num_ij = sum_{c,s} Xw_i[c,s] * Y_j[c,s] + Y_i[c,s] * Xw_j[c,s],   Y = present & (state != s)
 //   every term is >= 0.  The float64 weight is split into three bf16 planes (hi, mid, lo:
 //   24 significant bits); each plane has its own fp32 accumulator in TMEM (a product with the
 //   exact 0/1 operand is exact, and a plane's partial sums stay within fp32's 24 bits for
-//   realistic weight ranges), the planes are added in float64 in the epilogue, and the
-//   denominator P.P is a fourth accumulator.  Relative error vs the exact kernel <= 1e-6
-//   (tests/test_gpu_gemm.py).
+//   realistic weight ranges) and the planes are added in float64 in the epilogue.  Relative
+//   error vs the exact kernel <= 1e-6 (tests/test_gpu_gemm.py).
 //
-// Kernel: one CTA per 128x128 lower-triangle output tile, 6 warps: warp 0 = TMA producer,
-// warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue (TMEM -> registers
-// -> D, mirrored).  K is walked in 128-byte chunks (4 MMAs each) through a 4-stage
-// full/empty mbarrier ring.
+// Kernel: one CTA per 128x128 lower-triangle output tile (tiles rasterised in bands of 12 tile
+// rows, column-major inside a band, so concurrently running CTAs share operand blocks in L2),
+// 6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5
+// = epilogue (TMEM -> registers -> D, mirrored).  K is walked in 128-byte chunks (4 MMAs each)
+// through a full/empty mbarrier ring (3 stages and 2 CTAs per SM for int8, 5 stages for bf16).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -33,27 +33,21 @@ namespace cas {
 constexpr int GT = 128;            // tile edge (UMMA M = N = 128)
 constexpr int CHUNK_BYTES = 128;   // K bytes per pipeline stage row (one swizzle atom)
 constexpr int TILE_BYTES = GT * CHUNK_BYTES;  // 16 KB per operand tile
-constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;
-constexpr int MAX_SEGS = 8;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int SLOTS = 9;            // operand-tile ring (16 KB each)
+constexpr int MAXPW = 8;           // presence-mask words per cell (m <= 512)
+constexpr int BAND = 12;           // tile rows per rasterisation band
 constexpr int MAX_MAPS = 5;
-
-struct GemmSeg {
-  int map_a, map_b;  // tensor-map indices of the A / B operand matrices
-  int chunks;        // number of 128-byte K chunks
-  int acc;           // accumulator index (TMEM column block of 128)
-};
 
 struct GemmParams {
   CUtensorMap maps[MAX_MAPS];
-  GemmSeg segs[MAX_SEGS];
-  int nsegs;
-  int kind_i8;   // 1: kind::i8 (int32 acc)  0: kind::f16 bf16 (fp32 acc)
-  int naccs;     // accumulators in use (1 or 4)
+  int chunks;    // 128-byte K chunks per operand row
+  int ntile_rows;
+  int pw;        // presence-mask words per cell
+  const unsigned long long *pmask;  // [n, pw]
   int64_t n;
   void *D;
   int64_t ld;
-  int out_f64;
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------
@@ -137,39 +131,98 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Per-K-chunk program: which operand tiles are loaded (tensor map, row block I or column block J)
+// and which MMAs consume them.  Unweighted: A[I] x B[J].  Weighted: the one-hot "differs" operand Y
+// is loaded once per side and shared by the three weight planes -- 8 loads feed 6 MMA groups
+// (12 loads if every MMA group fetched its own pair), which matters because this kernel is bound
+// by L2->SM bandwidth, not by the tensor pipe.
+template <bool I8> struct Prog;
+template <> struct Prog<true> {
+  static constexpr int NL = 2, NM = 1;
+  __device__ static __forceinline__ int load_map(int l) { return l; }
+  __device__ static __forceinline__ int load_side(int l) { return l; }  // 0 = rows I, 1 = columns J
+  __device__ static __forceinline__ int mma_a(int) { return 0; }
+  __device__ static __forceinline__ int mma_b(int) { return 1; }
+  __device__ static __forceinline__ int mma_acc(int) { return 0; }
+  __device__ static __forceinline__ unsigned release(int) { return 0x3u; }
+};
+template <> struct Prog<false> {
+  // maps: 0..2 = Xw planes, 3 = Y.  loads: 0 Y[J] | 1..3 Xw_p[I] | 4 Y[I] | 5..7 Xw_p[J]
+  static constexpr int NL = 8, NM = 6;
+  __device__ static __forceinline__ int load_map(int l) { return l == 0 || l == 4 ? 3 : (l < 4 ? l - 1 : l - 5); }
+  __device__ static __forceinline__ int load_side(int l) { return (l == 0 || l >= 5) ? 1 : 0; }
+  __device__ static __forceinline__ int mma_a(int m) { return m < 3 ? m + 1 : 4; }
+  __device__ static __forceinline__ int mma_b(int m) { return m < 3 ? 0 : m + 2; }
+  __device__ static __forceinline__ int mma_acc(int m) { return m % 3; }
+  // operand tiles whose last consumer is MMA group m (bit l = load l)
+  __device__ static __forceinline__ unsigned release(int m) {
+    return m == 0 ? 0x02u : m == 1 ? 0x04u : m == 2 ? 0x09u : m == 3 ? 0x20u : m == 4 ? 0x40u : 0x90u;
+  }
+};
+
+template <typename TO>
 struct __align__(1024) GemmSmem {
-  uint8_t a[STAGES][TILE_BYTES];
-  uint8_t b[STAGES][TILE_BYTES];
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
-  uint64_t tmem_full;
+  static constexpr int HALF = sizeof(TO) == 4 ? 64 : 32;  // columns staged at a time per warp
+  uint8_t tile[SLOTS][TILE_BYTES];
+  TO stage[8][32][HALF + 1];         // per-epilogue-warp transpose tile for the direct stores
+  unsigned long long pm[GT][MAXPW];  // presence masks of the tile's columns
+  uint64_t full[SLOTS];
+  uint64_t empty[SLOTS];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
   uint32_t tmem_base;
 };
 
-template <bool I8, typename TO>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  GemmSmem &sm = *reinterpret_cast<GemmSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// linear tile index -> lower-triangle tile (ti >= tj): bands of BAND tile rows, column-major in a band
+__device__ __forceinline__ void tile_of(int64_t t, int T, int &ti, int &tj) {
+  int b0 = 0;
+  for (;;) {
+    const int hb = min(BAND, T - b0);
+    const int64_t cnt = (int64_t)b0 * hb + (int64_t)hb * (hb + 1) / 2;
+    if (t < cnt) {
+      const int64_t full = (int64_t)b0 * hb;
+      if (t < full) {
+        tj = (int)(t / hb);
+        ti = b0 + (int)(t % hb);
+      } else {
+        int64_t rem = t - full;
+        int c = 0;
+        while (rem >= hb - c) { rem -= hb - c; ++c; }
+        tj = b0 + c;
+        ti = b0 + c + (int)rem;
+      }
+      return;
+    }
+    t -= cnt;
+    b0 += hb;
+  }
+}
 
-  // lower-triangle tile (ti >= tj)
-  int64_t t = blockIdx.x;
-  int64_t r = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((r + 1) * (r + 2) / 2 <= t) ++r;
-  while (r * (r + 1) / 2 > t) --r;
-  const int ti = (int)r, tj = (int)(t - r * (r + 1) / 2);
-  const int row0 = ti * GT, col0 = tj * GT;
-  const uint32_t tmem_cols = p.naccs * GT;  // 128 or 512 (power of two >= 32)
+// Persistent kernel, one CTA per SM.  NACC accumulator buffers in TMEM: 2 for int8 (the epilogue of
+// tile t overlaps the MMAs of tile t+1), 1 for bf16 (3 planes x 128 columns leave no room for a
+// second set; the TMA producer still runs ahead into the next tile during the epilogue).
+template <bool I8, typename TO, int PW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using P = Prog<I8>;
+  constexpr int NACC = I8 ? 2 : 1;
+  constexpr int ACCW = (I8 ? 1 : 3) * GT;           // TMEM columns per accumulator buffer
+  constexpr uint32_t TMEM_COLS = I8 ? 256u : 512u;  // power of two >= NACC * ACCW
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  GemmSmem<TO> &sm = *reinterpret_cast<GemmSmem<TO> *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (int64_t)p.ntile_rows * (p.ntile_rows + 1) / 2;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    mbar_init(&sm.tmem_full, 1);
+    for (int s = 0; s < SLOTS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < (I8 ? 2 : 4); ++i)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[i]) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&sm.tmem_base)),
-                 "r"(tmem_cols)
+                 "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -179,19 +232,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
   const uint32_t tmem_base = sm.tmem_base;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: one operand tile per ring slot =====
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int sg = 0; sg < p.nsegs; ++sg) {
-        const GemmSeg seg = p.segs[sg];
-        const int elems_per_chunk = I8 ? CHUNK_BYTES : CHUNK_BYTES / 2;
-        for (int c = 0; c < seg.chunks; ++c) {
-          mbar_wait(&sm.empty[stage], phase ^ 1);
-          mbar_expect_tx(&sm.full[stage], 2 * TILE_BYTES);
-          tma_load_2d(sm.a[stage], &p.maps[seg.map_a], &sm.full[stage], c * elems_per_chunk, row0);
-          tma_load_2d(sm.b[stage], &p.maps[seg.map_b], &sm.full[stage], c * elems_per_chunk, col0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      uint32_t lc = 0;  // loads issued so far
+      const int elems_per_chunk = I8 ? CHUNK_BYTES : CHUNK_BYTES / 2;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int ti, tj;
+        tile_of(tile, p.ntile_rows, ti, tj);
+        const int row0 = ti * GT, col0 = tj * GT;
+        for (int c = 0; c < p.chunks; ++c) {
+#pragma unroll
+          for (int l = 0; l < P::NL; ++l, ++lc) {
+            const uint32_t slot = lc % SLOTS, phase = (lc / SLOTS) & 1u;
+            mbar_wait(&sm.empty[slot], phase ^ 1u);
+            mbar_expect_tx(&sm.full[slot], TILE_BYTES);
+            tma_load_2d(sm.tile[slot], &p.maps[P::load_map(l)], &sm.full[slot], c * elems_per_chunk,
+                        P::load_side(l) ? col0 : row0);
+          }
         }
       }
     }
@@ -202,85 +259,133 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
       // (BF16 = 1, signed int8 = 1), K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = ((I8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GT >> 3) << 17) |
                              ((uint32_t)(GT >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t started = 0;  // bit a set once accumulator a holds data
-      for (int sg = 0; sg < p.nsegs; ++sg) {
-        const GemmSeg seg = p.segs[sg];
-        const uint32_t tmem_d = tmem_base + (uint32_t)(seg.acc * GT);
-        for (int c = 0; c < seg.chunks; ++c) {
-          mbar_wait(&sm.full[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sm.a[stage]));
-          const uint64_t bdesc = make_smem_desc(smem_u32(sm.b[stage]));
+      uint32_t lc0 = 0;  // load counter of the current chunk's first load
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int as = (int)(it % NACC);
+        const uint32_t aphase = (uint32_t)((it / NACC) & 1);
+        mbar_wait(&sm.tempty[as], aphase ^ 1);  // epilogue has drained this accumulator buffer
+        tcgen05_fence_after();
+        for (int c = 0; c < p.chunks; ++c, lc0 += P::NL) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            // advance 32 bytes of K inside the swizzle atom: +2 in the (>>4) start-address field
-            umma<I8>(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                     ((started >> seg.acc) & 1u) | (kk > 0 ? 1u : 0u));
+          for (int m = 0; m < P::NM; ++m) {
+            const uint32_t la = lc0 + P::mma_a(m), lb = lc0 + P::mma_b(m);
+            const uint32_t sa = la % SLOTS, sb = lb % SLOTS;
+            mbar_wait(&sm.full[sa], (la / SLOTS) & 1u);
+            mbar_wait(&sm.full[sb], (lb / SLOTS) & 1u);
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_u32(sm.tile[sa]));
+            const uint64_t bdesc = make_smem_desc(smem_u32(sm.tile[sb]));
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACCW + P::mma_acc(m) * GT);
+            const bool first = (c == 0) && (m < (I8 ? 1 : 3));  // first MMA group into this accumulator
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              // advance 32 bytes of K inside the swizzle atom: +2 in the (>>4) start-address field
+              umma<I8>(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                       (first && kk == 0) ? 0u : 1u);
+            }
+            // free the operand tiles whose last consumer was this MMA group
+#pragma unroll
+            for (int l = 0; l < P::NL; ++l)
+              if ((P::release(m) >> l) & 1u) tcgen05_commit(&sm.empty[(lc0 + l) % SLOTS]);
           }
-          started |= 1u << seg.acc;
-          tcgen05_commit(&sm.empty[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        tcgen05_commit(&sm.tfull[as]);
       }
-      tcgen05_commit(&sm.tmem_full);
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +32 =====
-    mbar_wait(&sm.tmem_full, 0);
-    tcgen05_fence_after();
+    // ===== epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).. and the column half (w-2)/4 =====
+    constexpr int HALF = GemmSmem<TO>::HALF;
     const int q = warp & 3;
-    const int lrow = q * 32 + lane;            // row inside the tile == TMEM lane
-    const int64_t gi = (int64_t)row0 + lrow;   // global row
+    const int ch = (warp - 2) >> 2;        // which 64 columns of the tile
+    const int lrow = q * 32 + lane;        // row inside the tile == TMEM lane
+    const int et = threadIdx.x - 64;       // 0..255
     TO *__restrict__ D = static_cast<TO *>(p.D);
-    const bool diag_tile = (ti == tj);
-    for (int cb = 0; cb < GT; cb += 16) {
-      uint32_t v0[16], v1[16], v2[16], v3[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
-      tmem_ld16(taddr, v0);
-      if (!I8) {
-        tmem_ld16(taddr + GT, v1);
-        tmem_ld16(taddr + 2 * GT, v2);
-        tmem_ld16(taddr + 3 * GT, v3);
+    TO(*stage)[HALF + 1] = sm.stage[warp - 2];
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      int ti, tj;
+      tile_of(tile, p.ntile_rows, ti, tj);
+      const int row0 = ti * GT, col0 = tj * GT;
+      const int64_t gi = (int64_t)row0 + lrow;  // global row
+      const bool diag_tile = (ti == tj);
+      const bool whole = (int64_t)row0 + GT <= p.n && (int64_t)col0 + GT <= p.n;
+      // presence masks: this thread's row in registers, the tile's columns in shared memory
+      unsigned long long mrow[PW];
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with sm.pm
+#pragma unroll
+      for (int w = 0; w < PW; ++w) mrow[w] = gi < p.n ? p.pmask[gi * PW + w] : 0ull;
+      if (et < GT) {
+        const int64_t gj = (int64_t)col0 + et;
+#pragma unroll
+        for (int w = 0; w < PW; ++w) sm.pm[et][w] = gj < p.n ? p.pmask[gj * PW + w] : 0ull;
       }
-      tmem_ld_wait();
-      TO out[16];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int as = (int)(it % NACC);
+      mbar_wait(&sm.tfull[as], (uint32_t)((it / NACC) & 1));
+      tcgen05_fence_after();
+      // The accumulator row of a lane is written twice: mirrored (column gi of rows gj: the 32 lanes
+      // hit 32 consecutive addresses) straight from registers, and direct (row gi) through the
+      // warp's transpose tile so that those stores are coalesced too.
+      for (int part = 0; part < 64; part += HALF) {
+        const int cbase = ch * 64 + part;
+        for (int cb = cbase; cb < cbase + HALF; cb += 16) {
+          uint32_t v0[16], v1[16], v2[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACCW + cb);
+          tmem_ld16(taddr, v0);
+          if (!I8) {
+            tmem_ld16(taddr + GT, v1);
+            tmem_ld16(taddr + 2 * GT, v2);
+          }
+          tmem_ld_wait();
+          TO *mir = D + ((int64_t)col0 + cb) * p.ld + gi;  // element (gj0, gi), next column = + ld
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        double num, den;
-        if (I8) {
-          const int acc = (int)v0[e];
-          den = (double)(acc >> 12);
-          num = (double)(acc & 4095);
-        } else {
-          num = ((double)__uint_as_float(v0[e]) + (double)__uint_as_float(v1[e])) + (double)__uint_as_float(v2[e]);
-          den = (double)__uint_as_float(v3[e]);
+          for (int e = 0; e < 16; ++e) {
+            int den = 0;
+#pragma unroll
+            for (int w = 0; w < PW; ++w) den += __popcll(mrow[w] & sm.pm[cb + e][w]);
+            double num;
+            if (I8) num = (double)(int)v0[e];
+            else num = ((double)__uint_as_float(v0[e]) + (double)__uint_as_float(v1[e])) + (double)__uint_as_float(v2[e]);
+            TO d = (TO)0;
+            if (den > 0) {
+              if (sizeof(TO) == 8) {
+                d = (TO)__ddiv_rn(num, (double)den);
+              } else if (I8) {
+                // small integers: the correctly rounded float quotient equals fl32(fl64(num/den))
+                d = (TO)__fdiv_rn((float)num, (float)den);
+              } else {
+                d = (TO)__double2float_rn(__ddiv_rn(num, (double)den));
+              }
+            }
+            if (diag_tile && (cb + e == lrow)) d = (TO)0;
+            stage[lane][(cb - cbase) + e] = d;
+            if (!diag_tile && (whole || (gi < p.n && (int64_t)col0 + cb + e < p.n))) mir[(int64_t)e * p.ld] = d;
+          }
         }
-        double d = den > 0.0 ? __ddiv_rn(num, den) : 0.0;
-        if (diag_tile && (cb + e == lrow)) d = 0.0;
-        out[e] = (TO)d;
-      }
-      if (gi < p.n) {
-        const int64_t gj0 = (int64_t)col0 + cb;
-        TO *dst = D + gi * p.ld + gj0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (gj0 + e < p.n) dst[e] = out[e];
-        if (!diag_tile) {
-          // mirrored element (gj, gi): the 32 lanes of a warp write 32 consecutive columns
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (gj0 + e < p.n) D[(gj0 + e) * p.ld + gi] = out[e];
+        if (part + HALF == 64) {
+          // all TMEM reads of this tile are done: hand the accumulator buffer back to the MMA warp
+          tcgen05_fence_before();
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.tempty[as])) : "memory");
         }
+        __syncwarp();
+        // direct rows: lane l writes columns l (+32) of each of the warp's 32 rows
+        TO *dst = D + ((int64_t)row0 + q * 32) * p.ld + col0 + cbase;
+        for (int rr = 0; rr < 32; ++rr, dst += p.ld) {
+          if (!whole && (int64_t)row0 + q * 32 + rr >= p.n) break;
+#pragma unroll
+          for (int h = 0; h < HALF; h += 32)
+            if (whole || (int64_t)col0 + cbase + h + lane < p.n) dst[h + lane] = stage[rr][h + lane];
+        }
+        __syncwarp();
       }
     }
-    tcgen05_fence_before();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
 }
@@ -306,16 +411,27 @@ __global__ void encode_i8_kernel(const int32_t *__restrict__ cm, int64_t n, int 
     a[k] = -2;
     b[k] = 1;                                          // -2 X . X
   }
-  const int64_t kd = 2 * (int64_t)m + (int64_t)m * S + c;
-  a[kd] = 64;
-  b[kd] = 64;                                          // 4096 * P . P
+}
+
+// presence bit masks: one thread per (cell, 64-character word)
+__global__ void encode_mask_kernel(const int32_t *__restrict__ cm, int64_t n, int m, int pw, int32_t missing,
+                                   unsigned long long *__restrict__ pmask) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * pw) return;
+  const int64_t i = idx / pw;
+  const int w = (int)(idx - i * pw);
+  unsigned long long bits = 0;
+  for (int b = 0; b < 64; ++b) {
+    const int c = w * 64 + b;
+    if (c < m && cm[i * m + c] != missing) bits |= 1ull << b;
+  }
+  pmask[idx] = bits;
 }
 
 __global__ void encode_bf16_kernel(const int32_t *__restrict__ cm, int64_t n, int m, int S, int32_t missing,
                                    const double *__restrict__ w, __nv_bfloat16 *__restrict__ XW0,
                                    __nv_bfloat16 *__restrict__ XW1, __nv_bfloat16 *__restrict__ XW2,
-                                   __nv_bfloat16 *__restrict__ Y, __nv_bfloat16 *__restrict__ P, int64_t Kx,
-                                   int64_t Kd, int *__restrict__ err_flag) {
+                                   __nv_bfloat16 *__restrict__ Y, int64_t Kx, int *__restrict__ err_flag) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * m) return;
   const int64_t i = idx / m;
@@ -323,7 +439,6 @@ __global__ void encode_bf16_kernel(const int32_t *__restrict__ cm, int64_t n, in
   const int32_t s = cm[idx];
   if (s == missing) return;
   if (s < 0 || s > S) { atomicExch(err_flag, 1); return; }
-  P[i * Kd + c] = __float2bfloat16(1.0f);
   __nv_bfloat16 *y = Y + i * Kx + (int64_t)c * S;
   const __nv_bfloat16 one = __float2bfloat16(1.0f);
   for (int t = 0; t < S; ++t)
@@ -385,7 +500,7 @@ struct GemmLayout {
 
 static GemmLayout layout_of(int m, int S) {
   GemmLayout L;
-  L.Kp = round_up64((int64_t)m * (S + 3), CHUNK_BYTES);
+  L.Kp = round_up64((int64_t)m * (S + 2), CHUNK_BYTES);
   L.Kx = round_up64((int64_t)m * S, CHUNK_BYTES / 2);
   L.Kd = round_up64(m, CHUNK_BYTES / 2);
   return L;
@@ -396,12 +511,12 @@ size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t 
   GemmLayout L = layout_of(m, S);
   Carver c(nullptr);
   c.take<int>(64);
+  c.take<unsigned long long>((size_t)n * 8);
   if (!weighted) {
     c.take<int8_t>((size_t)n * L.Kp);
     c.take<int8_t>((size_t)n * L.Kp);
   } else {
     for (int i = 0; i < 4; ++i) c.take<__nv_bfloat16>((size_t)n * L.Kx);
-    c.take<__nv_bfloat16>((size_t)n * L.Kd);
   }
   return c.used();
 }
@@ -415,7 +530,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     set_error("CAS_MAP_TENSOR computes the whole map only (use CAS_MAP_EXACT for row blocks)");
     return CAS_ERR_UNSUPPORTED;
   }
-  CAS_REQUIRE(m < 2048, "CAS_MAP_TENSOR supports at most 2047 characters (m=%d)", m);
+  CAS_REQUIRE(m <= 64 * MAXPW, "CAS_MAP_TENSOR supports at most %d characters (m=%d)", 64 * MAXPW, m);
   CAS_REQUIRE(workspace_bytes >= whd_gemm_workspace_bytes(n, m, n_states, weighted), "workspace too small");
   GemmLayout L = layout_of(m, S);
   Carver carve(workspace);
@@ -424,9 +539,16 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.n = n; p.D = D; p.ld = ld; p.out_f64 = (dtype == CAS_F64);
+  p.n = n; p.D = D; p.ld = ld;
   const int64_t nm = n * (int64_t)m;
   const unsigned eb = (unsigned)((nm + 255) / 256);
+  int pw = (m + 63) / 64;
+  pw = pw <= 2 ? pw : (pw <= 4 ? 4 : 8);  // kernel templates: 1, 2, 4 or 8 words per cell
+  unsigned long long *pmask = carve.take<unsigned long long>((size_t)n * pw);
+  encode_mask_kernel<<<(unsigned)((n * pw + 255) / 256), 256, 0, stream>>>(cm, n, m, pw, missing, pmask);
+  CAS_LAUNCH_CHECK();
+  p.pw = pw; p.pmask = pmask;
+  p.ntile_rows = (int)((n + GT - 1) / GT);
   if (!weighted) {
     int8_t *A = carve.take<int8_t>((size_t)n * L.Kp);
     int8_t *B = carve.take<int8_t>((size_t)n * L.Kp);
@@ -438,20 +560,14 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     if (rc != CAS_OK) return rc;
     rc = make_map(&p.maps[1], B, n, L.Kp, 1);
     if (rc != CAS_OK) return rc;
-    p.nsegs = 1;
-    p.segs[0] = GemmSeg{0, 1, (int)(L.Kp / CHUNK_BYTES), 0};
-    p.kind_i8 = 1;
-    p.naccs = 1;
+    p.chunks = (int)(L.Kp / CHUNK_BYTES);
   } else {
     __nv_bfloat16 *XW[3];
     for (int i = 0; i < 3; ++i) XW[i] = carve.take<__nv_bfloat16>((size_t)n * L.Kx);
     __nv_bfloat16 *Y = carve.take<__nv_bfloat16>((size_t)n * L.Kx);
-    __nv_bfloat16 *P = carve.take<__nv_bfloat16>((size_t)n * L.Kd);
     for (int i = 0; i < 3; ++i) CAS_CUDA_TRY(cudaMemsetAsync(XW[i], 0, (size_t)n * L.Kx * 2, stream));
     CAS_CUDA_TRY(cudaMemsetAsync(Y, 0, (size_t)n * L.Kx * 2, stream));
-    CAS_CUDA_TRY(cudaMemsetAsync(P, 0, (size_t)n * L.Kd * 2, stream));
-    encode_bf16_kernel<<<eb, 256, 0, stream>>>(cm, n, m, S, missing, w, XW[0], XW[1], XW[2], Y, P, L.Kx, L.Kd,
-                                               err_flag);
+    encode_bf16_kernel<<<eb, 256, 0, stream>>>(cm, n, m, S, missing, w, XW[0], XW[1], XW[2], Y, L.Kx, err_flag);
     CAS_LAUNCH_CHECK();
     for (int i = 0; i < 3; ++i) {
       int rc = make_map(&p.maps[i], XW[i], n, L.Kx, 2);
@@ -459,34 +575,32 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     }
     int rc = make_map(&p.maps[3], Y, n, L.Kx, 2);
     if (rc != CAS_OK) return rc;
-    rc = make_map(&p.maps[4], P, n, L.Kd, 2);
-    if (rc != CAS_OK) return rc;
-    const int chunks = (int)(L.Kx / (CHUNK_BYTES / 2));
-    int sgi = 0;
-    for (int pl = 0; pl < 3; ++pl) {
-      p.segs[sgi++] = GemmSeg{pl, 3, chunks, pl};  // Xw_p[I] . Y[J]
-      p.segs[sgi++] = GemmSeg{3, pl, chunks, pl};  // Y[I] . Xw_p[J]
-    }
-    p.segs[sgi++] = GemmSeg{4, 4, (int)(L.Kd / (CHUNK_BYTES / 2)), 3};  // P[I] . P[J]
-    p.nsegs = sgi;
-    p.kind_i8 = 0;
-    p.naccs = 4;
+    p.chunks = (int)(L.Kx / (CHUNK_BYTES / 2));
   }
   const int64_t tiles = (n + GT - 1) / GT;
   const int64_t ntiles = tiles * (tiles + 1) / 2;
   CAS_REQUIRE(ntiles < 2147483647LL, "too many tiles");
-  const size_t smem = sizeof(GemmSmem) + 1024;
-#define LAUNCH_GEMM(I8, TO)                                                                        \
+#define LAUNCH_GEMM(I8, TO, PWV)                                                                   \
   do {                                                                                             \
-    CAS_CUDA_TRY(cudaFuncSetAttribute(whd_gemm_kernel<I8, TO>,                                     \
+    const size_t smem = sizeof(GemmSmem<TO>) + 1024;                                               \
+    CAS_CUDA_TRY(cudaFuncSetAttribute(whd_gemm_kernel<I8, TO, PWV>,                                \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    whd_gemm_kernel<I8, TO><<<(unsigned)ntiles, GEMM_THREADS, smem, stream>>>(p);                  \
+    const int64_t grid = ntiles < sm_count() ? ntiles : sm_count();                                \
+    whd_gemm_kernel<I8, TO, PWV><<<(unsigned)grid, GEMM_THREADS, smem, stream>>>(p);               \
+  } while (0)
+#define LAUNCH_PW(I8, TO)                                                                          \
+  do {                                                                                             \
+    if (pw == 1) LAUNCH_GEMM(I8, TO, 1);                                                           \
+    else if (pw == 2) LAUNCH_GEMM(I8, TO, 2);                                                      \
+    else if (pw <= 4) LAUNCH_GEMM(I8, TO, 4);                                                      \
+    else LAUNCH_GEMM(I8, TO, 8);                                                                   \
   } while (0)
   if (!weighted) {
-    if (dtype == CAS_F64) LAUNCH_GEMM(true, double); else LAUNCH_GEMM(true, float);
+    if (dtype == CAS_F64) LAUNCH_PW(true, double); else LAUNCH_PW(true, float);
   } else {
-    if (dtype == CAS_F64) LAUNCH_GEMM(false, double); else LAUNCH_GEMM(false, float);
+    if (dtype == CAS_F64) LAUNCH_PW(false, double); else LAUNCH_PW(false, float);
   }
+#undef LAUNCH_PW
 #undef LAUNCH_GEMM
   CAS_LAUNCH_CHECK();
   return CAS_OK;
