@@ -41,6 +41,14 @@ EXPORTS = (
     "cas_nccl_comm_destroy",
     "cas_sharded_solve",
     "cas_sharded_solve_emulated",
+    "cas_exchange_bytes",
+    "cas_exchange_alloc",
+    "cas_exchange_open",
+    "cas_exchange_close",
+    "cas_exchange_free",
+    "cas_exchange_error",
+    "cas_sharded_solve_p2p",
+    "cas_sharded_solve_emulated_p2p",
 )
 
 
@@ -93,6 +101,22 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_sharded_solve.argtypes = [vp, i64, i64, i32, i32, i64, i32, i32, vp, vp, vp, vp, sz, vp]
     L.cas_sharded_solve_emulated.restype = ctypes.c_int
     L.cas_sharded_solve_emulated.argtypes = [vp, i64, i64, i32, i32, i64, i32, vp, vp, vp, sz, vp]
+    u64 = ctypes.c_uint64
+    L.cas_exchange_bytes.restype = sz
+    L.cas_exchange_bytes.argtypes = [i64, i32, i32]
+    L.cas_exchange_alloc.restype = ctypes.c_int
+    L.cas_exchange_alloc.argtypes = [sz, ctypes.POINTER(vp), vp]
+    L.cas_exchange_open.restype = ctypes.c_int
+    L.cas_exchange_open.argtypes = [vp, ctypes.POINTER(vp)]
+    for fn in (L.cas_exchange_close, L.cas_exchange_free):
+        fn.restype = ctypes.c_int
+        fn.argtypes = [vp]
+    L.cas_exchange_error.restype = ctypes.c_int
+    L.cas_exchange_error.argtypes = [vp, vp, ctypes.POINTER(i32)]
+    L.cas_sharded_solve_p2p.restype = ctypes.c_int
+    L.cas_sharded_solve_p2p.argtypes = [vp, i64, i64, i32, i32, i64, i32, i32, vp, u64, vp, vp, vp, sz, vp]
+    L.cas_sharded_solve_emulated_p2p.restype = ctypes.c_int
+    L.cas_sharded_solve_emulated_p2p.argtypes = [vp, i64, i64, i32, i32, i64, i32, vp, u64, vp, vp, vp, sz, vp]
     L.cas_solve_host.restype = ctypes.c_int
     L.cas_solve_host.argtypes = [vp, i64, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]
 

@@ -22,6 +22,7 @@
 // already loaded), or none at all in the single-process emulation used to test the kernels on
 // one GPU (all virtual ranks share the gather buffers).
 #include <dlfcn.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <vector>
@@ -52,6 +53,37 @@ __host__ __device__ __forceinline__ int sh_chunk(int k, int G) {
   return ((nblocks + G - 1) / G) * SHB;
 }
 
+// ---- direct NVLink exchange (P2P): every rank owns an exchange buffer that its peers map
+// (cudaIpc) and write into with plain stores; iteration-tagged flags replace the collectives.
+constexpr int SH_MAXG = 16;
+struct ShExHeader {
+  unsigned long long flag1[SH_MAXG];  // flag1[r] = tag: rank r's candidate for that iteration has landed
+  unsigned long long flag2[SH_MAXG];  // flag2[r] = tag: rank r's rows (lo, hi, last) chunk has landed
+  Cand cand[SH_MAXG];
+  int error;                          // a spin-wait timed out
+  int pad[31];
+};
+static_assert(sizeof(ShExHeader) % 256 == 0, "exchange header must keep the gather area aligned");
+struct ShPeers {
+  char *ex[SH_MAXG];  // exchange buffers of all ranks (own one included); ex[0] == nullptr => no P2P
+};
+__device__ __forceinline__ ShExHeader *ex_header(char *ex) { return reinterpret_cast<ShExHeader *>(ex); }
+__device__ __forceinline__ char *ex_gath(char *ex) { return ex + sizeof(ShExHeader); }
+
+// spin until *flag >= tag (written by a peer GPU); gives up after ~2 s and records the failure
+__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long tag, int *error) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= tag) return;
+    if (clock64() - t0 > 4000000000LL) { atomicExch(error, 1); return; }
+  }
+}
+__device__ __forceinline__ void post_flag(unsigned long long *flag, unsigned long long tag) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(tag) : "memory");
+}
+
 struct ShScanArgs {
   const void *Dloc;
   int64_t ld;
@@ -64,7 +96,9 @@ struct ShScanArgs {
   const unsigned long long *rmax_bits;
   Cand *cand;       // per-CTA scratch
   unsigned *counter;
-  Cand *out;        // this rank's slot in the candidate gather buffer
+  Cand *out;        // this rank's slot in the candidate gather buffer (NCCL / shared-buffer modes)
+  ShPeers peers;    // P2P mode: publish the candidate to every rank
+  unsigned long long tag;
 };
 
 constexpr int SH_TR = 32;  // rows per scan tile (divides SHB, so a tile's slots are contiguous)
@@ -125,7 +159,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) sh_scan_kernel(ShScanArgs a) 
   if (!sLast) return;
   __threadfence();
   c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
-  if (threadIdx.x == 0) *a.out = c;
+  if (a.peers.ex[0] != nullptr) {
+    if (threadIdx.x < a.G) {
+      ShExHeader *h = ex_header(a.peers.ex[threadIdx.x]);
+      h->cand[a.r] = c;
+      __threadfence_system();
+      post_flag(&h->flag1[a.r], a.tag);
+    }
+  } else if (threadIdx.x == 0) {
+    *a.out = c;
+  }
 }
 
 struct ShColsArgs {
@@ -140,21 +183,58 @@ struct ShColsArgs {
   Sel *sel;
   int32_t *joins;
   int t;
+  ShPeers peers;
+  unsigned long long tag;
+  unsigned *counter;
 };
 
 template <typename T>
 __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
   __shared__ Cand sCand[8];
-  const Cand c = reduce_candidates(a.cand_all, a.G, sCand);
+  __shared__ bool sLast;
+  const bool p2p = a.peers.ex[0] != nullptr;
+  const Cand *cand_all = a.cand_all;
+  if (p2p) {
+    ShExHeader *own = ex_header(a.peers.ex[a.r]);
+    if (threadIdx.x < a.G) wait_flag(&own->flag1[threadIdx.x], a.tag, &own->error);
+    __syncthreads();
+    cand_all = own->cand;
+  }
+  const Cand c = reduce_candidates(cand_all, a.G, sCand);
   const int lo = min(c.si, c.sj), hi = max(c.si, c.sj), last = a.k - 1;
   const T *__restrict__ D = static_cast<const T *>(a.Dloc);
-  T *__restrict__ out = static_cast<T *>(a.mine);
   const int lr = blockIdx.x * 256 + threadIdx.x;
   if (lr < sh_count(a.k, a.r, a.G)) {
     const T *row = D + (int64_t)lr * a.ld;
-    out[lr] = row[lo];
-    out[a.chunk + lr] = row[hi];
-    out[2 * a.chunk + lr] = row[last];
+    const T va = row[lo], vb = row[hi], vl = row[last];
+    if (p2p) {
+      // write this rank's chunk straight into every rank's gather area over NVLink
+      for (int pr = 0; pr < a.G; ++pr) {
+        T *out = reinterpret_cast<T *>(ex_gath(a.peers.ex[pr])) + (size_t)a.r * 3 * a.chunk;
+        out[lr] = va;
+        out[a.chunk + lr] = vb;
+        out[2 * a.chunk + lr] = vl;
+      }
+    } else {
+      T *__restrict__ out = static_cast<T *>(a.mine);
+      out[lr] = va;
+      out[a.chunk + lr] = vb;
+      out[2 * a.chunk + lr] = vl;
+    }
+  }
+  if (p2p) {
+    // last block of this kernel signals "chunk landed" to every rank
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+      sLast = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sLast && threadIdx.x < a.G) {
+      __threadfence_system();
+      post_flag(&ex_header(a.peers.ex[threadIdx.x])->flag2[a.r], a.tag);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     Sel s;
@@ -184,6 +264,8 @@ struct ShMergeArgs {
   unsigned long long *rmax_bits;
   int new_id;
   int maintain_R;
+  ShPeers peers;
+  unsigned long long tag;
 };
 
 template <typename T, bool NJ>
@@ -191,7 +273,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
   __shared__ double sPart[MERGE_THREADS / 32];
   __shared__ bool sLast;
   T *__restrict__ D = static_cast<T *>(a.Dloc);
-  const T *__restrict__ g = static_cast<const T *>(a.gath);
+  const T *g = static_cast<const T *>(a.gath);
+  if (a.peers.ex[0] != nullptr) {
+    ShExHeader *own = ex_header(a.peers.ex[a.r]);
+    if (threadIdx.x < a.G) wait_flag(&own->flag2[threadIdx.x], a.tag, &own->error);
+    __syncthreads();
+    g = reinterpret_cast<const T *>(ex_gath(a.peers.ex[a.r]));
+  }
   const Sel s = *a.sel;
   const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1, G = a.G;
   const int64_t ld = a.ld;
@@ -275,20 +363,52 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
 // initial row sums of the local rows (same lane-strided order as rowsum_init_kernel)
 template <typename T>
 __global__ void __launch_bounds__(256) sh_rowsum_kernel(const T *__restrict__ D, int64_t ld, int k, int G,
-                                                        int r, double *__restrict__ mine) {
+                                                        int r, double *__restrict__ mine, int chunk,
+                                                        ShPeers peers, unsigned long long tag,
+                                                        unsigned *counter) {
+  __shared__ bool sLast;
   const int lr = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (lr >= sh_count(k, r, G)) return;
-  const T *__restrict__ row = D + (int64_t)lr * ld;
-  double s = 0.0;
-  for (int j = lane; j < k; j += 32) s = __dadd_rn(s, (double)row[j]);
+  const bool p2p = peers.ex[0] != nullptr;
+  if (lr < sh_count(k, r, G)) {
+    const T *__restrict__ row = D + (int64_t)lr * ld;
+    double s = 0.0;
+    for (int j = lane; j < k; j += 32) s = __dadd_rn(s, (double)row[j]);
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
-  if (lane == 0) mine[lr] = s;
+    for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+    if (lane == 0) {
+      if (p2p) {
+        for (int pr = 0; pr < G; ++pr)
+          (reinterpret_cast<double *>(ex_gath(peers.ex[pr])) + (size_t)r * chunk)[lr] = s;
+      } else {
+        mine[lr] = s;
+      }
+    }
+  }
+  if (p2p) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned prev = atomicInc(counter, gridDim.x - 1);
+      sLast = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sLast && threadIdx.x < G) {
+      __threadfence_system();
+      post_flag(&ex_header(peers.ex[threadIdx.x])->flag2[r], tag);
+    }
+  }
 }
 
-__global__ void sh_rscatter_kernel(const double *__restrict__ gath, int chunk, int k, int G,
-                                   double *__restrict__ R, unsigned long long *rmax_bits) {
+__global__ void sh_rscatter_kernel(const double *gath, int chunk, int k, int G, int r,
+                                   double *__restrict__ R, unsigned long long *rmax_bits, ShPeers peers,
+                                   unsigned long long tag) {
+  if (peers.ex[0] != nullptr) {
+    ShExHeader *own = ex_header(peers.ex[r]);
+    if (threadIdx.x < G) wait_flag(&own->flag2[threadIdx.x], tag, &own->error);
+    __syncthreads();
+    gath = reinterpret_cast<const double *>(ex_gath(peers.ex[r]));
+  }
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   double s = 0.0;
   if (v < k) {
@@ -410,13 +530,22 @@ struct ShRank {
 };
 
 // Runs the loop for the local virtual ranks `ranks` (one in real multi-process mode, G in the
-// emulation).  comm == nullptr => emulation: the ranks share ranks[0]'s gather buffers.
+// emulation).  Exchange modes:
+//   peers != nullptr : P2P -- kernels store into every rank's exchange buffer and poll tagged flags
+//   comm  != nullptr : NCCL all-gathers
+//   neither          : single-process emulation with shared gather buffers (no exchange at all)
 template <typename T, bool NJ>
 static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int64_t max_iters, void *comm,
-                  int32_t *joins, int32_t *last2, cudaStream_t stream) {
+                  const ShPeers *peers_in, unsigned long long epoch, int32_t *joins, int32_t *last2,
+                  cudaStream_t stream) {
   const int sms = sm_count();
   const int target_ctas = sms * 4;
-  const bool emu = (comm == nullptr);
+  ShPeers peers;
+  memset(&peers, 0, sizeof(peers));
+  if (peers_in) peers = *peers_in;
+  const bool p2p = peers.ex[0] != nullptr;
+  const bool emu = (comm == nullptr) && !p2p;
+  const unsigned long long tag0 = epoch << 32;
   Cand *cand_all = ranks[0].w.cand_all;
   char *gath = ranks[0].w.gath;
   for (auto &rk : ranks) {
@@ -429,21 +558,20 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     for (auto &rk : ranks) {
       const int nloc = sh_count((int)n, rk.r, G);
       double *mine = reinterpret_cast<double *>(emu ? gath : rk.w.gath) + (size_t)rk.r * chunk;
-      if (nloc > 0) {
-        sh_rowsum_kernel<T><<<(unsigned)((nloc + 7) / 8), 256, 0, stream>>>((const T *)rk.D, ld, (int)n, G,
-                                                                             rk.r, mine);
-        CAS_LAUNCH_CHECK();
-      }
+      const unsigned blocks = (unsigned)((nloc + 7) / 8 > 0 ? (nloc + 7) / 8 : 1);
+      sh_rowsum_kernel<T><<<blocks, 256, 0, stream>>>((const T *)rk.D, ld, (int)n, G, rk.r, mine, chunk, peers,
+                                                      tag0 + 1, rk.w.counters + 2);
+      CAS_LAUNCH_CHECK();
     }
-    if (!emu) {
+    if (!emu && !p2p) {
       ShRank &rk = ranks[0];
       double *buf = reinterpret_cast<double *>(rk.w.gath);
       CAS_NCCL_TRY(g_nccl.AllGather(buf + (size_t)rk.r * chunk, buf, (size_t)chunk * 8, NCCL_INT8, comm, stream));
     }
     for (auto &rk : ranks) {
       const double *buf = reinterpret_cast<const double *>(emu ? gath : rk.w.gath);
-      sh_rscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(buf, chunk, (int)n, G, rk.w.R,
-                                                                          rk.w.rmax_bits);
+      sh_rscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(buf, chunk, (int)n, G, rk.r, rk.w.R,
+                                                                          rk.w.rmax_bits, peers, tag0 + 1);
       CAS_LAUNCH_CHECK();
     }
   }
@@ -452,6 +580,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     const int k = (int)(n - t);
     const int chunk = sh_chunk(k, G);
     const int ncb = (k + TC - 1) / TC;
+    const unsigned long long tag = tag0 + 2 + (unsigned long long)t;
     // --- scan
     for (auto &rk : ranks) {
       ShScanArgs sa;
@@ -468,6 +597,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       sa.R = rk.w.R; sa.ids = rk.w.ids; sa.tinv = 1.0 / (double)(k - 2); sa.rmax_bits = rk.w.rmax_bits;
       sa.cand = rk.w.cand; sa.counter = rk.w.counters + 0;
       sa.out = (emu ? cand_all : rk.w.cand_all) + rk.r;
+      sa.peers = peers; sa.tag = tag;
       int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
       if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
       if (grid < 1) grid = 1;
@@ -475,7 +605,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       CAS_LAUNCH_CHECK();
     }
     // --- C1: candidates
-    if (!emu) {
+    if (!emu && !p2p) {
       ShRank &rk = ranks[0];
       CAS_NCCL_TRY(g_nccl.AllGather(rk.w.cand_all + rk.r, rk.w.cand_all, sizeof(Cand), NCCL_INT8, comm, stream));
     }
@@ -487,12 +617,13 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ca.mine = (emu ? gath : rk.w.gath) + (size_t)rk.r * 3 * chunk * sizeof(T);
       ca.ids = rk.w.ids; ca.sizes = NJ ? nullptr : rk.w.sizes; ca.sel = rk.w.sel;
       ca.joins = joins; ca.t = (int)t;
+      ca.peers = peers; ca.tag = tag; ca.counter = rk.w.counters + 2;
       const int nloc = sh_count(k, rk.r, G);
       sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
       CAS_LAUNCH_CHECK();
     }
     // --- C2: rows lo, hi, last
-    if (!emu) {
+    if (!emu && !p2p) {
       ShRank &rk = ranks[0];
       const size_t per = (size_t)3 * chunk * sizeof(T);
       CAS_NCCL_TRY(g_nccl.AllGather(rk.w.gath + (size_t)rk.r * per, rk.w.gath, per, NCCL_INT8, comm, stream));
@@ -505,6 +636,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.sel = rk.w.sel; ma.R = rk.w.R; ma.ids = rk.w.ids; ma.sizes = NJ ? nullptr : rk.w.sizes;
       ma.partial = rk.w.partial; ma.counter = rk.w.counters + 1; ma.rmax_bits = rk.w.rmax_bits;
       ma.new_id = (int)(n + t); ma.maintain_R = NJ ? 1 : 0;
+      ma.peers = peers; ma.tag = tag;
       sh_merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
       CAS_LAUNCH_CHECK();
     }
@@ -517,13 +649,16 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
 }
 
 static int sh_dispatch(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int dtype, int algo,
-                       int64_t max_iters, void *comm, int32_t *joins, int32_t *last2, cudaStream_t stream) {
+                       int64_t max_iters, void *comm, const ShPeers *peers, unsigned long long epoch,
+                       int32_t *joins, int32_t *last2, cudaStream_t stream) {
   if (algo == CAS_ALGO_NJ) {
-    if (dtype == CAS_F64) return sh_run<double, true>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
-    return sh_run<float, true>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
+    if (dtype == CAS_F64)
+      return sh_run<double, true>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
+    return sh_run<float, true>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
   }
-  if (dtype == CAS_F64) return sh_run<double, false>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
-  return sh_run<float, false>(ranks, n, ld, G, max_iters, comm, joins, last2, stream);
+  if (dtype == CAS_F64)
+    return sh_run<double, false>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
+  return sh_run<float, false>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
 }
 
 }  // namespace cas
@@ -598,7 +733,8 @@ int cas_sharded_solve(void *D_local, int64_t n, int64_t ld, int32_t dtype, int32
   ranks[0].D = D_local;
   ranks[0].w = sh_carve(workspace, n, world, dtype == CAS_F64 ? 8 : 4);
   ranks[0].r = rank;
-  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nccl_comm, joins, last2, (cudaStream_t)stream);
+  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nccl_comm, nullptr, 0, joins, last2,
+                     (cudaStream_t)stream);
 }
 
 int cas_sharded_solve_emulated(void *const *D_locals, int64_t n, int64_t ld, int32_t dtype, int32_t algo,
@@ -616,7 +752,119 @@ int cas_sharded_solve_emulated(void *const *D_locals, int64_t n, int64_t ld, int
     ranks[r].w = sh_carve(workspaces[r], n, world, dtype == CAS_F64 ? 8 : 4);
     ranks[r].r = r;
   }
-  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nullptr, joins, last2, (cudaStream_t)stream);
+  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nullptr, nullptr, 0, joins, last2,
+                     (cudaStream_t)stream);
+}
+
+// ---- P2P exchange buffers ------------------------------------------------------------------
+size_t cas_exchange_bytes(int64_t n, int32_t world, int32_t dtype) {
+  const size_t esz = dtype == CAS_F64 ? 8 : 4;
+  const size_t chunk = (size_t)sh_chunk((int)(n > 0 ? n : 1), world > 0 ? world : 1);
+  size_t per = 3 * chunk * esz;
+  if (per < chunk * 8) per = chunk * 8;
+  return sizeof(ShExHeader) + per * (size_t)(world > 0 ? world : 1) + 256;
+}
+
+int cas_exchange_alloc(size_t bytes, void **ptr_out, void *handle64_out) {
+  CAS_REQUIRE(ptr_out && handle64_out, "null pointer argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  void *p = nullptr;
+  CAS_CUDA_TRY(cudaMalloc(&p, bytes));
+  CAS_CUDA_TRY(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    memset(&h, 0, sizeof(h));  // same-process use (emulation) still works without a handle
+  }
+  memcpy(handle64_out, &h, 64);
+  *ptr_out = p;
+  return CAS_OK;
+}
+
+int cas_exchange_open(const void *handle64, void **ptr_out) {
+  CAS_REQUIRE(handle64 && ptr_out, "null pointer argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  CAS_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = p;
+  return CAS_OK;
+}
+
+int cas_exchange_close(void *ptr) {
+  if (ptr) CAS_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return CAS_OK;
+}
+
+int cas_exchange_free(void *ptr) {
+  if (ptr) CAS_CUDA_TRY(cudaFree(ptr));
+  return CAS_OK;
+}
+
+// 0 = fine, 1 = a flag wait timed out in some kernel (synchronises the stream)
+int cas_exchange_error(const void *own_exchange, void *stream, int32_t *error_out) {
+  CAS_REQUIRE(own_exchange && error_out, "null pointer argument");
+  int err = 0;
+  CAS_CUDA_TRY(cudaMemcpyAsync(&err, (const char *)own_exchange + offsetof(ShExHeader, error), sizeof(int),
+                               cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  *error_out = err;
+  return CAS_OK;
+}
+
+static int fill_peers(ShPeers &peers, void *const *exchange_ptrs, int world) {
+  memset(&peers, 0, sizeof(peers));
+  CAS_REQUIRE(world <= SH_MAXG, "P2P exchange supports at most %d ranks", SH_MAXG);
+  for (int r = 0; r < world; ++r) {
+    CAS_REQUIRE(exchange_ptrs[r] != nullptr, "null exchange buffer for rank %d", r);
+    peers.ex[r] = static_cast<char *>(exchange_ptrs[r]);
+  }
+  return CAS_OK;
+}
+
+int cas_sharded_solve_p2p(void *D_local, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int64_t max_iters,
+                          int32_t rank, int32_t world, void *const *exchange_ptrs, uint64_t epoch,
+                          int32_t *joins, int32_t *last2, void *workspace, size_t workspace_bytes,
+                          void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(D_local && joins && last2 && workspace && exchange_ptrs, "null pointer argument");
+  int rc = sh_check(n, ld, dtype, algo, world);
+  if (rc != CAS_OK) return rc;
+  CAS_REQUIRE(rank >= 0 && rank < world, "bad rank %d", rank);
+  CAS_REQUIRE(workspace_bytes >= cas_sharded_workspace_bytes(n, world, dtype), "workspace too small");
+  ShPeers peers;
+  rc = fill_peers(peers, exchange_ptrs, world);
+  if (rc != CAS_OK) return rc;
+  std::vector<ShRank> ranks(1);
+  ranks[0].D = D_local;
+  ranks[0].w = sh_carve(workspace, n, world, dtype == CAS_F64 ? 8 : 4);
+  ranks[0].r = rank;
+  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nullptr, &peers, epoch, joins, last2,
+                     (cudaStream_t)stream);
+}
+
+int cas_sharded_solve_emulated_p2p(void *const *D_locals, int64_t n, int64_t ld, int32_t dtype, int32_t algo,
+                                   int64_t max_iters, int32_t world, void *const *exchange_ptrs,
+                                   uint64_t epoch, int32_t *joins, int32_t *last2, void *const *workspaces,
+                                   size_t workspace_bytes, void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(D_locals && joins && last2 && workspaces && exchange_ptrs, "null pointer argument");
+  int rc = sh_check(n, ld, dtype, algo, world);
+  if (rc != CAS_OK) return rc;
+  CAS_REQUIRE(workspace_bytes >= cas_sharded_workspace_bytes(n, world, dtype), "workspace too small");
+  ShPeers peers;
+  rc = fill_peers(peers, exchange_ptrs, world);
+  if (rc != CAS_OK) return rc;
+  std::vector<ShRank> ranks(world);
+  for (int r = 0; r < world; ++r) {
+    CAS_REQUIRE(D_locals[r] && workspaces[r], "null shard pointer for rank %d", r);
+    ranks[r].D = D_locals[r];
+    ranks[r].w = sh_carve(workspaces[r], n, world, dtype == CAS_F64 ? 8 : 4);
+    ranks[r].r = r;
+  }
+  return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nullptr, &peers, epoch, joins, last2,
+                     (cudaStream_t)stream);
 }
 
 }  // extern "C"

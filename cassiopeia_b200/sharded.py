@@ -74,7 +74,7 @@ def build_shard(cm_dev, missing: int, table, n_states: int, rank: int, world: in
 
 
 def emulated_solve(codes: np.ndarray, missing: int, table, n_states: int, algo: str, world: int,
-                   dtype: str = "f32", max_iters: int = -1):
+                   dtype: str = "f32", max_iters: int = -1, p2p: bool = False):
     """All `world` virtual ranks in this process on the current GPU (no collective): the same
     kernels as the multi-process path, used to check that sharding does not change the joins."""
     torch = engine._torch()
@@ -91,10 +91,27 @@ def emulated_solve(codes: np.ndarray, missing: int, table, n_states: int, algo: 
     last2 = torch.full((2,), -1, dtype=torch.int32, device="cuda")
     dptr = (ctypes.c_void_p * world)(*[s.data_ptr() for s in shards])
     wptr = (ctypes.c_void_p * world)(*[w.data_ptr() for w in wss])
-    rc = L.cas_sharded_solve_emulated(dptr, n, ld, code, CAS_ALGO_NJ if algo == "nj" else CAS_ALGO_UPGMA,
-                                      int(max_iters), int(world), joins.data_ptr(), last2.data_ptr(), wptr,
-                                      ws_bytes, engine._stream_ptr(torch))
-    _lib.check(rc, "cas_sharded_solve_emulated")
+    algo_code = CAS_ALGO_NJ if algo == "nj" else CAS_ALGO_UPGMA
+    if p2p:
+        # every virtual rank gets its own exchange buffer; "peer" stores are local in this process
+        ex_bytes = int(L.cas_exchange_bytes(n, world, code))
+        exs = [torch.zeros(ex_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        eptr = (ctypes.c_void_p * world)(*[e.data_ptr() for e in exs])
+        rc = L.cas_sharded_solve_emulated_p2p(dptr, n, ld, code, algo_code, int(max_iters), int(world), eptr, 1,
+                                              joins.data_ptr(), last2.data_ptr(), wptr, ws_bytes,
+                                              engine._stream_ptr(torch))
+        _lib.check(rc, "cas_sharded_solve_emulated_p2p")
+        for e in exs:
+            err = ctypes.c_int32(0)
+            _lib.check(L.cas_exchange_error(e.data_ptr(), engine._stream_ptr(torch), ctypes.byref(err)),
+                       "cas_exchange_error")
+            if err.value:
+                raise _lib.B200LibraryError("a P2P flag wait timed out")
+    else:
+        rc = L.cas_sharded_solve_emulated(dptr, n, ld, code, algo_code, int(max_iters), int(world),
+                                          joins.data_ptr(), last2.data_ptr(), wptr, ws_bytes,
+                                          engine._stream_ptr(torch))
+        _lib.check(rc, "cas_sharded_solve_emulated")
     done = njoin if max_iters < 0 else min(njoin, max_iters)
     return joins[:done].cpu().numpy(), last2.cpu().numpy()
 
@@ -125,6 +142,91 @@ class NcclGroup:
         if self.handle:
             _lib.load().cas_nccl_comm_destroy(self.handle)
             self.handle = ctypes.c_void_p()
+
+
+class PeerGroup:
+    """Exchange buffers for the P2P loop: every rank cudaMallocs one, exports a cudaIpc handle,
+    the handles travel over torch.distributed and each rank maps its peers' buffers."""
+
+    def __init__(self, n: int, dtype: str = "f32"):
+        import torch
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        L = _lib.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.n = int(n)
+        self.code = CAS_F64 if dtype == "f64" else CAS_F32
+        self.bytes = int(L.cas_exchange_bytes(self.n, self.world, self.code))
+        self.own = ctypes.c_void_p()
+        handle = (ctypes.c_char * 64)()
+        _lib.check(L.cas_exchange_alloc(self.bytes, ctypes.byref(self.own), handle), "cas_exchange_alloc")
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine)
+        self.ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs.append(self.own.value)
+            else:
+                ptr = ctypes.c_void_p()
+                _lib.check(L.cas_exchange_open(bytes(gathered[r].cpu().tolist()), ctypes.byref(ptr)),
+                           "cas_exchange_open")
+                self.ptrs.append(ptr.value)
+        self.epoch = 0
+        dist.barrier()
+
+    def array(self):
+        return (ctypes.c_void_p * self.world)(*self.ptrs)
+
+    def check(self):
+        import torch
+
+        err = ctypes.c_int32(0)
+        _lib.check(_lib.load().cas_exchange_error(self.own, engine._stream_ptr(torch), ctypes.byref(err)),
+                   "cas_exchange_error")
+        if err.value:
+            raise _lib.B200LibraryError("a P2P flag wait timed out (peer rank stalled or died)")
+
+    def close(self):
+        import torch.distributed as dist
+
+        L = _lib.load()
+        if dist.is_initialized():
+            dist.barrier()
+        for r, ptr in enumerate(self.ptrs):
+            if r != self.rank and ptr:
+                L.cas_exchange_close(ptr)
+        if self.own:
+            L.cas_exchange_free(self.own)
+            self.own = ctypes.c_void_p()
+        self.ptrs = []
+
+
+def sharded_solve_p2p(shard, n: int, algo: str, group: PeerGroup, max_iters: int = -1):
+    """P2P variant of ``sharded_solve``: NVLink stores + flags from inside the kernels, no NCCL."""
+    torch = engine._torch()
+    L = _lib.load()
+    ld = int(shard.stride(0))
+    code = CAS_F64 if shard.dtype == torch.float64 else CAS_F32
+    assert code == group.code and int(n) <= group.n
+    ws_bytes = int(L.cas_sharded_workspace_bytes(int(n), group.world, code))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    njoin = max(int(n) - 2, 0)
+    joins = torch.full((njoin + 1, 2), -1, dtype=torch.int32, device="cuda")
+    last2 = torch.full((2,), -1, dtype=torch.int32, device="cuda")
+    group.epoch += 1
+    rc = L.cas_sharded_solve_p2p(shard.data_ptr(), int(n), ld, code, CAS_ALGO_NJ if algo == "nj" else CAS_ALGO_UPGMA,
+                                 int(max_iters), group.rank, group.world, group.array(), group.epoch,
+                                 joins.data_ptr(), last2.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 engine._stream_ptr(torch))
+    _lib.check(rc, "cas_sharded_solve_p2p")
+    done = njoin if max_iters < 0 else min(njoin, int(max_iters))
+    out = joins[:done].cpu().numpy(), last2.cpu().numpy()
+    group.check()
+    return out
 
 
 def sharded_solve(shard, n: int, algo: str, group: NcclGroup, max_iters: int = -1):
@@ -159,10 +261,21 @@ def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    group = NcclGroup()
     dt = "f32"
     codes, missing_code, table, n_states = bench.make_workload(args)
     n = codes.shape[0]
+    exchange = os.environ.get("CAS_SHARDED_EXCHANGE", "p2p")
+    if exchange == "p2p":
+        try:
+            group = PeerGroup(n, dt)
+            solve_fn = sharded_solve_p2p
+        except Exception as e:  # cudaIpc unavailable in this container
+            if rank == 0:
+                print(f"# P2P exchange unavailable ({e}); using NCCL all-gathers", flush=True)
+            exchange = "nccl"
+    if exchange != "p2p":
+        group = NcclGroup()
+        solve_fn = sharded_solve
     cm_dev = torch.from_numpy(codes).cuda()
     launches = [0]
 
@@ -171,7 +284,7 @@ def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
         launches[0] += engine.last_launch_count()
         mid = torch.cuda.Event(enable_timing=True)
         mid.record()
-        joins, last2 = sharded_solve(shard, n, "nj", group)
+        joins, last2 = solve_fn(shard, n, "nj", group)
         launches[0] += engine.last_launch_count()
         return joins, last2, mid
 
@@ -221,7 +334,9 @@ def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
             "roofline": {"bound": "hbm", "kernel": "sh_scan_kernel<float,NJ>", "achieved": achieved,
                          "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
                          "peak_source": peak_src + f" x {world} GPUs", "loop_ms": loop_ms,
-                         "collectives_per_iteration": "2 NCCL all-gathers (24 B x G candidates; 3 rows x k x 4 B)"},
+                         "exchange_per_iteration": ("P2P NVLink stores + tagged flags from inside the scan/cols kernels"
+                                                    if exchange == "p2p" else "2 NCCL all-gathers")
+                                                   + " (24 B x G candidates; 3 rows x k x 4 B)"},
             "e2e": {"value": ms_per_step / 1e3, "unit": "s",
                     "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(joins.nbytes + last2.nbytes),
                     "note": "sharded path: character matrix replicated on the devices before the timed region; "

@@ -138,6 +138,27 @@ CAS_API int cas_sharded_solve_emulated(void *const *D_locals_dev, int64_t n, int
                                int32_t *last2_dev, void *const *workspaces_dev,
                                size_t workspace_bytes, void *stream);
 
+/* P2P variant: no collective library in the loop.  Every rank owns an exchange buffer
+ * (cas_exchange_alloc: cudaMalloc + cudaIpc handle) that its peers map (cas_exchange_open) and
+ * write with plain NVLink stores from inside the scan / cols kernels; iteration-tagged flags
+ * (release/acquire at system scope) replace the two all-gathers.  exchange_ptrs[r] = rank r's buffer
+ * as mapped in this process; `epoch` must increase with every solve on the same buffers. */
+CAS_API size_t cas_exchange_bytes(int64_t n, int32_t world, int32_t dtype);
+CAS_API int cas_exchange_alloc(size_t bytes, void **ptr_out, void *handle64_out);
+CAS_API int cas_exchange_open(const void *handle64, void **ptr_out);
+CAS_API int cas_exchange_close(void *ptr);
+CAS_API int cas_exchange_free(void *ptr);
+CAS_API int cas_exchange_error(const void *own_exchange_dev, void *stream, int32_t *error_out);
+CAS_API int cas_sharded_solve_p2p(void *D_local_dev, int64_t n, int64_t ld, int32_t dtype, int32_t algo,
+                          int64_t max_iters, int32_t rank, int32_t world, void *const *exchange_ptrs,
+                          uint64_t epoch, int32_t *joins_dev, int32_t *last2_dev, void *workspace_dev,
+                          size_t workspace_bytes, void *stream);
+CAS_API int cas_sharded_solve_emulated_p2p(void *const *D_locals_dev, int64_t n, int64_t ld, int32_t dtype,
+                                   int32_t algo, int64_t max_iters, int32_t world,
+                                   void *const *exchange_ptrs, uint64_t epoch, int32_t *joins_dev,
+                                   int32_t *last2_dev, void *const *workspaces_dev,
+                                   size_t workspace_bytes, void *stream);
+
 /* ---- single-step hooks (float64, reference operation order) -----------------
  * cas_nj_q       : Q[n,n] (zero diagonal) of NeighborJoiningSolver.compute_q
  *                  (cassiopeia/solver/NeighborJoiningSolver.py:142-171); rowsum_scratch = n doubles.

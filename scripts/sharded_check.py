@@ -18,16 +18,22 @@ args = argparse.Namespace(cells=a.cells, chars=60, states=100, missing=0.2, muta
 codes, missing_code, table, n_states = bench.make_workload(args)
 n = codes.shape[0]
 cm_dev = torch.from_numpy(codes).cuda()
-shard = sharded.build_shard(cm_dev, missing_code, table, n_states, rank, world, "f32")
-torch.cuda.synchronize(); dist.barrier()
-t0 = time.perf_counter()
-joins, last2 = sharded.sharded_solve(shard, n, "nj", group)
-torch.cuda.synchronize()
-t1 = time.perf_counter()
 D = engine.whd_map(cm_dev, missing_code, table, n_states, dtype="f32")
 single, last_single = engine.agglomerate(D, n, "nj", "fast")
-ok = np.array_equal(joins, single) and np.array_equal(last2, last_single)
-print(f"rank {rank}/{world}: n={n} sharded solve {t1 - t0:.3f}s, identical to single GPU: {ok}", flush=True)
-assert ok
+del D
+peers = sharded.PeerGroup(n, "f32")
+for name, fn, grp in (("nccl", sharded.sharded_solve, group), ("p2p", sharded.sharded_solve_p2p, peers),
+                      ("p2p", sharded.sharded_solve_p2p, peers)):
+    shard = sharded.build_shard(cm_dev, missing_code, table, n_states, rank, world, "f32")
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    joins, last2 = fn(shard, n, "nj", grp)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ok = np.array_equal(joins, single) and np.array_equal(last2, last_single)
+    print(f"rank {rank}/{world}: n={n} {name} sharded solve {t1 - t0:.3f}s ({(t1 - t0) / (n - 2) * 1e6:.1f} us/iter), "
+          f"identical to single GPU: {ok}", flush=True)
+    assert ok
+peers.close()
 group.close()
 dist.destroy_process_group()

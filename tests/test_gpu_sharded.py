@@ -35,6 +35,31 @@ def test_sharded_nj_equals_single_gpu_fast(name, world):
     assert np.array_equal(last_single, last_shard)
 
 
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("name", ["sim1024_s0_nj_priors", "ties120_nj_plain"])
+def test_sharded_p2p_kernels_equal_single_gpu(name, world):
+    """The P2P exchange path (stores into every rank's exchange buffer + tagged flags), emulated in
+    one process where the "peer" buffers are local."""
+    from cassiopeia_b200 import engine, sharded
+
+    g = Golden(name)
+    cm, w, S = _inputs(g)
+    n = cm.shape[0]
+    D = engine.whd_map(cm, g.missing, w, S, dtype="f32")
+    single, last_single = engine.agglomerate(D, n, "nj", "fast")
+    shard, last_shard = sharded.emulated_solve(cm, g.missing, w, S, "nj", world, dtype="f32", p2p=True)
+    assert np.array_equal(single, shard) and np.array_equal(last_single, last_shard)
+
+
+def test_sharded_p2p_upgma_f64_reproduces_reference():
+    from cassiopeia_b200 import sharded
+
+    g = Golden("sim256_s1_upgma_priors")
+    cm, w, S = _inputs(g)
+    joins, _ = sharded.emulated_solve(cm, g.missing, w, S, "upgma", 4, dtype="f64", p2p=True)
+    assert np.array_equal(joins, g.joins)
+
+
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("name", ["sim1024_s0_upgma_plain", "sim256_s1_upgma_priors", "ties120_upgma_priors"])
 def test_sharded_upgma_f64_reproduces_reference(name, world):
