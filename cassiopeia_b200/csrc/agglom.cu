@@ -241,27 +241,69 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
   }
 }
 
-// strict NJ: R[c] = ((0 + d[o_0][c]) + d[o_1][c]) + ... over live nodes in id order
-template <typename T>
-__global__ void __launch_bounds__(64) rowsum_seq_kernel(const T *__restrict__ D, int64_t ld, int k,
-                                                        const int32_t *__restrict__ order,
-                                                        double *__restrict__ R,
-                                                        unsigned long long *rmax_bits) {
-  const int c = blockIdx.x * 64 + threadIdx.x;
-  double s = 0.0;
-  if (c < k) {
-    int p = 0;
-    for (; p + 8 <= k; p += 8) {
-      double x[8];
+// strict NJ: R[c] = ((0 + d[o_0][c]) + d[o_1][c]) + ... over live nodes in id order.
+// The additions of one column form a strictly sequential float64 chain (that is what makes the
+// result bit-identical to numba's d.sum(axis=1)), so the kernel is organised around it: a CTA owns
+// 32 adjacent columns (256 bytes per matrix row); all 8 warps stream the rows, in id order, into a
+// 4-stage shared-memory ring with cp.async (32 rows = 8 KB per stage), and warp 0 walks each landed
+// stage with one lane per column.  Global latency is hidden behind the ring; what remains is the
+// dependent-add chain (k x ~10 cycles) or HBM bandwidth (8 k^2 bytes), whichever is larger.
+constexpr int RS_COLS = 32, RS_ROWS = 32, RS_STAGES = 4, RS_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rowsum_seq_kernel(const double *__restrict__ D, int64_t ld, int k,
+                                                                const int32_t *__restrict__ order,
+                                                                double *__restrict__ R,
+                                                                unsigned long long *rmax_bits) {
+  __shared__ __align__(16) double tile[RS_STAGES][RS_ROWS][RS_COLS];
+  const int c0 = blockIdx.x * RS_COLS;
+  const int tid = threadIdx.x;
+  const int nstages = (k + RS_ROWS - 1) / RS_ROWS;
+  // each thread moves 16 bytes (2 columns) of 2 rows per stage: row = tid/16 + 16*i, column pair tid%16
+  const int cpair = tid & 15, rbase = tid >> 4;
+  auto issue = [&](int s) {
+    if (s < nstages) {
+      const int p0 = s * RS_ROWS;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = (double)D[(int64_t)order[p + u] * ld + c];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) s = __dadd_rn(s, x[u]);
+      for (int i = 0; i < RS_ROWS / 16; ++i) {
+        const int r = rbase + 16 * i, p = p0 + r;
+        // columns beyond ld never happen (ld is a multiple of 32); rows beyond k are skipped by the reader
+        if (p < k) cp_async16(&tile[s % RS_STAGES][r][cpair * 2], D + (int64_t)order[p] * ld + c0 + cpair * 2);
+      }
     }
-    for (; p < k; ++p) s = __dadd_rn(s, (double)D[(int64_t)order[p] * ld + c]);
-    R[c] = s;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int s = 0; s < RS_STAGES - 1; ++s) issue(s);
+  double sum = 0.0;
+  for (int s = 0; s < nstages; ++s) {
+    issue(s + RS_STAGES - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(RS_STAGES - 1) : "memory");
+    __syncthreads();
+    if (tid < RS_COLS) {
+      const int rows = min(RS_ROWS, k - s * RS_ROWS);
+      const double(*t)[RS_COLS] = tile[s % RS_STAGES];
+      int r = 0;
+      for (; r + 8 <= rows; r += 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = t[r + u][tid];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, x[u]);
+      }
+      for (; r < rows; ++r) sum = __dadd_rn(sum, t[r][tid]);
+    }
+    __syncthreads();  // the stage may be refilled
   }
-  warp_atomic_absmax(rmax_bits, s);
+  if (tid < RS_COLS) {
+    const bool live = c0 + tid < k;
+    if (live) R[c0 + tid] = sum;
+    warp_atomic_absmax(rmax_bits, live ? sum : 0.0);
+  }
 }
 
 // fast NJ: initial row sums, one warp per row, fixed lane-strided order + shuffle tree
@@ -388,9 +430,8 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     k_final = k - 1;
     const int cur = (int)(t & 1);
     if (strict_nj) {
-      rowsum_seq_kernel<T><<<(unsigned)((k + 63) / 64), 64, 0, stream>>>((const T *)D, ld, k,
-                                                                          w.order[cur], w.R,
-                                                                          w.rmax_bits);
+      rowsum_seq_kernel<<<(unsigned)((k + RS_COLS - 1) / RS_COLS), RS_THREADS, 0, stream>>>(
+          (const double *)D, ld, k, w.order[cur], w.R, w.rmax_bits);
       CAS_LAUNCH_CHECK();
     }
     ScanArgs sa;
