@@ -25,6 +25,8 @@
 //   merge                  : new row/column, swap compaction, id/size/row-sum maintenance.
 // HBM roofline: the scan reads every live unordered pair once, E*k(k-1)/2 bytes
 // (E = 4 fast, 8 strict); merge touches O(k) elements.
+#include <stdlib.h>
+
 #include "agglom_common.cuh"
 
 namespace cas {
@@ -333,13 +335,16 @@ __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *
     if (sizes) sizes[v] = 1;
     if (order) { order[v] = v; pos[v] = v; }
   }
-  if (v < 8) counters[v] = 0;
+  if (v < 16) counters[v] = 0;
   if (v == 0) *rmax_bits = 0ull;
 }
 
-__global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2) {
+__global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2, const int *error) {
   if (threadIdx.x == 0) {
-    if (n >= 2) {
+    if (error && *error) {  // a grid barrier of the persistent loop timed out
+      last2[0] = -2;
+      last2[1] = -2;
+    } else if (n >= 2) {
       last2[0] = min(ids[0], ids[1]);
       last2[1] = max(ids[0], ids[1]);
     } else {
@@ -351,7 +356,15 @@ __global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2) {
 
 // -------------------------------------------------------------------------------------
 
+// agglom_persistent.cu
+int persistent_loop(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int64_t iters, double *R,
+                    int32_t *ids, int32_t *sizes, void *cand_scratch, double *partial,
+                    unsigned long long *rmax_bits, unsigned *bar_words, int *error, int32_t *joins,
+                    cudaStream_t stream);
+size_t persistent_cand_bytes();
+
 struct AgglomWorkspace {
+  void *candx;
   double *R;
   int32_t *ids, *sizes;
   int32_t *order[2], *pos[2];
@@ -378,8 +391,17 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.partial = c.take<double>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
   w.counters = c.take<unsigned>(64);
   w.rmax_bits = c.take<unsigned long long>(8);
+  w.candx = c.take<char>(persistent_cand_bytes());
   w.bytes = c.used();
   return w;
+}
+
+// CAS_PERSISTENT=1 selects the one-launch cooperative loop (agglom_persistent.cu).  It is bit-identical
+// to the multi-kernel loop but measured slightly slower on B200 (two software grid barriers cost about
+// as much as two kernel launches), so it is opt-in; tests run both and compare.
+static bool persistent_enabled() {
+  const char *e = getenv("CAS_PERSISTENT");
+  return e && e[0] == '1';
 }
 
 size_t agglom_workspace_bytes(int64_t n) { return carve_workspace(nullptr, n > 0 ? n : 1).bytes; }
@@ -424,7 +446,21 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     CAS_LAUNCH_CHECK();
   }
   int64_t k_final = n;
-  for (int64_t t = 0; t + 2 < n; ++t) {
+  const int64_t total_iters = n > 2 ? ((max_iters >= 0 && max_iters < n - 2) ? max_iters : n - 2) : 0;
+  bool done_persistent = false;
+  if (!strict_nj && total_iters > 0 && persistent_enabled()) {
+    // whole loop in one cooperative launch (agglom_persistent.cu)
+    int rc = persistent_loop(D, n, ld, sizeof(T) == 8 ? CAS_F64 : CAS_F32, NJ ? CAS_ALGO_NJ : CAS_ALGO_UPGMA,
+                             total_iters, w.R, w.ids, w.sizes, w.candx, w.partial, w.rmax_bits, w.counters + 4,
+                             (int *)(w.counters + 6), joins, stream);
+    if (rc == CAS_OK) {
+      done_persistent = true;
+      k_final = n - total_iters;
+    } else if (rc != CAS_ERR_UNSUPPORTED) {
+      return rc;
+    }
+  }
+  for (int64_t t = 0; !done_persistent && t + 2 < n; ++t) {
     if (max_iters >= 0 && t >= max_iters) break;
     const int k = (int)(n - t);
     k_final = k - 1;
@@ -458,7 +494,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
     CAS_LAUNCH_CHECK();
   }
-  last2_kernel<<<1, 32, 0, stream>>>(w.ids, (int)(k_final < 2 ? k_final : 2), last2);
+  last2_kernel<<<1, 32, 0, stream>>>(w.ids, (int)(k_final < 2 ? k_final : 2), last2, (const int *)(w.counters + 6));
   CAS_LAUNCH_CHECK();
   return CAS_OK;
 }

@@ -30,14 +30,28 @@ template <typename T> struct VecOf;
 template <> struct VecOf<float> { static constexpr int N = 4; };
 template <> struct VecOf<double> { static constexpr int N = 2; };
 
+// Streaming 128-bit loads of the map.  COH = false: the map is read-only for the whole kernel
+// (non-coherent path, no L1 allocation).  COH = true: the persistent loop kernel rewrites the map
+// between phases, so loads must be served from L2 (ld.global.cg) to see other CTAs' stores.
+template <bool COH = false>
 __device__ __forceinline__ void ld_stream(const float *p, float (&v)[4]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+  if (COH)
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p) : "memory");
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
 }
+template <bool COH = false>
 __device__ __forceinline__ void ld_stream(const double *p, double (&v)[2]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-               : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  if (COH)
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(v[0]), "=d"(v[1]) : "l"(p));
 }
+template <bool COH, typename X>
+__device__ __forceinline__ X ld_state(const X *p) { return COH ? __ldcg(p) : *p; }
 
 __device__ __forceinline__ unsigned long long make_key(int ida, int idb) {
   unsigned lo = (unsigned)min(ida, idb), hi = (unsigned)max(ida, idb);
@@ -45,14 +59,15 @@ __device__ __forceinline__ unsigned long long make_key(int ida, int idb) {
 }
 
 // rare path: candidate ties (or beats) the thread's running best
+template <bool COH = false>
 __device__ __forceinline__ void tie_path(double q, int i, int j, double &bq, int &bi, int &bj,
-                                         const int32_t *__restrict__ ids) {
+                                         const int32_t *ids) {
   if (q < bq || bi < 0) {
     bq = q; bi = i; bj = j;
     return;
   }
-  unsigned long long kn = make_key(ids[i], ids[j]);
-  unsigned long long ko = make_key(ids[bi], ids[bj]);
+  unsigned long long kn = make_key(ld_state<COH>(ids + i), ld_state<COH>(ids + j));
+  unsigned long long ko = make_key(ld_state<COH>(ids + bi), ld_state<COH>(ids + bj));
   if (kn < ko) { bi = i; bj = j; }
 }
 
@@ -94,11 +109,11 @@ template <> __device__ __forceinline__ double round_to<double>(double v) { retur
 // Scans columns [c0, jend) of one matrix row (slot i) with one warp: float32 screen against the
 // staged u_j block `sU`, exact float64 re-evaluation of the survivors.  (bq, bi, bj) is the
 // lane's running best (value, row slot, column slot).
-template <typename T, bool NJ>
-__device__ __forceinline__ void scan_row_segment(const T *__restrict__ row, int i, int c0, int jend,
-                                                 int lane, const float *sU, const double *__restrict__ R,
+template <typename T, bool NJ, bool COH = false>
+__device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, int jend,
+                                                 int lane, const float *sU, const double *R,
                                                  double Ri, double tinv, double umax,
-                                                 const int32_t *__restrict__ ids, double &bq, int &bi,
+                                                 const int32_t *ids, double &bq, int &bi,
                                                  int &bj) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;          // independent 128-bit loads in flight per lane
@@ -117,13 +132,13 @@ __device__ __forceinline__ void scan_row_segment(const T *__restrict__ row, int 
     const bool whole = (jb + STEP * U <= jend);
     if (whole) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) ld_stream(row + jb + u * STEP + lane * V, v[u]);
+      for (int u = 0; u < U; ++u) ld_stream<COH>(row + jb + u * STEP + lane * V, v[u]);
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int j = jb + u * STEP + lane * V;
         if (j < jend) {
-          ld_stream(row + j, v[u]);
+          ld_stream<COH>(row + j, v[u]);
         } else {
 #pragma unroll
           for (int e = 0; e < V; ++e) v[u][e] = (T)INFINITY;
@@ -155,10 +170,10 @@ __device__ __forceinline__ void scan_row_segment(const T *__restrict__ row, int 
             double q = (double)v[u][e];
             if (NJ) {
               // q = d_ij - ( (1/(k-2)) * (rs_i + rs_j) ), no FMA  (NeighborJoiningSolver.py:163-170)
-              q = __dsub_rn(q, __dmul_rn(tinv, __dadd_rn(Ri, R[j + e])));
+              q = __dsub_rn(q, __dmul_rn(tinv, __dadd_rn(Ri, ld_state<COH>(R + j + e))));
             }
             if (q <= bq || bi < 0) {
-              tie_path(q, i, j + e, bq, bi, bj, ids);
+              tie_path<COH>(q, i, j + e, bq, bi, bj, ids);
               thr = threshold();
             }
           }
@@ -169,10 +184,10 @@ __device__ __forceinline__ void scan_row_segment(const T *__restrict__ row, int 
 }
 
 // Reduces the lanes' bests to one candidate per CTA (thread 0 returns it).
-__device__ __forceinline__ Cand block_best(double bq, int bi, int bj, const int32_t *__restrict__ ids,
-                                           Cand *sCand) {
+template <bool COH = false>
+__device__ __forceinline__ Cand block_best(double bq, int bi, int bj, const int32_t *ids, Cand *sCand) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long bkey = (bi >= 0) ? make_key(ids[bi], ids[bj]) : ~0ull;
+  unsigned long long bkey = (bi >= 0) ? make_key(ld_state<COH>(ids + bi), ld_state<COH>(ids + bj)) : ~0ull;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     double oq = __shfl_down_sync(0xffffffffu, bq, off);

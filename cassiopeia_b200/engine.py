@@ -119,6 +119,8 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     joins_h = joins[:done].cpu().numpy()
     last2_h = last2.cpu().numpy()
+    if last2_h[0] == -2:
+        raise B200LibraryError("a grid barrier of the persistent loop kernel timed out")
     return joins_h, last2_h
 
 

@@ -81,3 +81,25 @@ def test_solve_host_matches_device_path():
     joins, last2, tm = engine.solve_host(cm, g.missing, w, S, "nj", "strict", "exact")
     assert np.array_equal(joins, g.joins)
     assert (tm >= 0).all()
+
+
+@pytest.mark.parametrize("name,mode,dt", [("sim1024_s0_nj_priors", "fast", "f32"), ("sim256_s1_nj_plain", "fast", "f64"),
+                                          ("sim1024_s0_upgma_plain", "strict", "f64"), ("ties120_upgma_priors", "fast", "f32")])
+def test_persistent_loop_equals_multi_kernel_loop(name, mode, dt, monkeypatch):
+    """The one-launch cooperative loop and the launch-per-phase loop run the same arithmetic."""
+    from cassiopeia_b200 import engine
+
+    g = Golden(name)
+    w, S = _table(g)
+    cm = g.ordered_cm.astype(np.int32)
+    n = cm.shape[0]
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CAS_PERSISTENT", flag)
+        D = engine.whd_map(cm, g.missing, w, S, dtype=dt, method="exact")
+        out[flag] = engine.agglomerate(D, n, g.algo, mode)
+        launches = engine.last_launch_count()
+        assert (launches < 10) == (flag == "1"), launches
+    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+    if mode == "strict":
+        assert np.array_equal(out["1"][0], g.joins)
