@@ -62,3 +62,20 @@ def dissimilarity_map_frame_inputs(character_matrix, priors, missing_state_indic
         n = cm.shape[0]
         return names, D[:, :n].cpu().numpy()
     return names, D
+
+
+def row_to_all_distances(character_matrix, row_name, priors, missing_state_indicator: int,
+                         prior_transformation: str = "negative_log"):
+    """Distances from the sample `row_name` to every sample of `character_matrix` (float64, exact kernel),
+    as {name: distance}.  One map row block on the GPU -- used for the implicit-root row when a map already
+    exists (reference NeighborJoiningSolver.py:293-307 evaluates the function per leaf in Python)."""
+    weights = None
+    if priors:
+        weights = solver_utilities.transform_priors(priors, prior_transformation)
+    cm = host_prep.as_int_matrix(character_matrix)
+    names = list(character_matrix.index)
+    r = names.index(row_name)
+    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing_state_indicator, weights)
+    D = engine.whd_map(codes, missing_code, table, n_states, dtype="f64", method="exact", rows=(r, r + 1))
+    row = D[0, : len(names)].cpu().numpy()
+    return {nm: float(row[i]) for i, nm in enumerate(names)}

@@ -9,6 +9,7 @@ import numpy as np
 import pandas as pd
 
 from .. import engine
+from ..data import utilities as data_utilities
 from ..mixins import DistanceSolverError
 from . import dissimilarity_functions, solver_utilities
 from .DistanceSolver import B200_IMPLEMENTATIONS, DistanceSolver
@@ -75,7 +76,16 @@ class NeighborJoiningSolver(DistanceSolver):
         try:
             if cassiopeia_tree.get_dissimilarity_map() is None:
                 self._pending_device_map = self._compute_device_map(cassiopeia_tree, rooted_character_matrix)
+            elif dissimilarity_functions.is_gpu_kernel(self.dissimilarity_function):
+                # one row block of the CUDA map kernel instead of n Python calls
+                dissimilarity = data_utilities.row_to_all_distances(
+                    rooted_character_matrix, "root", cassiopeia_tree.priors,
+                    cassiopeia_tree.missing_state_indicator, self.prior_transformation)
+                dissimilarity["root"] = 0
+                cassiopeia_tree.set_dissimilarity("root", dissimilarity)
             else:
+                # a user-supplied Python function can only be evaluated on the host, per leaf, exactly as
+                # the reference does; the map itself was supplied by the user
                 weights = None
                 if cassiopeia_tree.priors:
                     weights = solver_utilities.transform_priors(cassiopeia_tree.priors, self.prior_transformation)
