@@ -32,6 +32,7 @@ EXPORTS = (
     "cas_solve_host",
     "cas_nj_q",
     "cas_update_map",
+    "cas_agglom_stats",
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
     "cas_sharded_workspace_bytes",
@@ -79,6 +80,8 @@ def _declare(L: ctypes.CDLL) -> None:
     for fn in (L.cas_nj_solve, L.cas_upgma_solve):
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, i64, i64, i32, i32, i64, vp, vp, vp, sz, vp]
+    L.cas_agglom_stats.restype = ctypes.c_int
+    L.cas_agglom_stats.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.cas_nj_q.restype = ctypes.c_int
     L.cas_nj_q.argtypes = [vp, i64, i64, vp, vp, vp]
     L.cas_update_map.restype = ctypes.c_int

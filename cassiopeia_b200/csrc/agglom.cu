@@ -49,6 +49,7 @@ struct ScanArgs {
   Sel *sel;
   int32_t *joins;
   int t;  // iteration index
+  unsigned long long *stats;  // [0] near-tie iterations, [1] exact-tie iterations
 };
 
 template <typename T, bool NJ>
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
   const double umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
-  double bq = INFINITY;
+  double bq = INFINITY, b2 = INFINITY;
   int bi = -1, bj = -1;
   int staged_cb = -1;
 
@@ -92,11 +93,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
       if (jend <= c0) continue;
       const T *__restrict__ row = D + (int64_t)i * a.ld;
       const double Ri = NJ ? a.R[i] : 0.0;
-      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj);
+      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj, b2);
     }
   }
 
-  Cand c = block_best(bq, bi, bj, a.ids, sCand);
+  Cand c = block_best(bq, bi, bj, b2, a.ids, sCand);
   if (threadIdx.x == 0) {
     a.cand[blockIdx.x] = c;
     __threadfence();
@@ -120,6 +121,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
     *a.sel = s;
     a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
     a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
+    // near-tie diagnostics: runner-up within 1e-6 (relative, absolute below 1) of the winner
+    const double gap = c.q2 - c.q;
+    if (gap <= 1e-6 * fmax(1.0, fabs(c.q))) atomicAdd(a.stats + 0, 1ull);
+    if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
   }
 }
 
@@ -336,7 +341,7 @@ __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *
     if (order) { order[v] = v; pos[v] = v; }
   }
   if (v < 16) counters[v] = 0;
-  if (v == 0) *rmax_bits = 0ull;
+  if (v == 0) { rmax_bits[0] = 0ull; rmax_bits[2] = 0ull; rmax_bits[3] = 0ull; }
 }
 
 __global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2, const int *error) {
@@ -373,6 +378,7 @@ struct AgglomWorkspace {
   double *partial;
   unsigned *counters;
   unsigned long long *rmax_bits;
+  unsigned long long *stats;
   size_t bytes;
 };
 
@@ -391,6 +397,7 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.partial = c.take<double>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
   w.counters = c.take<unsigned>(64);
   w.rmax_bits = c.take<unsigned long long>(8);
+  w.stats = w.rmax_bits + 2;
   w.candx = c.take<char>(persistent_cand_bytes());
   w.bytes = c.used();
   return w;
@@ -476,6 +483,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     sa.R = w.R; sa.ids = w.ids; sa.sizes = NJ ? nullptr : w.sizes;
     sa.tinv = 1.0 / (double)(k - 2);
     sa.rmax_bits = w.rmax_bits;
+    sa.stats = w.stats;
     sa.cand = w.cand; sa.counter = w.counters + 0; sa.sel = w.sel; sa.joins = joins; sa.t = (int)t;
     int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
     if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
@@ -520,4 +528,16 @@ int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, in
   return CAS_ERR_INVALID;
 }
 
+}  // namespace cas
+
+namespace cas {
+int agglom_read_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *near_ties, int64_t *exact_ties) {
+  AgglomWorkspace w = carve_workspace(const_cast<void *>(workspace), n > 0 ? n : 1);
+  unsigned long long h[2] = {0, 0};
+  CAS_CUDA_TRY(cudaMemcpyAsync(h, w.stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (near_ties) *near_ties = (int64_t)h[0];
+  if (exact_ties) *exact_ties = (int64_t)h[1];
+  return CAS_OK;
+}
 }  // namespace cas

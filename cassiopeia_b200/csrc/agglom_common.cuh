@@ -17,6 +17,8 @@ struct Cand {
   double q;
   unsigned long long key;  // (id_lo << 32) | id_hi ; ~0 = empty
   int si, sj;              // slots, si > sj (row, column of the lower triangle)
+  double q2;               // runner-up: smallest exactly evaluated value of any other pair (+inf if none);
+                           // exact whenever it lies within the screening margin of q (near-tie diagnostics)
 };
 
 struct Sel {
@@ -60,12 +62,18 @@ __device__ __forceinline__ unsigned long long make_key(int ida, int idb) {
 
 // rare path: candidate ties (or beats) the thread's running best
 template <bool COH = false>
-__device__ __forceinline__ void tie_path(double q, int i, int j, double &bq, int &bi, int &bj,
+__device__ __forceinline__ void tie_path(double q, int i, int j, double &bq, int &bi, int &bj, double &b2,
                                          const int32_t *ids) {
-  if (q < bq || bi < 0) {
+  if (bi < 0) {
     bq = q; bi = i; bj = j;
     return;
   }
+  if (q < bq) {
+    b2 = fmin(b2, bq);  // the old best becomes a runner-up
+    bq = q; bi = i; bj = j;
+    return;
+  }
+  b2 = q;  // exact tie: runner-up equals the best
   unsigned long long kn = make_key(ld_state<COH>(ids + i), ld_state<COH>(ids + j));
   unsigned long long ko = make_key(ld_state<COH>(ids + bi), ld_state<COH>(ids + bj));
   if (kn < ko) { bi = i; bj = j; }
@@ -114,7 +122,7 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
                                                  int lane, const float *sU, const double *R,
                                                  double Ri, double tinv, double umax,
                                                  const int32_t *ids, double &bq, int &bi,
-                                                 int &bj) {
+                                                 int &bj, double &b2) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;          // independent 128-bit loads in flight per lane
   constexpr int STEP = 32 * V;  // elements per warp-wide load
@@ -173,8 +181,10 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
               q = __dsub_rn(q, __dmul_rn(tinv, __dadd_rn(Ri, ld_state<COH>(R + j + e))));
             }
             if (q <= bq || bi < 0) {
-              tie_path<COH>(q, i, j + e, bq, bi, bj, ids);
+              tie_path<COH>(q, i, j + e, bq, bi, bj, b2, ids);
               thr = threshold();
+            } else {
+              b2 = fmin(b2, q);  // passed the screen but lost: a runner-up
             }
           }
         }
@@ -183,25 +193,40 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
   }
 }
 
+// merges candidate o into c: the better one wins, the runner-up is the smallest of the rest
+__device__ __forceinline__ void cand_merge(Cand &c, const Cand &o) {
+  if (cand_better(o.q, o.key, c.q, c.key)) {
+    const double r = fmin(o.q2, fmin(c.q2, c.si >= 0 ? c.q : INFINITY));
+    c = o;
+    c.q2 = r;
+  } else {
+    c.q2 = fmin(c.q2, fmin(o.q2, o.si >= 0 ? o.q : INFINITY));
+  }
+}
+__device__ __forceinline__ Cand cand_shfl_down(const Cand &c, int off) {
+  Cand o;
+  o.q = __shfl_down_sync(0xffffffffu, c.q, off);
+  o.key = __shfl_down_sync(0xffffffffu, c.key, off);
+  o.si = __shfl_down_sync(0xffffffffu, c.si, off);
+  o.sj = __shfl_down_sync(0xffffffffu, c.sj, off);
+  o.q2 = __shfl_down_sync(0xffffffffu, c.q2, off);
+  return o;
+}
+
 // Reduces the lanes' bests to one candidate per CTA (thread 0 returns it).
 template <bool COH = false>
-__device__ __forceinline__ Cand block_best(double bq, int bi, int bj, const int32_t *ids, Cand *sCand) {
+__device__ __forceinline__ Cand block_best(double bq, int bi, int bj, double b2, const int32_t *ids, Cand *sCand) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long bkey = (bi >= 0) ? make_key(ld_state<COH>(ids + bi), ld_state<COH>(ids + bj)) : ~0ull;
+  Cand c;
+  c.q = bq; c.si = bi; c.sj = bj; c.q2 = b2;
+  c.key = (bi >= 0) ? make_key(ld_state<COH>(ids + bi), ld_state<COH>(ids + bj)) : ~0ull;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    double oq = __shfl_down_sync(0xffffffffu, bq, off);
-    unsigned long long ok = __shfl_down_sync(0xffffffffu, bkey, off);
-    int oi = __shfl_down_sync(0xffffffffu, bi, off);
-    int oj = __shfl_down_sync(0xffffffffu, bj, off);
-    if (cand_better(oq, ok, bq, bkey)) { bq = oq; bkey = ok; bi = oi; bj = oj; }
-  }
-  if (lane == 0) { sCand[warp].q = bq; sCand[warp].key = bkey; sCand[warp].si = bi; sCand[warp].sj = bj; }
+  for (int off = 16; off > 0; off >>= 1) cand_merge(c, cand_shfl_down(c, off));
+  if (lane == 0) sCand[warp] = c;
   __syncthreads();
-  Cand c = sCand[0];
+  c = sCand[0];
   if (threadIdx.x == 0) {
-    for (int w = 1; w < SCAN_WARPS; ++w)
-      if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
+    for (int w = 1; w < SCAN_WARPS; ++w) cand_merge(c, sCand[w]);
   }
   return c;
 }
@@ -210,29 +235,23 @@ __device__ __forceinline__ Cand block_best(double bq, int bi, int bj, const int3
 __device__ __forceinline__ Cand reduce_candidates(const Cand *cand, int count, Cand *sCand) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Cand c;
-  c.q = INFINITY; c.key = ~0ull; c.si = -1; c.sj = -1;
+  c.q = INFINITY; c.key = ~0ull; c.si = -1; c.sj = -1; c.q2 = INFINITY;
   for (int x = threadIdx.x; x < count; x += blockDim.x) {
     Cand o;
     o.q = __ldcg(&cand[x].q);
     o.key = __ldcg(&cand[x].key);
     o.si = __ldcg(&cand[x].si);
     o.sj = __ldcg(&cand[x].sj);
-    if (cand_better(o.q, o.key, c.q, c.key)) c = o;
+    o.q2 = __ldcg(&cand[x].q2);
+    cand_merge(c, o);
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    double oq = __shfl_down_sync(0xffffffffu, c.q, off);
-    unsigned long long ok = __shfl_down_sync(0xffffffffu, c.key, off);
-    int oi = __shfl_down_sync(0xffffffffu, c.si, off);
-    int oj = __shfl_down_sync(0xffffffffu, c.sj, off);
-    if (cand_better(oq, ok, c.q, c.key)) { c.q = oq; c.key = ok; c.si = oi; c.sj = oj; }
-  }
+  for (int off = 16; off > 0; off >>= 1) cand_merge(c, cand_shfl_down(c, off));
   __syncthreads();
   if (lane == 0) sCand[warp] = c;
   __syncthreads();
   c = sCand[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-    if (cand_better(sCand[w].q, sCand[w].key, c.q, c.key)) c = sCand[w];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) cand_merge(c, sCand[w]);
   return c;  // identical in every thread
 }
 

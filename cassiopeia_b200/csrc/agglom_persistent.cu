@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(PT, 1) loop_kernel(LoopArgs a) {
 
     // ---- P1: scan
     const double umax = NJ ? tinv * __longlong_as_double(__ldcg(a.rmax_bits)) : 0.0;
-    double bq = INFINITY;
+    double bq = INFINITY, b2 = INFINITY;
     int bi = -1, bj = -1;
     int staged_cb = -1;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(PT, 1) loop_kernel(LoopArgs a) {
         const int jend = min(c1, i);
         if (jend <= c0) continue;
         scan_row_segment<T, NJ, true>(D + (int64_t)i * ld, i, c0, jend, lane, sU, a.R, Ri, tinv, umax, a.ids,
-                                      bq, bi, bj);
+                                      bq, bi, bj, b2);
       }
     }
     // CTA candidate, published with everything the merge needs

@@ -45,6 +45,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
                  int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t agglom_workspace_bytes(int64_t n);
+int agglom_read_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *near_ties, int64_t *exact_ties);
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
                  size_t workspace_bytes, cudaStream_t stream);
@@ -118,6 +119,11 @@ int cas_whd_map_cyclic(const int32_t *cm, int64_t n, int32_t m, int32_t missing,
 size_t cas_agglom_workspace_bytes(int64_t n, int32_t algo, int32_t mode) {
   (void)algo; (void)mode;
   return agglom_workspace_bytes(n);
+}
+
+int cas_agglom_stats(const void *workspace, int64_t n, void *stream, int64_t *near_ties, int64_t *exact_ties) {
+  CAS_REQUIRE(workspace, "null pointer argument");
+  return agglom_read_stats(workspace, n, (cudaStream_t)stream, near_ties, exact_ties);
 }
 
 int cas_nj_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t mode, int64_t max_iters,

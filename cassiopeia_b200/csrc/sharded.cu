@@ -61,7 +61,7 @@ struct ShExHeader {
   unsigned long long flag2[SH_MAXG];  // flag2[r] = tag: rank r's rows (lo, hi, last) chunk has landed
   Cand cand[SH_MAXG];
   int error;                          // a spin-wait timed out
-  int pad[31];
+  int pad[63];
 };
 static_assert(sizeof(ShExHeader) % 256 == 0, "exchange header must keep the gather area aligned");
 struct ShPeers {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) sh_scan_kernel(ShScanArgs a) 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
   const double umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
-  double bq = INFINITY;
+  double bq = INFINITY, b2 = INFINITY;
   int bi = -1, bj = -1;
   int staged_cb = -1;
 
@@ -144,11 +144,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) sh_scan_kernel(ShScanArgs a) 
       if (jend <= c0) continue;
       const T *__restrict__ row = D + (int64_t)lr * a.ld;
       const double Ri = NJ ? a.R[i] : 0.0;
-      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj);
+      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj, b2);
     }
   }
 
-  Cand c = block_best(bq, bi, bj, a.ids, sCand);
+  Cand c = block_best(bq, bi, bj, b2, a.ids, sCand);
   if (threadIdx.x == 0) {
     a.cand[blockIdx.x] = c;
     __threadfence();

@@ -48,6 +48,10 @@ def device_info() -> dict:
             "total_bytes": tot.value}
 
 
+#: near-tie diagnostics of the most recent `agglomerate` call: {"near_ties": int, "exact_ties": int}
+last_stats = {"near_ties": 0, "exact_ties": 0}
+
+
 def last_launch_count() -> int:
     return int(_lib.load().cas_last_launch_count())
 
@@ -116,6 +120,11 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     rc = fn(D.data_ptr(), int(n), ld, dtype, _MODE[mode], int(max_iters), joins.data_ptr(),
             last2.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(torch))
     _lib.check(rc, f"cas_{algo}_solve")
+    launches = int(L.cas_last_launch_count())
+    near, exact = ctypes.c_int64(0), ctypes.c_int64(0)
+    _lib.check(L.cas_agglom_stats(ws.data_ptr(), int(n), _stream_ptr(torch), ctypes.byref(near),
+                                  ctypes.byref(exact)), "cas_agglom_stats")
+    last_stats["near_ties"], last_stats["exact_ties"] = int(near.value), int(exact.value)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     joins_h = joins[:done].cpu().numpy()
     last2_h = last2.cpu().numpy()

@@ -170,6 +170,14 @@ CAS_API int cas_nj_q(const double *D_dev, int64_t n, int64_t ld, double *Q_dev, 
 CAS_API int cas_update_map(const double *D_dev, int64_t n, int64_t ld, int32_t algo, int64_t i, int64_t j,
                    int64_t size_i, int64_t size_j, double *out_dev, int64_t ld_out, void *stream);
 
+/* Near-tie diagnostics of the last loop run with this workspace (synchronises the stream):
+ * near_ties  = iterations whose runner-up criterion value lay within 1e-6 (relative; absolute
+ *              below 1) of the winner's -- the joins a float32 map may decide differently from
+ *              the reference; exact_ties = iterations decided by the (id_lo, id_hi) rule alone.
+ * Counted by the multi-kernel single-GPU loop. */
+CAS_API int cas_agglom_stats(const void *workspace_dev, int64_t n, void *stream, int64_t *near_ties,
+                     int64_t *exact_ties);
+
 /* number of kernels the last cas_*_solve / cas_whd_map / cas_solve_host call on this
  * thread launched (bench.py's gpu_launches) */
 CAS_API int64_t cas_last_launch_count(void);
