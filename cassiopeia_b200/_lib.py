@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcas_b200.so")
+LIB_PATH = os.environ.get("CAS_B200_LIBRARY", os.path.join(_HERE, "libcas_b200.so"))
 
 # constants of include/cas_b200.h
 CAS_ABI_VERSION = 1
