@@ -390,6 +390,325 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
   }
 }
 
+// =============================================================================================
+// 2-SM variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x N2 output tile
+// (N2 = 256 for int8, 128 for bf16 whose three planes already fill TMEM).  Each CTA stages its own
+// 128 rows of the row-block operand and HALF of the column-block operand; one thread of the leader
+// CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes
+// each CTA's 128 accumulator rows into that CTA's TMEM.  Per MMA cycle every SM fetches half as many
+// operand bytes as the 1-SM kernel above, which is what bounds that kernel (L2->SM ~46 B/clk/SM).
+// =============================================================================================
+constexpr int BAND2 = 6;  // 256-row tile rows per rasterisation band
+
+struct Gemm2Params {
+  CUtensorMap maps[4];       // box 128 B x 128 rows
+  CUtensorMap maps_half[4];  // box 128 B x 64 rows (bf16: half of the 128-column block)
+  int chunks;
+  int nrow_tiles;            // ceil(n / 256)
+  int ncol_tiles;            // ceil(n / N2)
+  int pw;
+  const unsigned long long *pmask;
+  int64_t n;
+  void *D;
+  int64_t ld;
+};
+
+template <typename TO>
+struct __align__(1024) Gemm2Smem {
+  static constexpr int NSLOT = sizeof(TO) == 4 ? 10 : 8;
+  static constexpr int HALF = 32;
+  uint8_t tile[NSLOT][TILE_BYTES];
+  TO stage[8][32][HALF + 1];
+  unsigned long long pm[256][MAXPW];
+  uint64_t full[NSLOT];
+  uint64_t empty[NSLOT];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(cta_rank));
+  return out;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *map, uint32_t leader_bar,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)0x3)
+      : "memory");
+}
+template <bool I8>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if (I8) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+            tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+            tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// work item -> (row tile of 256 rows, column tile of N2 columns), r = 256 / N2.  Column tile c is live
+// for row tile ti when it starts at or left of the row tile's last row: c < min(ncol, r * (ti + 1));
+// the cap only ever binds for the last row tile.  Bands of BAND2 row tiles, column-major in a band,
+// so the clusters running at any moment share a handful of operand blocks in L2.
+__host__ __device__ __forceinline__ int64_t tile2_prefix(int b0, int r) {
+  return (int64_t)r * b0 * (b0 + 1) / 2;  // work items of row tiles [0, b0)
+}
+__device__ __forceinline__ void tile2_of(int64_t t, int T, int r, int ncol, int &ti, int &tj) {
+  int b0 = (int)((sqrt(8.0 * (double)t / r + 1.0) - 1.0) * 0.5);
+  b0 = min(b0, T - 1) / BAND2 * BAND2;
+  while (b0 > 0 && tile2_prefix(b0, r) > t) b0 -= BAND2;
+  while (b0 + BAND2 < T && tile2_prefix(b0 + BAND2, r) <= t) b0 += BAND2;
+  t -= tile2_prefix(b0, r);
+  const int hb = min(BAND2, T - b0);
+  const int cfull = min(ncol, r * (b0 + 1));  // columns live for every row tile of the band
+  if (t < (int64_t)cfull * hb) {
+    tj = (int)(t / hb);
+    ti = b0 + (int)(t % hb);
+    return;
+  }
+  t -= (int64_t)cfull * hb;
+  const int cend = min(ncol, r * (b0 + hb));
+  for (int c = cfull; c < cend; ++c) {
+    const int first = c / r;  // first row tile for which column c is live
+    const int cnt = b0 + hb - first;
+    if (t < cnt) { tj = c; ti = first + (int)t; return; }
+    t -= cnt;
+  }
+  ti = T - 1; tj = 0;  // not reached for t < tile2_count
+}
+static int64_t tile2_count(int T, int r, int ncol) {
+  int64_t cnt = 0;
+  for (int ti = 0; ti < T; ++ti) {
+    const int c = r * (ti + 1);
+    cnt += c < ncol ? c : ncol;
+  }
+  return cnt;
+}
+
+template <bool I8, typename TO, int PW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm2_kernel(const __grid_constant__ Gemm2Params p,
+                                                                    const int64_t nwork) {
+  using P = Prog<I8>;
+  using SM = Gemm2Smem<TO>;
+  constexpr int NSLOT = SM::NSLOT;
+  constexpr int N2 = I8 ? 256 : 128;
+  constexpr int NACC = I8 ? 2 : 1;
+  constexpr int ACCW = I8 ? 256 : 3 * 128;  // TMEM columns per accumulator buffer
+  constexpr uint32_t TMEM_COLS = 512u;
+  constexpr int BROWS = N2 / 2;             // rows of the column-block operand staged by one CTA
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SM &sm = *reinterpret_cast<SM *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_rank();
+  const bool leader = crank == 0;
+  const int64_t wstart = blockIdx.x >> 1, wstride = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 512); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < (I8 ? 2 : 4); ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps_half[i]) : "memory");
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&sm.tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own rows of the I operand, own half of the J operand =====
+    if (lane == 0) {
+      uint32_t lc = 0;
+      const int elems_per_chunk = I8 ? CHUNK_BYTES : CHUNK_BYTES / 2;
+      for (int64_t work = wstart; work < nwork; work += wstride) {
+        int ti, tj;
+        tile2_of(work, p.nrow_tiles, 256 / N2, p.ncol_tiles, ti, tj);
+        const int row0 = ti * 256 + (int)crank * 128, col0 = tj * N2 + (int)crank * BROWS;
+        for (int c = 0; c < p.chunks; ++c) {
+#pragma unroll
+          for (int l = 0; l < P::NL; ++l, ++lc) {
+            const uint32_t slot = lc % NSLOT, phase = (lc / NSLOT) & 1u;
+            mbar_wait(&sm.empty[slot], phase ^ 1u);
+            const bool jside = P::load_side(l) != 0;
+            const uint32_t my_bytes = jside ? (uint32_t)(BROWS * CHUNK_BYTES) : (uint32_t)TILE_BYTES;
+            // all bytes of both CTAs are accounted on the leader's barrier
+            if (leader) mbar_expect_tx(&sm.full[slot], 2 * my_bytes);
+            const uint32_t leader_bar = mapa_u32(smem_u32(&sm.full[slot]), 0);
+            const CUtensorMap *map = (jside && BROWS == 64) ? &p.maps_half[P::load_map(l)] : &p.maps[P::load_map(l)];
+            tma_load_2d_2sm(sm.tile[slot], map, leader_bar, c * elems_per_chunk, jside ? col0 : row0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+    if (leader && lane == 0) {
+      const uint32_t idesc = ((I8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      uint32_t lc0 = 0;
+      int64_t it = 0;
+      for (int64_t work = wstart; work < nwork; work += wstride, ++it) {
+        const int as = (int)(it % NACC);
+        const uint32_t aphase = (uint32_t)((it / NACC) & 1);
+        mbar_wait(&sm.tempty[as], aphase ^ 1);  // both CTAs' epilogues have drained this buffer
+        tcgen05_fence_after();
+        for (int c = 0; c < p.chunks; ++c, lc0 += P::NL) {
+#pragma unroll
+          for (int m = 0; m < P::NM; ++m) {
+            const uint32_t la = lc0 + P::mma_a(m), lb = lc0 + P::mma_b(m);
+            const uint32_t sa = la % NSLOT, sb = lb % NSLOT;
+            mbar_wait(&sm.full[sa], (la / NSLOT) & 1u);
+            mbar_wait(&sm.full[sb], (lb / NSLOT) & 1u);
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_u32(sm.tile[sa]));
+            const uint64_t bdesc = make_smem_desc(smem_u32(sm.tile[sb]));
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACCW + P::mma_acc(m) * 128);
+            const bool first = (c == 0) && (m < (I8 ? 1 : 3));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_2sm<I8>(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                           (first && kk == 0) ? 0u : 1u);
+#pragma unroll
+            for (int l = 0; l < P::NL; ++l)
+              if ((P::release(m) >> l) & 1u) tcgen05_commit_2sm(&sm.empty[(lc0 + l) % NSLOT]);
+          }
+        }
+        tcgen05_commit_2sm(&sm.tfull[as]);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): this CTA's 128 rows x N2 columns =====
+    constexpr int HALF = SM::HALF;
+    constexpr int WCOLS = N2 / 2;          // columns per epilogue warp
+    const int q = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    const int lrow = q * 32 + lane;
+    const int et = threadIdx.x - 64;       // 0..255
+    TO *__restrict__ D = static_cast<TO *>(p.D);
+    TO(*stage)[HALF + 1] = sm.stage[warp - 2];
+    const uint32_t leader_tempty0 = mapa_u32(smem_u32(&sm.tempty[0]), 0);
+    const uint32_t leader_tempty1 = mapa_u32(smem_u32(&sm.tempty[1]), 0);
+    int64_t it = 0;
+    for (int64_t work = wstart; work < nwork; work += wstride, ++it) {
+      int ti, tj;
+      tile2_of(work, p.nrow_tiles, 256 / N2, p.ncol_tiles, ti, tj);
+      const int row0 = ti * 256 + (int)crank * 128, col0 = tj * N2;
+      const int64_t gi = (int64_t)row0 + lrow;
+      // strictly below the diagonal and fully inside the map: no per-element tests
+      const bool whole = (int64_t)col0 + N2 <= row0 && (int64_t)row0 + 128 <= p.n;
+      unsigned long long mrow[PW];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int w = 0; w < PW; ++w) mrow[w] = gi < p.n ? p.pmask[gi * PW + w] : 0ull;
+      if (et < N2) {
+        const int64_t gj = (int64_t)col0 + et;
+#pragma unroll
+        for (int w = 0; w < PW; ++w) sm.pm[et][w] = gj < p.n ? p.pmask[gj * PW + w] : 0ull;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int as = (int)(it % NACC);
+      mbar_wait(&sm.tfull[as], (uint32_t)((it / NACC) & 1));
+      tcgen05_fence_after();
+      for (int part = 0; part < WCOLS; part += HALF) {
+        const int cbase = ch * WCOLS + part;
+        for (int cb = cbase; cb < cbase + HALF; cb += 16) {
+          uint32_t v0[16], v1[16], v2[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACCW + cb);
+          tmem_ld16(taddr, v0);
+          if (!I8) {
+            tmem_ld16(taddr + 128, v1);
+            tmem_ld16(taddr + 256, v2);
+          }
+          tmem_ld_wait();
+          TO *mir = D + ((int64_t)col0 + cb) * p.ld + gi;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            int den = 0;
+#pragma unroll
+            for (int w = 0; w < PW; ++w) den += __popcll(mrow[w] & sm.pm[cb + e][w]);
+            double num;
+            if (I8) num = (double)(int)v0[e];
+            else num = ((double)__uint_as_float(v0[e]) + (double)__uint_as_float(v1[e])) + (double)__uint_as_float(v2[e]);
+            TO d = (TO)0;
+            if (den > 0) {
+              if (sizeof(TO) == 8) d = (TO)__ddiv_rn(num, (double)den);
+              else if (I8) d = (TO)__fdiv_rn((float)num, (float)den);
+              else d = (TO)__double2float_rn(__ddiv_rn(num, (double)den));
+            }
+            const int64_t gj = (int64_t)col0 + cb + e;
+            if (gj == gi) d = (TO)0;
+            stage[lane][(cb - cbase) + e] = d;
+            // every unordered pair is produced once: only elements on or below the diagonal are used
+            if (whole || (gi < p.n && gj < gi)) mir[(int64_t)e * p.ld] = d;
+          }
+        }
+        if (part + HALF == WCOLS) {
+          tcgen05_fence_before();
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                           as == 0 ? leader_tempty0 : leader_tempty1)
+                       : "memory");
+        }
+        __syncwarp();
+        TO *dst = D + ((int64_t)row0 + q * 32) * p.ld + col0 + cbase;
+        for (int rr = 0; rr < 32; ++rr, dst += p.ld) {
+          const int64_t grow = (int64_t)row0 + q * 32 + rr;
+          if (!whole && grow >= p.n) break;
+          // direct rows: columns up to and including the diagonal
+          if (whole || (int64_t)col0 + cbase + lane <= grow) dst[lane] = stage[rr][lane];
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ---- operand encoding (K1) -----------------------------------------------------------------
 // one thread per (cell, character); buffers are zero-filled beforehand
 __global__ void encode_i8_kernel(const int32_t *__restrict__ cm, int64_t n, int m, int S, int32_t missing,
@@ -476,12 +795,12 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // [rows, kcols] row-major matrix of `esz`-byte elements, box = 128 bytes x 128 rows, 128B swizzle
-static int make_map(CUtensorMap *map, void *base, int64_t rows, int64_t kcols, int esz) {
+static int make_map(CUtensorMap *map, void *base, int64_t rows, int64_t kcols, int esz, int box_rows = GT) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return CAS_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)kcols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(kcols * esz)};
-  cuuint32_t box[2] = {(cuuint32_t)(CHUNK_BYTES / esz), (cuuint32_t)GT};
+  cuuint32_t box[2] = {(cuuint32_t)(CHUNK_BYTES / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult rc = fn(map, esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base,
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -504,6 +823,12 @@ static GemmLayout layout_of(int m, int S) {
   L.Kx = round_up64((int64_t)m * S, CHUNK_BYTES / 2);
   L.Kd = round_up64(m, CHUNK_BYTES / 2);
   return L;
+}
+
+// CAS_GEMM_CTA_GROUP=1 selects the single-SM 128 x 128 kernel, 2 (default) the SM-pair kernel
+static int gemm_cta_group() {
+  const char *e = getenv("CAS_GEMM_CTA_GROUP");
+  return (e && e[0] == '1') ? 1 : 2;
 }
 
 size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted) {
@@ -540,6 +865,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.n = n; p.D = D; p.ld = ld;
+  void *map_bases[4] = {nullptr, nullptr, nullptr, nullptr};
   const int64_t nm = n * (int64_t)m;
   const unsigned eb = (unsigned)((nm + 255) / 256);
   int pw = (m + 63) / 64;
@@ -560,6 +886,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     if (rc != CAS_OK) return rc;
     rc = make_map(&p.maps[1], B, n, L.Kp, 1);
     if (rc != CAS_OK) return rc;
+    map_bases[0] = A; map_bases[1] = B;
     p.chunks = (int)(L.Kp / CHUNK_BYTES);
   } else {
     __nv_bfloat16 *XW[3];
@@ -575,7 +902,67 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     }
     int rc = make_map(&p.maps[3], Y, n, L.Kx, 2);
     if (rc != CAS_OK) return rc;
+    for (int i = 0; i < 3; ++i) map_bases[i] = XW[i];
+    map_bases[3] = Y;
     p.chunks = (int)(L.Kx / (CHUNK_BYTES / 2));
+  }
+  if (gemm_cta_group() == 2) {
+    // 2-SM kernel: 256-row tiles, N2 = 256 (int8) / 128 (bf16) columns, clusters of two CTAs
+    Gemm2Params q;
+    memset(&q, 0, sizeof(q));
+    q.n = n; q.D = D; q.ld = ld; q.pw = pw; q.pmask = pmask; q.chunks = p.chunks;
+    const int nmaps = weighted ? 4 : 2;
+    const int esz = weighted ? 2 : 1;
+    const int64_t kcols = weighted ? L.Kx : L.Kp;
+    const int N2 = weighted ? 128 : 256;
+    for (int i = 0; i < nmaps; ++i) {
+      q.maps[i] = p.maps[i];
+      void *base = map_bases[i];
+      int rc = make_map(&q.maps_half[i], base, n, kcols, esz, 64);
+      if (rc != CAS_OK) return rc;
+    }
+    q.nrow_tiles = (int)((n + 255) / 256);
+    q.ncol_tiles = (int)((n + N2 - 1) / N2);
+    const int64_t nwork = tile2_count(q.nrow_tiles, 256 / N2, q.ncol_tiles);
+#define LAUNCH_GEMM2(I8, TO, PWV)                                                                  \
+  do {                                                                                             \
+    const size_t smem = sizeof(Gemm2Smem<TO>) + 1024;                                              \
+    CAS_CUDA_TRY(cudaFuncSetAttribute(whd_gemm2_kernel<I8, TO, PWV>,                               \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    cudaLaunchConfig_t cfg;                                                                        \
+    memset(&cfg, 0, sizeof(cfg));                                                                  \
+    cudaLaunchAttribute attr[1];                                                                   \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                              \
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;      \
+    cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;           \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                            \
+    cfg.gridDim = dim3(2);                                                                         \
+    int nclusters = 0;                                                                             \
+    if (cudaOccupancyMaxActiveClusters(&nclusters, whd_gemm2_kernel<I8, TO, PWV>, &cfg) !=         \
+            cudaSuccess || nclusters <= 0) {                                                       \
+      (void)cudaGetLastError();                                                                    \
+      nclusters = sm_count() / 2;                                                                  \
+    }                                                                                              \
+    const int64_t g = nwork < nclusters ? nwork : nclusters;                                       \
+    cfg.gridDim = dim3((unsigned)(2 * g));                                                         \
+    CAS_CUDA_TRY(cudaLaunchKernelEx(&cfg, whd_gemm2_kernel<I8, TO, PWV>, q, nwork));               \
+  } while (0)
+#define LAUNCH_PW2(I8, TO)                                                                         \
+  do {                                                                                             \
+    if (pw == 1) LAUNCH_GEMM2(I8, TO, 1);                                                          \
+    else if (pw == 2) LAUNCH_GEMM2(I8, TO, 2);                                                     \
+    else if (pw <= 4) LAUNCH_GEMM2(I8, TO, 4);                                                     \
+    else LAUNCH_GEMM2(I8, TO, 8);                                                                  \
+  } while (0)
+    if (!weighted) {
+      if (dtype == CAS_F64) LAUNCH_PW2(true, double); else LAUNCH_PW2(true, float);
+    } else {
+      if (dtype == CAS_F64) LAUNCH_PW2(false, double); else LAUNCH_PW2(false, float);
+    }
+#undef LAUNCH_PW2
+#undef LAUNCH_GEMM2
+    CAS_LAUNCH_CHECK();
+    return CAS_OK;
   }
   const int64_t tiles = (n + GT - 1) / GT;
   const int64_t ntiles = tiles * (tiles + 1) / 2;

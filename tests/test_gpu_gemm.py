@@ -9,6 +9,14 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-6  # north-star tolerance for prior-weighted distances (float32 storage)
 
 
+@pytest.fixture(params=["2", "1"], ids=["sm_pair", "single_sm"], autouse=True)
+def cta_group(request, monkeypatch):
+    """Both tensor-core kernels are tested: the SM-pair kernel (tcgen05 cta_group::2, the default) and
+    the single-SM 128 x 128 kernel (CAS_GEMM_CTA_GROUP=1); the library reads the variable per call."""
+    monkeypatch.setenv("CAS_GEMM_CTA_GROUP", request.param)
+    return request.param
+
+
 def _inputs(g):
     w = g.weights
     if w is not None:
@@ -57,7 +65,7 @@ def test_gemm_sizes_not_multiple_of_tile():
     from cassiopeia_b200 import engine
     from cassiopeia_b200.synthetic import simulate_character_matrix
 
-    for n, m, S in ((129, 7, 3), (300, 33, 17), (1000, 40, 50)):
+    for n, m, S in ((5, 3, 2), (129, 7, 3), (255, 20, 9), (257, 20, 9), (300, 33, 17), (1000, 40, 50), (1537, 70, 20)):
         cm, priors, table = simulate_character_matrix(n, m, S, seed=n, mutation_rate=0.7, missing_fraction=0.15)
         with np.errstate(invalid="ignore"):
             w = np.nan_to_num(-np.log(table))
