@@ -825,10 +825,13 @@ static GemmLayout layout_of(int m, int S) {
   return L;
 }
 
-// CAS_GEMM_CTA_GROUP=1 selects the single-SM 128 x 128 kernel, 2 (default) the SM-pair kernel
-static int gemm_cta_group() {
+// CAS_GEMM_CTA_GROUP=1 forces the single-SM 128 x 128 kernel, =2 the SM-pair kernel.  Default: the
+// SM-pair kernel for int8 (operand-feed bound: 1.2-1.7x faster, 75 % tensor-pipe activity at K = 20k)
+// and the single-SM kernel for bf16 (bound by operand latency, not bandwidth; measured 7 % faster).
+static int gemm_cta_group(bool weighted) {
   const char *e = getenv("CAS_GEMM_CTA_GROUP");
-  return (e && e[0] == '1') ? 1 : 2;
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return weighted ? 1 : 2;
 }
 
 size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted) {
@@ -906,7 +909,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     map_bases[3] = Y;
     p.chunks = (int)(L.Kx / (CHUNK_BYTES / 2));
   }
-  if (gemm_cta_group() == 2) {
+  if (gemm_cta_group(weighted) == 2) {
     // 2-SM kernel: 256-row tiles, N2 = 256 (int8) / 128 (bf16) columns, clusters of two CTAs
     Gemm2Params q;
     memset(&q, 0, sizeof(q));
