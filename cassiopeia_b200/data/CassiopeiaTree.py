@@ -56,7 +56,8 @@ class CassiopeiaTree:
 
     @character_matrix.setter
     def character_matrix(self, character_matrix: pd.DataFrame) -> None:
-        if not all(type(i) == str for i in character_matrix.index):
+        index = character_matrix.index
+        if index.inferred_type != "string" and not all(type(i) == str for i in index):
             raise CassiopeiaTreeError("Index of character matrix must consist of strings.")
         self._character_matrix = character_matrix.copy()
 
@@ -146,18 +147,28 @@ class CassiopeiaTree:
         if any(not isinstance(n, str) for n in tree.nodes):
             tree = nx.relabel_nodes(tree, {n: str(n) for n in tree.nodes})
         self._network = tree
-        for n in tree.nodes:
-            tree.nodes[n]["character_states"] = []
+        # networkx's node / adjacency dictionaries are used directly: the view objects cost a Python
+        # call per access, which dominates on trees with 10^5 nodes
+        node_attrs = tree._node
+        for attrs in node_attrs.values():
+            attrs["character_states"] = []
         character_matrix = self.layers[layer] if layer else self.character_matrix
         if character_matrix is not None:
             self.set_character_states_at_leaves(layer=layer)
-        for u, v, attrs in tree.edges(data=True):
-            if "length" not in attrs:
-                attrs["length"] = 1
+        succ = tree._succ
+        for nbrs in succ.values():
+            for attrs in nbrs.values():
+                if "length" not in attrs:
+                    attrs["length"] = 1
         root = self.root
-        tree.nodes[root]["time"] = 0
-        for u, v in nx.dfs_edges(tree, source=root):
-            tree.nodes[v]["time"] = tree.nodes[u]["time"] + tree[u][v]["length"]
+        node_attrs[root]["time"] = 0
+        stack = [root]
+        while stack:
+            u = stack.pop()
+            t = node_attrs[u]["time"]
+            for v, attrs in succ[u].items():
+                node_attrs[v]["time"] = t + attrs["length"]
+                stack.append(v)
 
     def set_character_states_at_leaves(self, character_matrix=None, layer: Optional[str] = None) -> None:
         self._check_tree()
@@ -172,23 +183,27 @@ class CassiopeiaTree:
             raise CassiopeiaTreeError("Character matrix index does not match set of leaves.")
         rows = character_matrix.to_numpy().tolist()
         by_name = dict(zip(character_matrix.index.tolist(), rows))
+        node_attrs = self._network._node
         for n in leaves:
-            self._network.nodes[n]["character_states"] = by_name[n]
+            node_attrs[n]["character_states"] = by_name[n]
 
     @property
     def root(self) -> str:
         self._check_tree()
-        return [n for n in self._network if self._network.in_degree(n) == 0][0]
+        pred = self._network._pred
+        return next(n for n in self._network._node if not pred[n])
 
     @property
     def leaves(self) -> List[str]:
         self._check_tree()
-        return [n for n in self._network if self._network.out_degree(n) == 0]
+        succ = self._network._succ
+        return [n for n in self._network._node if not succ[n]]
 
     @property
     def internal_nodes(self) -> List[str]:
         self._check_tree()
-        return [n for n in self._network if self._network.out_degree(n) > 0]
+        succ = self._network._succ
+        return [n for n in self._network._node if succ[n]]
 
     @property
     def nodes(self) -> List[str]:
@@ -227,6 +242,13 @@ class CassiopeiaTree:
     def set_character_states(self, node: str, states: List[int]) -> None:
         self._check_tree()
         self._network.nodes[node]["character_states"] = list(states)
+
+    def set_internal_character_states(self, states_by_node: Dict[str, List[int]]) -> None:
+        """Bulk form of ``set_character_states`` for internal nodes (used by the array-based solver tail)."""
+        self._check_tree()
+        nodes = self._network.nodes
+        for node, states in states_by_node.items():
+            nodes[node]["character_states"] = states
 
     def get_branch_length(self, parent: str, child: str) -> float:
         self._check_tree()

@@ -152,11 +152,67 @@ class DistanceSolver(abc.ABC):
         self.last_join_list = (joins, last2, names)
         self.finish_tree(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges)
 
+    #: use the array-based tail (cassiopeia_b200/tree_tail.py) when the stock ``root_tree`` is in place
+    fast_tail = True
+
     def finish_tree(self, cassiopeia_tree, names: List[str], joins: np.ndarray, last2: np.ndarray,
                     layer: Optional[str] = None, collapse_mutationless_edges: bool = False) -> None:
-        """Host tail of `solve`: replays an id-space join list (leaf at map row p has id p, the
-        t-th join creates id n+t) through the reference's graph-building sequence (:181-199),
-        roots the tree and populates `cassiopeia_tree` (:207-231)."""
+        """Host tail of `solve`: turns an id-space join list (leaf at map row p has id p, the
+        t-th join creates id n+t) into the rooted, populated tree of reference :181-231.
+
+        Two equivalent routes: the array-based one (`_finish_tree_arrays`) and the
+        generic one that replays the join list through the reference's graph-building calls and hooks
+        (`_finish_tree_generic`; used when a subclass overrides ``root_tree``, for fewer than 3 samples and
+        for non-integer state matrices)."""
+        if self.fast_tail and self._fast_tail_applicable(cassiopeia_tree, names, layer):
+            self._finish_tree_arrays(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges)
+        else:
+            self._finish_tree_generic(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges)
+
+    _stock_root_tree = None  # set by the concrete solvers to their own root_tree
+
+    def _fast_tail_applicable(self, cassiopeia_tree, names, layer) -> bool:
+        if len(names) < 3 or type(self).root_tree is not type(self)._stock_root_tree:
+            return False
+        if self._algo != "upgma" and cassiopeia_tree.root_sample_name not in names:
+            return False
+        character_matrix = cassiopeia_tree.layers[layer] if layer is not None else cassiopeia_tree.character_matrix
+        if character_matrix is None:
+            return True
+        return all(np.issubdtype(dt, np.integer) for dt in character_matrix.dtypes)
+
+    def _finish_tree_arrays(self, cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges) -> None:
+        from .. import tree_tail
+
+        node_name_generator = solver_utilities.node_name_generator()
+        internal_names = [next(node_name_generator) for _ in range(len(joins))]
+        # remove root from character matrix before populating tree (:214-222)
+        if cassiopeia_tree.root_sample_name in cassiopeia_tree.character_matrix.index:
+            cassiopeia_tree.character_matrix = cassiopeia_tree.character_matrix.drop(
+                index=cassiopeia_tree.root_sample_name)
+        leaf_states = None
+        if collapse_mutationless_edges:
+            character_matrix = (cassiopeia_tree.layers[layer] if layer is not None
+                                else cassiopeia_tree.character_matrix)
+            values = character_matrix.to_numpy()
+            pos = character_matrix.index.get_indexer(list(names))
+            leaf_states = np.zeros((len(names), values.shape[1]), dtype=values.dtype)
+            leaf_states[pos >= 0] = values[pos[pos >= 0]]
+        tree, internal_states = tree_tail.build_final_tree(
+            names, internal_names, joins, last2, self._algo, cassiopeia_tree.root_sample_name, leaf_states,
+            cassiopeia_tree.missing_state_indicator, collapse_mutationless_edges)
+        cassiopeia_tree.populate_tree(tree, layer=layer)
+        if internal_states:
+            bulk = getattr(cassiopeia_tree, "set_internal_character_states", None)
+            if bulk is not None:
+                bulk(internal_states)
+            else:  # the reference's tree object: one public call per internal node
+                for node, states in internal_states.items():
+                    cassiopeia_tree.set_character_states(node, states)
+
+    def _finish_tree_generic(self, cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges) -> None:
+        """Replays the join list through the reference's graph-building sequence (:181-199), roots the tree
+        with the (possibly overridden) ``root_tree`` hook and runs the tree object's own collapse passes."""
         node_name_generator = solver_utilities.node_name_generator()
         n = len(names)
         tree = nx.Graph()

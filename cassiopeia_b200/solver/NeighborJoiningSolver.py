@@ -98,3 +98,6 @@ class NeighborJoiningSolver(DistanceSolver):
                 cassiopeia_tree.set_dissimilarity("root", dissimilarity)
         finally:
             cassiopeia_tree.character_matrix = character_matrix
+
+
+NeighborJoiningSolver._stock_root_tree = NeighborJoiningSolver.root_tree

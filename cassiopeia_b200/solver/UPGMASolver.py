@@ -59,3 +59,6 @@ class UPGMASolver(DistanceSolver):
     def setup_root_finder(self, cassiopeia_tree) -> None:
         """The root is created by ``root_tree``; only its name is fixed here (:240-250)."""
         cassiopeia_tree.root_sample_name = "root"
+
+
+UPGMASolver._stock_root_tree = UPGMASolver.root_tree
