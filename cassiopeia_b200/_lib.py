@@ -25,6 +25,7 @@ EXPORTS = (
     "cas_device_info",
     "cas_whd_workspace_bytes",
     "cas_whd_map",
+    "cas_pairwise_map",
     "cas_agglom_workspace_bytes",
     "cas_nj_solve",
     "cas_upgma_solve",
@@ -75,6 +76,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_whd_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
     L.cas_whd_map.restype = ctypes.c_int
     L.cas_whd_map.argtypes = [vp, i64, i32, i32, vp, i32, vp, i64, i32, i64, i64, i32, vp, sz, vp]
+    L.cas_pairwise_map.restype = ctypes.c_int
+    L.cas_pairwise_map.argtypes = [i32, i32, vp, i64, i32, i32, vp, i32, vp, i64, i32, i64, i64, vp, sz, vp]
     L.cas_agglom_workspace_bytes.restype = sz
     L.cas_agglom_workspace_bytes.argtypes = [i64, i32, i32]
     for fn in (L.cas_nj_solve, L.cas_upgma_solve):

@@ -39,6 +39,10 @@ int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
                   int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
                   void *workspace, size_t workspace_bytes, cudaStream_t stream, int cyc_G = 0,
                   int cyc_r = 0);
+int pairwise_exact_map(int32_t fn, int32_t flags, const int32_t *cm, int64_t n, int32_t m, int32_t missing,
+                       const double *w, int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0,
+                       int64_t row1, void *workspace, size_t workspace_bytes, cudaStream_t stream, int cyc_G = 0,
+                       int cyc_r = 0);
 int whd_read_error_flag(const void *workspace, cudaStream_t stream, int *flag);
 size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted);
 int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
@@ -100,6 +104,20 @@ int cas_whd_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const 
   CAS_REQUIRE(method == CAS_MAP_EXACT, "bad map method %d", method);
   return whd_exact_map(cm, n, m, missing, w, n_states, D, ld, dtype, row0, row1, workspace,
                        workspace_bytes, (cudaStream_t)stream);
+}
+
+int cas_pairwise_map(int32_t fn, int32_t flags, const int32_t *cm, int64_t n, int32_t m, int32_t missing,
+                     const double *w, int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0,
+                     int64_t row1, void *workspace, size_t workspace_bytes, void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(cm && D && workspace, "null pointer argument");
+  CAS_REQUIRE(n >= 1 && m >= 1, "empty character matrix (n=%lld, m=%d)", (long long)n, m);
+  CAS_REQUIRE(0 <= row0 && row0 <= row1 && row1 <= n, "bad row block [%lld,%lld)",
+              (long long)row0, (long long)row1);
+  CAS_REQUIRE(ld >= n, "ld=%lld < n=%lld", (long long)ld, (long long)n);
+  CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
+  return pairwise_exact_map(fn, flags, cm, n, m, missing, w, n_states, D, ld, dtype, row0, row1, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
 }
 
 int cas_whd_map_cyclic(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,

@@ -62,11 +62,21 @@ __device__ __forceinline__ float cvt_out<float>(double v) { return __double2floa
 
 // grid.x enumerates tiles.  tri != 0: lower-triangular tiles of the full map, mirrored.
 // tri == 0: all tiles of the row block [row0,row1) x [0,n).
-template <typename T, bool WEIGHTED>
+//
+// FN selects the pair function (CAS_FN_* of cas_b200.h), all of
+// cassiopeia/solver/dissimilarity_functions.py, all symmetric, all accumulated in character order:
+//   0 weighted_hamming_distance (:12-72)            differing present pairs: w(a)+w(b) | 1 | 2, / #present
+//   1 hamming_similarity_without_missing (:75-113)   equal cut states: w(a) | 1, not normalised
+//   2 hamming_similarity_normalized_over_missing (:116-160)   same numerator / #present
+//   3 hamming_distance (:163-194)                    a != b (missing is a state); ignore_missing skips
+//                                                    positions where either is missing; integer
+//   4 weighted_hamming_similarity (:197-240)         equal cut: 2 w(a) | 2; equal uncut: 1 (unweighted only)
+//   5 exponential_negative_hamming_distance (:243-300)   exp(-(0)), 0 when nothing is shared
+template <typename T, bool WEIGHTED, int FN>
 __global__ void __launch_bounds__(256)
 whd_exact_kernel(const uint16_t *__restrict__ codes, const double *__restrict__ wrow, int64_t n,
                  int m, int m_pad, T *__restrict__ D, int64_t ld, int64_t row0, int64_t row1,
-                 int tri, int tiles_x, int cyc_G, int cyc_r) {
+                 int tri, int tiles_x, int cyc_G, int cyc_r, int ignore_missing) {
   __shared__ __align__(16) uint16_t sA[CK][CPAD];
   __shared__ __align__(16) uint16_t sB[CK][CPAD];
   __shared__ __align__(16) double sWA[WEIGHTED ? CK : 1][WPAD];
@@ -134,14 +144,33 @@ whd_exact_kernel(const uint16_t *__restrict__ codes, const double *__restrict__ 
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
           const bool pres = (a[x] != MISS) && (b[y] != MISS);
-          const bool neq = pres && (a[x] != b[y]);
           npres[x][y] += pres ? 1 : 0;
-          if (WEIGHTED) {
-            // d += w(a) + w(b): weights summed first, then accumulated (reference order)
-            const double t = __dadd_rn(wa[x], wb[y]);
-            if (neq) acc[x][y] = __dadd_rn(acc[x][y], t);
+          if (FN == 0 || FN == 5) {
+            const bool neq = pres && (a[x] != b[y]);
+            if (WEIGHTED) {
+              // d += w(a) + w(b): weights summed first, then accumulated (reference order)
+              const double t = __dadd_rn(wa[x], wb[y]);
+              if (neq) acc[x][y] = __dadd_rn(acc[x][y], t);
+            } else {
+              if (neq) inum[x][y] += (a[x] != 0 ? 1 : 0) + (b[y] != 0 ? 1 : 0);
+            }
+          } else if (FN == 1 || FN == 2) {
+            const bool hit = pres && (a[x] == b[y]) && (a[x] != 0);
+            if (WEIGHTED) {
+              if (hit) acc[x][y] = __dadd_rn(acc[x][y], wa[x]);
+            } else {
+              inum[x][y] += hit ? 1 : 0;
+            }
+          } else if (FN == 3) {
+            const bool differ = (a[x] != b[y]) && (pres || !ignore_missing);
+            inum[x][y] += differ ? 1 : 0;
           } else {
-            if (neq) inum[x][y] += (a[x] != 0 ? 1 : 0) + (b[y] != 0 ? 1 : 0);
+            const bool eq = pres && (a[x] == b[y]);
+            if (WEIGHTED) {
+              if (eq && a[x] != 0) acc[x][y] = __dadd_rn(acc[x][y], __dmul_rn(2.0, wa[x]));
+            } else {
+              if (eq) inum[x][y] += (a[x] != 0) ? 2 : 1;
+            }
           }
         }
       }
@@ -159,9 +188,12 @@ whd_exact_kernel(const uint16_t *__restrict__ codes, const double *__restrict__ 
       const int64_t gj = j0 + tx * 4 + y;
       if (gj >= n) continue;
       double v = 0.0;
-      if (npres[x][y] > 0) {
-        const double num = WEIGHTED ? acc[x][y] : (double)inum[x][y];
+      const double num = WEIGHTED ? acc[x][y] : (double)inum[x][y];
+      if (FN == 1 || FN == 3) {
+        v = num;
+      } else if (npres[x][y] > 0) {
         v = __ddiv_rn(num, (double)npres[x][y]);
+        if (FN == 5) v = exp(-v);
       }
       if (gi == gj) v = 0.0;
       const T o = cvt_out<T>(v);
@@ -182,11 +214,27 @@ size_t whd_exact_workspace_bytes(int64_t n, int32_t m, int32_t weighted) {
   return c.used();
 }
 
+int pairwise_exact_map(int32_t fn, int32_t flags, const int32_t *cm, int64_t n, int32_t m, int32_t missing,
+                       const double *w, int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0,
+                       int64_t row1, void *workspace, size_t workspace_bytes, cudaStream_t stream, int cyc_G,
+                       int cyc_r);
+
 int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
                   int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
                   void *workspace, size_t workspace_bytes, cudaStream_t stream, int cyc_G, int cyc_r) {
+  return pairwise_exact_map(CAS_FN_WEIGHTED_HAMMING_DISTANCE, 0, cm, n, m, missing, w, n_states, D, ld, dtype,
+                            row0, row1, workspace, workspace_bytes, stream, cyc_G, cyc_r);
+}
+
+int pairwise_exact_map(int32_t fn, int32_t flags, const int32_t *cm, int64_t n, int32_t m, int32_t missing,
+                       const double *w, int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0,
+                       int64_t row1, void *workspace, size_t workspace_bytes, cudaStream_t stream, int cyc_G,
+                       int cyc_r) {
   CAS_REQUIRE(n_states >= 0 && n_states <= 65534, "n_states=%d outside [0, 65534]", n_states);
-  const bool weighted = (w != nullptr);
+  CAS_REQUIRE(fn >= 0 && fn <= 5, "unknown pair function %d", fn);
+  // hamming_distance takes no weights (reference signature :163-168)
+  const bool weighted = (w != nullptr) && fn != CAS_FN_HAMMING_DISTANCE;
+  const int ignore_missing = (flags & CAS_FN_FLAG_IGNORE_MISSING) ? 1 : 0;
   CAS_REQUIRE(workspace_bytes >= whd_exact_workspace_bytes(n, m, weighted),
               "workspace too small for whd map");
   Carver carve(workspace);
@@ -217,14 +265,29 @@ int whd_exact_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
   CAS_REQUIRE(ntiles < (int64_t)2147483647, "too many tiles");
   if (ntiles == 0) return CAS_OK;
   dim3 grid((unsigned)ntiles);
-#define LAUNCH(T, W)                                                                          \
-  whd_exact_kernel<T, W><<<grid, 256, 0, stream>>>(codes, wrow, n, m, mp, (T *)D, ld, row0,  \
-                                                   row1, full ? 1 : 0, (int)tiles_c, cyc_G, cyc_r)
-  if (dtype == CAS_F64) {
-    if (weighted) LAUNCH(double, true); else LAUNCH(double, false);
-  } else {
-    if (weighted) LAUNCH(float, true); else LAUNCH(float, false);
+#define LAUNCH(T, W, F)                                                                        \
+  whd_exact_kernel<T, W, F><<<grid, 256, 0, stream>>>(codes, wrow, n, m, mp, (T *)D, ld, row0, \
+                                                      row1, full ? 1 : 0, (int)tiles_c, cyc_G, \
+                                                      cyc_r, ignore_missing)
+#define LAUNCH_TW(F)                                                                           \
+  do {                                                                                         \
+    if (dtype == CAS_F64) {                                                                    \
+      if (weighted) LAUNCH(double, true, F); else LAUNCH(double, false, F);                    \
+    } else {                                                                                   \
+      if (weighted) LAUNCH(float, true, F); else LAUNCH(float, false, F);                      \
+    }                                                                                          \
+  } while (0)
+  switch (fn) {
+    case 0: LAUNCH_TW(0); break;
+    case 1: LAUNCH_TW(1); break;
+    case 2: LAUNCH_TW(2); break;
+    case 3:
+      if (dtype == CAS_F64) LAUNCH(double, false, 3); else LAUNCH(float, false, 3);
+      break;
+    case 4: LAUNCH_TW(4); break;
+    default: LAUNCH_TW(5); break;
   }
+#undef LAUNCH_TW
 #undef LAUNCH
   CAS_LAUNCH_CHECK();
   return CAS_OK;

@@ -10,19 +10,30 @@ from ..mixins import DistanceSolverError
 from ..solver import dissimilarity_functions, solver_utilities
 
 
-def _require_gpu_function(dissimilarity_function: Optional[Callable]) -> None:
-    if dissimilarity_function is None or not dissimilarity_functions.is_gpu_kernel(dissimilarity_function):
+_MATCH_LOOKUP = ("hamming_similarity_without_missing", "hamming_similarity_normalized_over_missing",
+                 "weighted_hamming_similarity")
+
+
+def _require_gpu_function(dissimilarity_function: Optional[Callable]) -> str:
+    """Name of the CUDA pair function implementing `dissimilarity_function`; raises otherwise."""
+    name = None if dissimilarity_function is None else dissimilarity_functions.gpu_kernel_name(dissimilarity_function)
+    if name is None:
         raise DistanceSolverError(
-            "only `weighted_hamming_distance` is built as a CUDA kernel; for any other dissimilarity "
+            "only the pair functions of `dissimilarity_functions` (weighted_hamming_distance, the hamming "
+            "similarities, exponential_negative_hamming_distance) are built as CUDA kernels; for any other "
             "function populate the tree with a precomputed dissimilarity map (there is no CPU fallback)"
         )
+    return name
 
 
 def device_map(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dict[int, float]]],
-               dtype: str = "f64", method: str = "exact"):
+               dtype: str = "f64", method: str = "exact", function: str = "weighted_hamming_distance"):
     """[n, ld] CUDA tensor holding the full symmetric map of the int matrix `cm` (rows as given)."""
-    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing, weights)
-    return engine.whd_map(codes, missing_code, table, n_states, dtype=dtype, method=method)
+    lookup = "match" if function in _MATCH_LOOKUP else "mismatch"
+    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing, weights, lookup=lookup)
+    if function != "weighted_hamming_distance":
+        method = "exact"
+    return engine.whd_map(codes, missing_code, table, n_states, dtype=dtype, method=method, function=function)
 
 
 def compute_dissimilarity_map(cm: np.ndarray, C: int, dissimilarity_function: Callable,
@@ -30,11 +41,11 @@ def compute_dissimilarity_map(cm: np.ndarray, C: int, dissimilarity_function: Ca
                               missing_state_indicator: int = -1, threads: int = 1) -> np.ndarray:
     """Condensed float64 vector of the C*(C-1)/2 pairwise dissimilarities, row-major pair
     order -- the contract of cassiopeia/data/utilities.py:189-295 (`threads` is ignored)."""
-    _require_gpu_function(dissimilarity_function)
+    function = _require_gpu_function(dissimilarity_function)
     cm = host_prep.as_int_matrix(cm)[:C]
     if C < 2:
         return np.zeros(0, dtype=np.float64)
-    D = device_map(cm, missing_state_indicator, weights, dtype="f64", method="exact")
+    D = device_map(cm, missing_state_indicator, weights, dtype="f64", method="exact", function=function)
     full = D[:, :C].cpu().numpy()
     iu = np.triu_indices(C, k=1)
     return np.ascontiguousarray(full[iu])
@@ -50,14 +61,14 @@ def dissimilarity_map_frame_inputs(character_matrix, priors, missing_state_indic
     Restates cassiopeia/data/CassiopeiaTree.py:1914-1958: priors -> weights, the
     de-duplication row order, the square map.  `to_host=False` keeps the map on the
     device as an [n, ld] CUDA tensor (used by the solvers for large n)."""
-    _require_gpu_function(dissimilarity_function)
+    function = _require_gpu_function(dissimilarity_function)
     weights = None
     if priors:
         weights = solver_utilities.transform_priors(priors, prior_transformation)
     cm = host_prep.as_int_matrix(character_matrix)
     order = host_prep.reference_row_order(cm)
     names = [character_matrix.index[i] for i in order.tolist()]
-    D = device_map(cm[order], missing_state_indicator, weights, dtype=dtype, method=method)
+    D = device_map(cm[order], missing_state_indicator, weights, dtype=dtype, method=method, function=function)
     if to_host:
         n = cm.shape[0]
         return names, D[:, :n].cpu().numpy()
@@ -65,7 +76,8 @@ def dissimilarity_map_frame_inputs(character_matrix, priors, missing_state_indic
 
 
 def row_to_all_distances(character_matrix, row_name, priors, missing_state_indicator: int,
-                         prior_transformation: str = "negative_log"):
+                         prior_transformation: str = "negative_log",
+                         dissimilarity_function: Optional[Callable] = None):
     """Distances from the sample `row_name` to every sample of `character_matrix` (float64, exact kernel),
     as {name: distance}.  One map row block on the GPU -- used for the implicit-root row when a map already
     exists (reference NeighborJoiningSolver.py:293-307 evaluates the function per leaf in Python)."""
@@ -75,7 +87,12 @@ def row_to_all_distances(character_matrix, row_name, priors, missing_state_indic
     cm = host_prep.as_int_matrix(character_matrix)
     names = list(character_matrix.index)
     r = names.index(row_name)
-    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing_state_indicator, weights)
-    D = engine.whd_map(codes, missing_code, table, n_states, dtype="f64", method="exact", rows=(r, r + 1))
+    function = ("weighted_hamming_distance" if dissimilarity_function is None
+                else _require_gpu_function(dissimilarity_function))
+    lookup = "match" if function in _MATCH_LOOKUP else "mismatch"
+    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing_state_indicator, weights,
+                                                                    lookup=lookup)
+    D = engine.whd_map(codes, missing_code, table, n_states, dtype="f64", method="exact", rows=(r, r + 1),
+                       function=function)
     row = D[0, : len(names)].cpu().numpy()
     return {nm: float(row[i]) for i, nm in enumerate(names)}

@@ -56,12 +56,28 @@ def last_launch_count() -> int:
     return int(_lib.load().cas_last_launch_count())
 
 
+#: pair-function codes of the C ABI (CAS_FN_* in include/cas_b200.h), keyed by the reference's function names
+PAIR_FUNCTIONS = {
+    "weighted_hamming_distance": 0,
+    "hamming_similarity_without_missing": 1,
+    "hamming_similarity_normalized_over_missing": 2,
+    "hamming_distance": 3,
+    "weighted_hamming_similarity": 4,
+    "exponential_negative_hamming_distance": 5,
+}
+
+
 def whd_map(cm, missing: int, weights: Optional[np.ndarray], n_states: int, dtype: str = "f64",
-            method: str = "exact", rows: Optional[Tuple[int, int]] = None, out=None):
+            method: str = "exact", rows: Optional[Tuple[int, int]] = None, out=None,
+            function: str = "weighted_hamming_distance", ignore_missing: bool = False):
     """Pairwise weighted-Hamming map of an int32 [n, m] matrix of compact state codes.
 
     cm may be a numpy array (copied to the device) or a CUDA int32 tensor.  Returns a
     CUDA tensor of shape [rows, ld] (ld = padded_ld(n)); columns >= n are padding.
+
+    `function` names any pair function of the reference's dissimilarity_functions.py (PAIR_FUNCTIONS);
+    all but `weighted_hamming_distance` run on the exact CUDA-core kernel only.  `ignore_missing` is
+    `hamming_distance`'s `ignore_missing_state`.
     """
     torch = _torch()
     L = _lib.load()
@@ -88,10 +104,20 @@ def whd_map(cm, missing: int, weights: Optional[np.ndarray], n_states: int, dtyp
     code = _METHOD[method]
     ws_bytes = int(L.cas_whd_workspace_bytes(n, m, int(n_states), 1 if w_t is not None else 0, code))
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda")
-    rc = L.cas_whd_map(cm_t.data_ptr(), n, m, int(missing), w_t.data_ptr() if w_t is not None else None,
-                       int(n_states), out.data_ptr(), ld, CAS_F64 if dtype == "f64" else CAS_F32,
-                       r0, r1, code, ws.data_ptr(), ws_bytes, _stream_ptr(torch))
-    _lib.check(rc, "cas_whd_map")
+    fn_code = PAIR_FUNCTIONS[function]
+    if fn_code != 0:
+        if method != "exact":
+            raise ValueError(f"`{function}` is built on the exact kernel only (method='exact')")
+        rc = L.cas_pairwise_map(fn_code, 1 if ignore_missing else 0, cm_t.data_ptr(), n, m, int(missing),
+                                w_t.data_ptr() if w_t is not None else None, int(n_states), out.data_ptr(), ld,
+                                CAS_F64 if dtype == "f64" else CAS_F32, r0, r1, ws.data_ptr(), ws_bytes,
+                                _stream_ptr(torch))
+        _lib.check(rc, "cas_pairwise_map")
+    else:
+        rc = L.cas_whd_map(cm_t.data_ptr(), n, m, int(missing), w_t.data_ptr() if w_t is not None else None,
+                           int(n_states), out.data_ptr(), ld, CAS_F64 if dtype == "f64" else CAS_F32,
+                           r0, r1, code, ws.data_ptr(), ws_bytes, _stream_ptr(torch))
+        _lib.check(rc, "cas_whd_map")
     # first int of the workspace: "state outside [0, n_states]" flag set by the encode kernels
     flag = int(ws[:4].view(torch.int32).item())
     if flag:

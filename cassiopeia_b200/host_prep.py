@@ -59,14 +59,17 @@ def reference_row_order(cm: np.ndarray) -> np.ndarray:
     return np.concatenate([uniq, dups])
 
 
-def compact_states(cm: np.ndarray, missing: int,
-                   weights: Optional[Dict[int, Dict[int, float]]]) -> Tuple[np.ndarray, int, Optional[np.ndarray], int]:
+def compact_states(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dict[int, float]]],
+                   lookup: str = "mismatch") -> Tuple[np.ndarray, int, Optional[np.ndarray], int]:
     """Returns (codes int32 [n, m], missing_code, weight_table or None, n_states).
 
-    Raises KeyError where the reference's numba dict lookup would: a weighted character
+    Raises KeyError where the reference's numba dict lookup would.  lookup="mismatch"
+    (weighted_hamming_distance, exponential_negative_hamming_distance): a weighted character
     that shows at least two distinct present states must have a weight for each of its
     non-zero states (a state is only looked up when it takes part in a mismatch,
-    dissimilarity_functions.py:56-69).
+    dissimilarity_functions.py:56-69).  lookup="match" (the similarity functions, :104-110,
+    :150-156, :228-233): a non-zero state is looked up when two samples share it, so every
+    non-zero state carried by at least two samples needs a weight.
     """
     n, m = cm.shape
     present = cm != missing
@@ -108,15 +111,19 @@ def compact_states(cm: np.ndarray, missing: int,
         table = np.zeros((m, n_states + 1), dtype=np.float64)
         for c in range(m):
             col = codes[:, c]
-            seen = np.unique(col[col != missing_code])
-            if seen.size < 2:
-                continue  # no mismatch possible at this character: never looked up
+            seen, counts = np.unique(col[col != missing_code], return_counts=True)
+            if lookup == "mismatch":
+                if seen.size < 2:
+                    continue  # no mismatch possible at this character: never looked up
+                needed = seen[seen != 0]
+            else:
+                needed = seen[(seen != 0) & (counts >= 2)]
+                if needed.size == 0:
+                    continue
             if c not in weights:
                 raise KeyError(c)
             wc = weights[c]
-            for code in seen.tolist():
-                if code == 0:
-                    continue
+            for code in needed.tolist():
                 label = code if label_of is None else int(label_of[c][code])
                 if label not in wc:
                     raise KeyError(label)

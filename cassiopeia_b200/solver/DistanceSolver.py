@@ -69,6 +69,8 @@ class DistanceSolver(abc.ABC):
             return self.map_method
         if cassiopeia_tree.priors or character_matrix.shape[1] > 512:
             return "exact"
+        if dissimilarity_functions.gpu_kernel_name(self.dissimilarity_function) != "weighted_hamming_distance":
+            return "exact"
         return "tensor"
 
     # ------------------------------------------------------------ map handling

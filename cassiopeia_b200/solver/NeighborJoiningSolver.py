@@ -80,7 +80,8 @@ class NeighborJoiningSolver(DistanceSolver):
                 # one row block of the CUDA map kernel instead of n Python calls
                 dissimilarity = data_utilities.row_to_all_distances(
                     rooted_character_matrix, "root", cassiopeia_tree.priors,
-                    cassiopeia_tree.missing_state_indicator, self.prior_transformation)
+                    cassiopeia_tree.missing_state_indicator, self.prior_transformation,
+                    self.dissimilarity_function)
                 dissimilarity["root"] = 0
                 cassiopeia_tree.set_dissimilarity("root", dissimilarity)
             else:

@@ -94,6 +94,31 @@ CAS_API int cas_whd_map(const int32_t *cm_dev, int64_t n, int32_t m, int32_t mis
                 int64_t row1, int32_t method, void *workspace_dev, size_t workspace_bytes,
                 void *stream);
 
+/* ---- the other pairwise functions of cassiopeia/solver/dissimilarity_functions.py ----------
+ * Same layout, workspace (cas_whd_workspace_bytes(..., CAS_MAP_EXACT)) and bit-exact float64
+ * accumulation in character order as cas_whd_map(method = CAS_MAP_EXACT); `fn` selects the pair
+ * function.  Replaces cassiopeia/data/utilities.py:189-295 `compute_dissimilarity_map` called with
+ *   CAS_FN_WEIGHTED_HAMMING_DISTANCE                    dissimilarity_functions.py:12-72
+ *   CAS_FN_HAMMING_SIMILARITY_WITHOUT_MISSING           :75-113  (SharedMutationJoiningSolver's default)
+ *   CAS_FN_HAMMING_SIMILARITY_NORMALIZED_OVER_MISSING   :116-160
+ *   CAS_FN_HAMMING_DISTANCE                             :163-194 (integer; w_dev ignored; flag
+ *                                                       CAS_FN_FLAG_IGNORE_MISSING = ignore_missing_state)
+ *   CAS_FN_WEIGHTED_HAMMING_SIMILARITY                  :197-240
+ *   CAS_FN_EXPONENTIAL_NEGATIVE_HAMMING_DISTANCE        :243-300 (exp() within 1 ulp of the host libm)
+ * The diagonal is 0 for every function (the reference fills only i < j, scipy squareform zeroes it).
+ */
+#define CAS_FN_WEIGHTED_HAMMING_DISTANCE 0
+#define CAS_FN_HAMMING_SIMILARITY_WITHOUT_MISSING 1
+#define CAS_FN_HAMMING_SIMILARITY_NORMALIZED_OVER_MISSING 2
+#define CAS_FN_HAMMING_DISTANCE 3
+#define CAS_FN_WEIGHTED_HAMMING_SIMILARITY 4
+#define CAS_FN_EXPONENTIAL_NEGATIVE_HAMMING_DISTANCE 5
+#define CAS_FN_FLAG_IGNORE_MISSING 1
+CAS_API int cas_pairwise_map(int32_t fn, int32_t flags, const int32_t *cm_dev, int64_t n, int32_t m,
+                     int32_t missing, const double *w_dev, int32_t n_states, void *D_dev, int64_t ld,
+                     int32_t dtype, int64_t row0, int64_t row1, void *workspace_dev, size_t workspace_bytes,
+                     void *stream);
+
 /* ---- agglomeration loops ---------------------------------------------------
  * D_dev    : [n, ld] symmetric map (both triangles valid), destroyed.  ld % 32 == 0.
  * joins_dev: [max(n-2,0), 2] int32 out; join t merges ids (lo, hi) into id n+t

@@ -36,6 +36,11 @@ def lib() -> ctypes.CDLL:
         L.oracle_whd_pair.argtypes = [vp, vp, ctypes.c_int, i64, vp, ctypes.c_int]
         L.oracle_whd_map_rows.restype = None
         L.oracle_whd_map_rows.argtypes = [vp, i64, ctypes.c_int, i64, vp, ctypes.c_int, i64, i64, vp, ctypes.c_int]
+        L.oracle_pair_fn.restype = dbl
+        L.oracle_pair_fn.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, i64, vp, ctypes.c_int]
+        L.oracle_pairwise_map_rows.restype = None
+        L.oracle_pairwise_map_rows.argtypes = [ctypes.c_int, ctypes.c_int, vp, i64, ctypes.c_int, i64, vp,
+                                               ctypes.c_int, i64, i64, vp, ctypes.c_int]
         L.oracle_nj.restype = ctypes.c_int
         L.oracle_nj.argtypes = [vp, i64, vp, vp, i64, ctypes.c_int]
         L.oracle_upgma.restype = ctypes.c_int
@@ -141,6 +146,43 @@ def whd_map(cm: np.ndarray, missing: int = -1, table: Optional[np.ndarray] = Non
         int(table.shape[1]) if table is not None else 0,
         int(r0), int(r1), out.ctypes.data, int(threads),
     )
+    return out
+
+
+#: pair-function codes (the product's CAS_FN_* values; names = reference function names)
+PAIR_FUNCTIONS = {
+    "weighted_hamming_distance": 0,
+    "hamming_similarity_without_missing": 1,
+    "hamming_similarity_normalized_over_missing": 2,
+    "hamming_distance": 3,
+    "weighted_hamming_similarity": 4,
+    "exponential_negative_hamming_distance": 5,
+}
+
+
+def pair_fn(fn: str, s1, s2, missing=-1, table: Optional[np.ndarray] = None, ignore_missing: bool = False) -> float:
+    a = np.ascontiguousarray(s1, dtype=np.int64)
+    b = np.ascontiguousarray(s2, dtype=np.int64)
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.float64)
+    return float(lib().oracle_pair_fn(
+        PAIR_FUNCTIONS[fn], 1 if ignore_missing else 0, a.ctypes.data, b.ctypes.data, int(a.shape[0]),
+        int(missing), table.ctypes.data if table is not None else None,
+        int(table.shape[1]) if table is not None else 0))
+
+
+def pairwise_map(fn: str, cm: np.ndarray, missing: int = -1, table: Optional[np.ndarray] = None,
+                 ignore_missing: bool = False, threads: int = 0) -> np.ndarray:
+    """Full symmetric float64 map of any pair function of the reference's dissimilarity_functions.py."""
+    cm = np.ascontiguousarray(cm, dtype=np.int64)
+    n, m = cm.shape
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.float64)
+    out = np.empty((n, n), dtype=np.float64)
+    lib().oracle_pairwise_map_rows(
+        PAIR_FUNCTIONS[fn], 1 if ignore_missing else 0, cm.ctypes.data, n, m, int(missing),
+        table.ctypes.data if table is not None else None, int(table.shape[1]) if table is not None else 0,
+        0, n, out.ctypes.data, int(threads))
     return out
 
 
