@@ -193,8 +193,8 @@ def test_gpu_pairwise_maps_match_oracle_at_size():
 @pytest.mark.gpu
 def test_gpu_compute_dissimilarity_map_with_similarity_function():
     """The reference-facing wrapper (data/utilities.py:189-295 contract: condensed vector, pair order)."""
-    import cassiopeia_b200 as cb
     from cassiopeia_b200.data import utilities
+    from cassiopeia_b200.mixins import DistanceSolverError
     from cassiopeia_b200.solver import dissimilarity_functions as df
 
     z, cm, missing, tab = golden_inputs(pairwise_goldens()[0])
@@ -203,5 +203,5 @@ def test_gpu_compute_dissimilarity_map_with_similarity_function():
     vec = utilities.compute_dissimilarity_map(cm, n, df.hamming_similarity_without_missing, weights, missing)
     iu = np.triu_indices(n, k=1)
     assert np.array_equal(vec, z["hamming_similarity_without_missing_w"][iu])
-    with pytest.raises(cb.DistanceSolverError):
+    with pytest.raises(DistanceSolverError):
         utilities.compute_dissimilarity_map(cm, n, lambda a, b, m, w: 0.0, None, missing)
