@@ -34,6 +34,7 @@ EXPORTS = (
     "cas_nj_q",
     "cas_update_map",
     "cas_agglom_stats",
+    "cas_agglom_scanned_elements",
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
     "cas_sharded_workspace_bytes",
@@ -85,6 +86,8 @@ def _declare(L: ctypes.CDLL) -> None:
         fn.argtypes = [vp, i64, i64, i32, i32, i64, vp, vp, vp, sz, vp]
     L.cas_agglom_stats.restype = ctypes.c_int
     L.cas_agglom_stats.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.cas_agglom_scanned_elements.restype = ctypes.c_int
+    L.cas_agglom_scanned_elements.argtypes = [vp, i64, vp, ctypes.POINTER(i64)]
     L.cas_nj_q.restype = ctypes.c_int
     L.cas_nj_q.argtypes = [vp, i64, i64, vp, vp, vp]
     L.cas_update_map.restype = ctypes.c_int

@@ -128,6 +128,289 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pruned scan (exact): SURVEY §8(f) rank 4, "exact accelerated NJ beyond the dense scan".
+//
+// LB[i][s] (float, order-preserving encoding, row-major) is a LOWER bound of d(i, j) over the live columns
+// j < i of sub-segment s (SW = 128 columns).  For NJ, Rsub[s] is an UPPER bound of the row sums of the slots
+// of sub-segment s, so every pair of (row i, sub-segment s) has
+//     q = d - tinv (R_i + R_j)  >=  LB[i][s] - tinv (R_i + Rsub[s])      (UPGMA: q = d >= LB[i][s]).
+// `gbest` is the exact criterion value of some real live pair -- warm-started by the previous merge from the
+// previous scan's per-CTA winners re-evaluated with the new row sums, lowered by every warp that finds a
+// better pair -- hence an upper bound of the minimum.  A sub-segment whose bound exceeds gbest by more than
+// the near-tie window can hold neither the minimum nor a tie nor a near-tie and is skipped without touching
+// the map; everything else is screened and evaluated exactly as in the dense kernel, so the selected pair
+// and the near-tie diagnostics are IDENTICAL to the dense scan's whatever the timing of the gbest updates.
+// Bounds are kept valid, not tight:
+//   * a scanned sub-segment stores its exact minimum (self-healing: loose bounds get scanned, then are tight);
+//   * the merge lowers the bounds of the rewritten column entries (new values in column lo, moved values in
+//     column hi) with atomicMin and rebuilds Rsub with atomicMax; removed elements only leave a bound loose;
+//   * the launch's last CTA marks rows lo and hi unknown (-inf: they are rescanned once, 2k elements) and
+//     clears Rsub / gbest for the merge.
+// Initially every bound is -inf, so the first iteration is a dense scan that fills LB.
+// One warp owns a row: lane = sub-segment, so the bounds of 4096 columns are one coalesced 128-byte load
+// and one ballot; needed sub-segments are read four at a time (four 128-bit loads in flight per lane).
+// u_j = fl32(tinv R_j) comes from the global array `uf` the merge maintains (L1-resident) instead of the
+// dense kernel's shared-memory staging, because neighbouring warps work on unrelated columns.
+constexpr int SW = 128;  // columns per lower bound
+constexpr int POOL = 512;  // pairs kept to warm-start the bound (>= CTAs of the pruned scan)
+
+struct PruneArgs {
+  unsigned *LB;               // [n][stride]
+  int64_t stride;             // sub-segments per row, multiple of 32
+  unsigned *Rsub;             // [stride] encoded float, NJ only
+  const float *uf;            // [n] fl32(tinv * R_j), NJ only
+  unsigned long long *gbest;  // encoded double
+  unsigned long long *scanned;  // statistics: map elements actually read
+  unsigned long long *cta_read; // [gridDim] per-CTA element counts of this launch (summed by the last CTA)
+};
+
+template <typename T, bool NJ>
+struct RowScan {
+  static constexpr int V = VecOf<T>::N;
+  const double *R;
+  const int32_t *ids;
+  double tinv, umax;
+  double bq, b2;
+  int bi, bj;
+  int i;
+  double Ri, ui;
+  double cap;  // gbest + margin: exact evaluation (and candidate recording) stops above it.  The margin is
+               // the near-tie window or 1 % of |gbest|, whichever is larger: pairs above the window cannot
+               // win, tie or be a near-tie runner-up; the extra 1 % keeps the per-CTA winners that warm-start
+               // the next iteration's bound plentiful at negligible cost
+  float thr;
+  // near-tie window of the diagnostics (1e-6 relative, absolute below 1) around the value x
+  static __device__ __forceinline__ double window(double x) { return 1.0000001e-6 * fmax(1.0, fabs(x)); }
+  // the lane's own best is usually far looser than the global bound (a lane sees few elements per launch)
+  __device__ __forceinline__ float threshold() const {
+    const double best = bi >= 0 ? fmin(bq, cap) : cap;
+    if (best == INFINITY) return INFINITY;
+    if (!NJ) return __double2float_ru(best);
+    const double B = best + ui;
+    return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + 1e-300);
+  }
+  __device__ __forceinline__ void set_cap(double gb) {
+    const double c = gb + fmax(window(gb), 0.01 * fabs(gb)) + 1e-9 * fabs(gb);
+    if (c < cap) { cap = c; thr = threshold(); }
+  }
+  __device__ __forceinline__ void set_row(int row, double ri) {
+    i = row; Ri = ri;
+    ui = NJ ? __dmul_rn(tinv, Ri) : 0.0;
+    thr = threshold();
+  }
+  // one 128-bit vector of row i starting at column j; columns >= jend are not part of the triangle.
+  // Returns the minimum of the float32 (rounded-down) dissimilarities of the valid columns.
+  __device__ __forceinline__ float vec(const T (&v)[V], const float (&su)[V], int j, int jend) {
+    float sv[V], qf[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      sv[e] = (j + e < jend) ? screen_value(v[e]) : INFINITY;
+      qf[e] = NJ ? __fsub_rn(sv[e], su[e]) : sv[e];
+    }
+    float m = qf[0], dm = sv[0];
+#pragma unroll
+    for (int e = 1; e < V; ++e) { m = fminf(m, qf[e]); dm = fminf(dm, sv[e]); }
+    if (m <= thr) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        if (qf[e] <= thr && j + e < jend) {
+          double q = (double)v[e];
+          if (NJ) q = __dsub_rn(q, __dmul_rn(tinv, __dadd_rn(Ri, R[j + e])));
+          if (q <= bq || bi < 0) {
+            tie_path<false>(q, i, j + e, bq, bi, bj, b2, ids);
+            thr = threshold();
+          } else {
+            b2 = fmin(b2, q);
+          }
+        }
+      }
+    }
+    return dm;
+  }
+};
+
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a, PruneArgs p) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int LOADS = SW / (32 * V);  // 128-bit loads per lane and sub-segment (1 float, 2 double)
+  constexpr int G = 8 / LOADS;          // sub-segments in flight: eight 128-bit loads per lane
+  constexpr int CH = 8;                 // chunks of 32 sub-segments decided together (32768 columns)
+  __shared__ Cand sCand[SCAN_WARPS];
+  __shared__ bool sLast;
+  __shared__ unsigned long long sRead[SCAN_WARPS];
+  __shared__ unsigned short sList[SCAN_WARPS][CH * 32];  // per warp: needed sub-segments of the round
+
+  const T *__restrict__ D = static_cast<const T *>(a.D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = a.k;
+  RowScan<T, NJ> rs;
+  rs.R = a.R; rs.ids = a.ids; rs.tinv = a.tinv;
+  rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
+  rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
+  double gb_seen = INFINITY;  // latest value of gbest this warp has read or written
+  unsigned long long nread = 0;
+  const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
+  unsigned short *list = sList[warp];
+
+  // rows are dealt to warps from the bottom (longest first)
+  for (int i = k - 1 - gw; i >= 1; i -= W) {
+    const T *__restrict__ row = D + (int64_t)i * a.ld;
+    rs.set_row(i, NJ ? a.R[i] : 0.0);
+    unsigned *lbrow = p.LB + (int64_t)i * p.stride;
+    const int nsub = (i + SW - 1) / SW;  // sub-segments holding a column < i
+    bool scanned_any = false;
+    for (int sb = 0; sb < nsub; sb += CH * 32) {
+      // ---- decide: lane l looks at sub-segments sb + 32 c + l, c < CH (coalesced 128-byte loads)
+      const double gb = dec_f64(__ldcg(p.gbest));
+      gb_seen = gb;
+      rs.set_cap(gb);
+      unsigned lbv[CH], rsv[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int sgm = sb + c * 32 + lane;
+        lbv[c] = sgm < nsub ? lbrow[sgm] : enc_f32(INFINITY);
+        rsv[c] = (NJ && sgm < nsub) ? p.Rsub[sgm] : enc_f32(0.f);
+      }
+      unsigned flags = 0;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        if (sb + c * 32 >= nsub) break;  // warp-uniform: no sub-segment of this chunk exists
+        const double lb = (double)dec_f32(lbv[c]);
+        double bound = lb, mag = fabs(lb) + fabs(gb);
+        if (NJ) {
+          const double us = a.tinv * (double)dec_f32(rsv[c]);
+          bound = lb - (rs.ui + us);
+          mag += fabs(rs.ui) + fabs(us);
+        }
+        // near-tie window + rounding slack of the bound
+        const double window = RowScan<T, NJ>::window(gb) + 1e-9 * mag;
+        const bool nd = (sb + c * 32 + lane < nsub) && !(bound > gb + window);  // true while gb = +inf / lb = -inf
+        flags |= (nd ? 1u : 0u) << c;
+      }
+      // ---- compact the needed sub-segments into the warp's list
+      const int cnt = __popc(flags);
+      int pre = cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, pre, off);
+        if (lane >= off) pre += o;
+      }
+      const int total = __shfl_sync(0xffffffffu, pre, 31);
+      if (total == 0) continue;
+      {
+        int wpos = pre - cnt;
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          if ((flags >> c) & 1u) list[wpos++] = (unsigned short)(c * 32 + lane);
+      }
+      __syncwarp();
+      // ---- read them, G at a time
+      for (int base = 0; base < total; base += G) {
+        int sg[G];
+        T v[G][LOADS][V];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          sg[g] = (base + g < total) ? sb + (int)list[base + g] : -1;
+          if (sg[g] >= 0) {
+#pragma unroll
+            for (int l = 0; l < LOADS; ++l) {
+              const int j = sg[g] * SW + l * 32 * V + lane * V;
+              if (j < i) {
+                ld_stream<false>(row + j, v[g][l]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[g][l][e] = (T)INFINITY;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (sg[g] < 0) continue;  // warp-uniform
+          float dm = INFINITY;
+#pragma unroll
+          for (int l = 0; l < LOADS; ++l) {
+            const int j = sg[g] * SW + l * 32 * V + lane * V;
+            float su[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) su[e] = 0.f;
+            if (NJ && j < i) {
+              if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
+              else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
+            }
+            dm = fminf(dm, rs.vec(v[g][l], su, j, i));
+          }
+          const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32(dm));
+          if (lane == 0) lbrow[sg[g]] = m;
+          nread += (unsigned long long)(min(i, (sg[g] + 1) * SW) - sg[g] * SW);
+        }
+      }
+      scanned_any = true;
+      __syncwarp();  // the list is rewritten by the next round
+    }
+    if (scanned_any) {
+      double wb = rs.bq;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, off));
+      // publish only real improvements of the global bound (one address: keep the atomics rare)
+      if (wb < gb_seen) {
+        if (lane == 0) atomicMin(p.gbest, enc_f64(wb));
+        gb_seen = wb;
+        rs.set_cap(wb);
+      }
+    }
+  }
+
+  if (lane == 0) sRead[warp] = nread;
+  Cand c = block_best(rs.bq, rs.bi, rs.bj, rs.b2, a.ids, sCand);  // contains a __syncthreads
+  if (threadIdx.x == 0) {
+    a.cand[blockIdx.x] = c;
+    unsigned long long tot = 0;
+    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) tot += sRead[w2];
+    p.cta_read[blockIdx.x] = tot;
+    __threadfence();
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
+  const int lo = min(c.si, c.sj), hi = max(c.si, c.sj);
+  if (threadIdx.x == 0) {
+    Sel s;
+    s.lo = lo;
+    s.hi = hi;
+    s.dij = (double)D[(int64_t)s.lo * a.ld + s.hi];
+    s.size_lo = a.sizes ? a.sizes[s.lo] : 1;
+    s.size_hi = a.sizes ? a.sizes[s.hi] : 1;
+    s.id_lo = a.ids[s.lo];
+    s.id_hi = a.ids[s.hi];
+    *a.sel = s;
+    a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
+    a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
+    const double gap = c.q2 - c.q;
+    if (gap <= 1e-6 * fmax(1.0, fabs(c.q))) atomicAdd(a.stats + 0, 1ull);
+    if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
+    *p.gbest = enc_f64(INFINITY);
+  }
+  {
+    unsigned long long tot = 0;
+    for (int x = threadIdx.x; x < (int)gridDim.x; x += SCAN_THREADS) tot += __ldcg(p.cta_read + x);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if (lane == 0 && tot) atomicAdd(p.scanned, tot);
+  }
+  // rows lo and hi are rewritten by the merge: bounds unknown.  Every other CTA has finished (counter).
+  const int nsk = (k + SW - 1) / SW;
+  for (int sgm = threadIdx.x; sgm < nsk; sgm += SCAN_THREADS) {
+    p.LB[(int64_t)lo * p.stride + sgm] = enc_f32(-INFINITY);
+    p.LB[(int64_t)hi * p.stride + sgm] = enc_f32(-INFINITY);
+    if (NJ) p.Rsub[sgm] = enc_f32(-INFINITY);
+  }
+}
+
 struct MergeArgs {
   void *D;
   int64_t ld;
@@ -144,7 +427,46 @@ struct MergeArgs {
   // strict NJ: live slots in id order, double buffered
   const int32_t *order_old; const int32_t *pos_old;
   int32_t *order_new; int32_t *pos_new;
+  // pruned scan (or null): lower bounds [row][sub-segment], per-sub-segment row-sum maxima and
+  // fl32(tinv_next * R) (NJ), last scan's per-CTA winners (warm start of gbest)
+  unsigned *LB; int64_t lb_stride; unsigned *Rsub; float *uf; double tinv_next;
+  const Cand *cand; int ncand; unsigned long long *gbest; int32_t *pool;
 };
+
+// Pruned scan: upper bound of the next iteration's minimum = the smallest criterion value, under the NEW
+// row sums, of a persistent pool of good pairs: entry x keeps the better of its previous pair and the
+// winner CTA x found in the scan that just ended (pairs touching the joined slots are dropped, the moved
+// slot is renamed).  Called by every thread of the merge's last CTA; all other CTAs' writes are fenced.
+template <typename T, bool NJ>
+__device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int hi, int last) {
+  const T *D = static_cast<const T *>(a.D);
+  // value of the pair (x, y), given in pre-merge slots, in the post-merge state; +inf if it no longer exists
+  auto eval = [&](int x, int y, int &si, int &sj) -> double {
+    si = -1; sj = -1;
+    if (x < 0 || y < 0 || x == lo || y == lo || x == hi || y == hi) return INFINITY;
+    if (x == last) x = hi;  // the node of the last slot moved into slot hi (hi != last here)
+    if (y == last) y = hi;
+    if (x >= last || y >= last) return INFINITY;
+    si = max(x, y); sj = min(x, y);
+    double q = (double)__ldcg(D + (int64_t)si * a.ld + sj);
+    if (NJ) q = __dsub_rn(q, __dmul_rn(a.tinv_next, __dadd_rn(__ldcg(a.R + si), __ldcg(a.R + sj))));
+    return q;
+  };
+  double best = INFINITY;
+  for (int x = threadIdx.x; x < POOL; x += MERGE_THREADS) {
+    // entry x of the persistent pool: the better of its old pair and CTA x's winner of the last scan
+    int pi, pj, ci = -1, cj = -1;
+    const double qp = eval(a.pool[2 * x], a.pool[2 * x + 1], pi, pj);
+    double qc = INFINITY;
+    if (x < a.ncand) qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
+    if (qc < qp) { a.pool[2 * x] = ci; a.pool[2 * x + 1] = cj; }
+    else { a.pool[2 * x] = pi; a.pool[2 * x + 1] = pj; }
+    best = fmin(best, fmin(qp, qc));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if ((threadIdx.x & 31) == 0 && best < INFINITY) atomicMin(a.gbest, enc_f64(best));
+}
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
@@ -156,6 +478,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
   const int64_t ld = a.ld;
   const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
   double contrib = 0.0;
+  float r_up = -INFINITY;       // pruned scan: this thread's new row sum, rounded up
 
   if (v < k) {
     if (v == lo) {
@@ -181,14 +504,31 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       contrib = (double)nvs;
       double Rv = 0.0;
       if (a.maintain_R) Rv = __dadd_rn(__dsub_rn(__dsub_rn(a.R[v], da), db), contrib);
+      T moved = (T)0;
       if (hi != last && v != last) {
         // the node in the last live slot moves into slot hi
         const T l = D[(int64_t)last * ld + v];
         D[(int64_t)hi * ld + v] = l;
         D[(int64_t)v * ld + hi] = l;
+        moved = l;
       }
       D[(int64_t)lo * ld + v] = nvs;
       D[(int64_t)v * ld + lo] = nvs;
+      if (a.LB) {
+        // lower bounds follow the values: pair (ve, lo) gets nvs, pair (v, hi) gets the moved value;
+        // rows lo and hi themselves were marked unknown by the scan's last CTA
+        const int ve = (v == last && hi != last) ? hi : v;
+        if (ve > lo && ve != hi)
+          atomicMin(a.LB + (int64_t)ve * a.lb_stride + lo / SW, enc_f32(screen_value(nvs)));
+        if (hi != last && v != last && v > hi)
+          atomicMin(a.LB + (int64_t)v * a.lb_stride + hi / SW, enc_f32(screen_value(moved)));
+        if (a.maintain_R) {
+          const float ru = __double2float_ru(Rv);
+          a.uf[ve] = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
+          if (ve == v) r_up = ru;
+          else atomicMax(a.Rsub + ve / SW, enc_f32(ru));
+        }
+      }
       if (v == last && hi != last) {
         D[(int64_t)hi * ld + lo] = nvs;
         D[(int64_t)lo * ld + hi] = nvs;
@@ -218,6 +558,24 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     }
   }
 
+  if (a.LB && a.maintain_R) {
+    // one atomic per warp: its 32 slots lie in one sub-segment (SW % 32 == 0)
+    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(r_up));
+    if ((threadIdx.x & 31) == 0 && m != enc_f32(-INFINITY)) atomicMax(a.Rsub + (v / SW), m);
+  }
+  if (a.LB && !a.maintain_R) {
+    // UPGMA: no row sums; the last CTA to finish warm-starts gbest
+    __shared__ bool sLastU;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+      sLastU = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sLastU) warm_start_gbest<T, NJ>(a, lo, hi, last);
+    return;
+  }
   if (!a.maintain_R) return;
   {
     // keep the screening bound max|row sum| current (all lanes participate)
@@ -245,7 +603,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
     a.R[lo] = sum;
     atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
+    if (a.LB) {
+      atomicMax(a.Rsub + lo / SW, enc_f32(__double2float_ru(sum)));
+      a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
+    }
   }
+  if (sLast && a.LB) warm_start_gbest<T, NJ>(a, lo, hi, last);
 }
 
 // strict NJ: R[c] = ((0 + d[o_0][c]) + d[o_1][c]) + ... over live nodes in id order.
@@ -317,7 +680,8 @@ __global__ void __launch_bounds__(RS_THREADS) rowsum_seq_kernel(const double *__
 template <typename T>
 __global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ D, int64_t ld, int k,
                                                           double *__restrict__ R,
-                                                          unsigned long long *rmax_bits) {
+                                                          unsigned long long *rmax_bits, unsigned *Rsub,
+                                                          float *uf, double tinv) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= k) return;
@@ -329,7 +693,21 @@ __global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ 
   if (lane == 0) {
     R[row] = s;
     atomicMax(rmax_bits, (unsigned long long)__double_as_longlong(fabs(s)));
+    if (Rsub) {
+      atomicMax(Rsub + row / SW, enc_f32(__double2float_ru(s)));
+      uf[row] = __double2float_rn(__dmul_rn(tinv, s));
+    }
   }
+}
+
+// pruned scan: every bound starts at -inf ("unknown": the first iteration scans everything)
+__global__ void prune_init_kernel(unsigned *LB, int64_t count, unsigned *Rsub, int nsub, unsigned long long *gbest,
+                                  unsigned long long *scanned) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned ninf = enc_f32(-INFINITY);
+  for (int64_t e = x; e < count; e += (int64_t)gridDim.x * blockDim.x) LB[e] = ninf;
+  for (int64_t e = x; e < nsub; e += (int64_t)gridDim.x * blockDim.x) Rsub[e] = ninf;
+  if (x == 0) { *gbest = enc_f64(INFINITY); *scanned = 0ull; }
 }
 
 __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *order, int32_t *pos,
@@ -379,6 +757,10 @@ struct AgglomWorkspace {
   unsigned *counters;
   unsigned long long *rmax_bits;
   unsigned long long *stats;
+  unsigned *LB; unsigned *Rsub; float *uf; unsigned long long *gbest; unsigned long long *scanned;
+  unsigned long long *cta_read;
+  int32_t *pool;
+  int64_t lb_stride;
   size_t bytes;
 };
 
@@ -399,6 +781,14 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.rmax_bits = c.take<unsigned long long>(8);
   w.stats = w.rmax_bits + 2;
   w.candx = c.take<char>(persistent_cand_bytes());
+  w.lb_stride = ((n + SW - 1) / SW + 31) / 32 * 32;
+  w.LB = c.take<unsigned>((size_t)w.lb_stride * (size_t)n);
+  w.Rsub = c.take<unsigned>((size_t)w.lb_stride + 32);
+  w.uf = c.take<float>((size_t)n + 32);
+  w.gbest = c.take<unsigned long long>(2);
+  w.scanned = w.gbest + 1;
+  w.cta_read = c.take<unsigned long long>(MAX_SCAN_CTAS);
+  w.pool = c.take<int32_t>(2 * POOL);
   w.bytes = c.used();
   return w;
 }
@@ -409,6 +799,13 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
 static bool persistent_enabled() {
   const char *e = getenv("CAS_PERSISTENT");
   return e && e[0] == '1';
+}
+
+// CAS_PRUNE=0 selects the dense scan (every live pair read every iteration); default: pruned scan for
+// every mode except strict NJ (whose sequential row sums read the whole map each iteration anyway).
+static bool prune_enabled() {
+  const char *e = getenv("CAS_PRUNE");
+  return !(e && e[0] == '0');
 }
 
 size_t agglom_workspace_bytes(int64_t n) { return carve_workspace(nullptr, n > 0 ? n : 1).bytes; }
@@ -448,14 +845,25 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
                                                   w.rmax_bits);
     CAS_LAUNCH_CHECK();
   }
+  const bool prune = !strict_nj && prune_enabled() && n > 2;
+  if (prune) {
+    prune_init_kernel<<<sms * 4, 256, 0, stream>>>(w.LB, w.lb_stride * n, w.Rsub, (int)w.lb_stride, w.gbest,
+                                                   w.scanned);
+    CAS_LAUNCH_CHECK();
+    CAS_CUDA_TRY(cudaMemsetAsync(w.pool, 0xFF, 2 * POOL * sizeof(int32_t), stream));  // all -1
+  } else {
+    CAS_CUDA_TRY(cudaMemsetAsync(w.scanned, 0, sizeof(unsigned long long), stream));
+  }
   if (fast_nj && n > 2) {
-    rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>((const T *)D, ld, (int)n, w.R, w.rmax_bits);
+    rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>((const T *)D, ld, (int)n, w.R, w.rmax_bits,
+                                                                        prune ? w.Rsub : nullptr, w.uf,
+                                                                        1.0 / (double)(n - 2));
     CAS_LAUNCH_CHECK();
   }
   int64_t k_final = n;
   const int64_t total_iters = n > 2 ? ((max_iters >= 0 && max_iters < n - 2) ? max_iters : n - 2) : 0;
   bool done_persistent = false;
-  if (!strict_nj && total_iters > 0 && persistent_enabled()) {
+  if (!strict_nj && total_iters > 0 && persistent_enabled() && !prune) {
     // whole loop in one cooperative launch (agglom_persistent.cu)
     int rc = persistent_loop(D, n, ld, sizeof(T) == 8 ? CAS_F64 : CAS_F32, NJ ? CAS_ALGO_NJ : CAS_ALGO_UPGMA,
                              total_iters, w.R, w.ids, w.sizes, w.candx, w.partial, w.rmax_bits, w.counters + 4,
@@ -488,7 +896,18 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
     if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
     if (grid < 1) grid = 1;
-    scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+    if (prune) {
+      PruneArgs pa;
+      pa.LB = w.LB; pa.stride = w.lb_stride; pa.Rsub = w.Rsub; pa.uf = w.uf; pa.gbest = w.gbest;
+      pa.scanned = w.scanned; pa.cta_read = w.cta_read;
+      // one warp per row: enough CTAs to give every SM four, never more warps than rows
+      grid = (k + SCAN_WARPS - 1) / SCAN_WARPS;
+      if (grid > sms * 3) grid = sms * 3;  // three resident CTAs per SM (80 registers)
+      if (grid > POOL) grid = POOL;
+      scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
+    } else {
+      scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+    }
     CAS_LAUNCH_CHECK();
 
     MergeArgs ma;
@@ -499,6 +918,9 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.pos_old = strict_nj ? w.pos[cur] : nullptr;
     ma.order_new = strict_nj ? w.order[cur ^ 1] : nullptr;
     ma.pos_new = strict_nj ? w.pos[cur ^ 1] : nullptr;
+    ma.LB = prune ? w.LB : nullptr; ma.lb_stride = w.lb_stride; ma.Rsub = w.Rsub; ma.uf = w.uf;
+    ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
+    ma.cand = w.cand; ma.ncand = grid; ma.gbest = w.gbest; ma.pool = w.pool;
     merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
     CAS_LAUNCH_CHECK();
   }
@@ -531,6 +953,15 @@ int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, in
 }  // namespace cas
 
 namespace cas {
+int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements) {
+  AgglomWorkspace w = carve_workspace(const_cast<void *>(workspace), n > 0 ? n : 1);
+  unsigned long long h = 0;
+  CAS_CUDA_TRY(cudaMemcpyAsync(&h, w.scanned, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (elements) *elements = (int64_t)h;
+  return CAS_OK;
+}
+
 int agglom_read_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *near_ties, int64_t *exact_ties) {
   AgglomWorkspace w = carve_workspace(const_cast<void *>(workspace), n > 0 ? n : 1);
   unsigned long long h[2] = {0, 0};

@@ -106,7 +106,25 @@ __device__ __forceinline__ void warp_atomic_absmax(unsigned long long *dst, doub
     unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
     b = o > b ? o : b;
   }
-  if ((threadIdx.x & 31) == 0) atomicMax(dst, b);
+  // the maximum only ever grows: almost every warp can skip the (single-address) atomic
+  if ((threadIdx.x & 31) == 0 && b > __ldcg(dst)) atomicMax(dst, b);
+}
+
+// Order-preserving unsigned encodings of float / double (unsigned compare == numeric compare), so that
+// atomicMin / atomicMax maintain lower / upper bounds that may be negative.
+__device__ __forceinline__ unsigned enc_f32(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f32(unsigned e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e);
+}
+__device__ __forceinline__ unsigned long long enc_f64(double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_f64(unsigned long long e) {
+  return __longlong_as_double((long long)((e >> 63) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e));
 }
 
 template <typename T> __device__ __forceinline__ T round_to(double v);
@@ -117,12 +135,15 @@ template <> __device__ __forceinline__ double round_to<double>(double v) { retur
 // Scans columns [c0, jend) of one matrix row (slot i) with one warp: float32 screen against the
 // staged u_j block `sU`, exact float64 re-evaluation of the survivors.  (bq, bi, bj) is the
 // lane's running best (value, row slot, column slot).
-template <typename T, bool NJ, bool COH = false>
+//
+// TRACK: additionally returns in `dmin` the lane's minimum of the float32 (rounded-down) dissimilarities
+// it read -- the pruned scan stores the segment minimum as the next iterations' lower bound.
+template <typename T, bool NJ, bool COH = false, bool TRACK = false>
 __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, int jend,
                                                  int lane, const float *sU, const double *R,
                                                  double Ri, double tinv, double umax,
                                                  const int32_t *ids, double &bq, int &bi,
-                                                 int &bj, double &b2) {
+                                                 int &bj, double &b2, float *dmin = nullptr) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;          // independent 128-bit loads in flight per lane
   constexpr int STEP = 32 * V;  // elements per warp-wide load
@@ -161,8 +182,20 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
         float su[V];
         if (V == 4) *reinterpret_cast<float4 *>(su) = *reinterpret_cast<const float4 *>(&sU[j - c0]);
         else *reinterpret_cast<float2 *>(su) = *reinterpret_cast<const float2 *>(&sU[j - c0]);
+        if (TRACK) {
+          float sv[V];
 #pragma unroll
-        for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(screen_value(v[u][e]), su[e]);
+          for (int e = 0; e < V; ++e) sv[e] = screen_value(v[u][e]);
+          float mm = sv[0];
+#pragma unroll
+          for (int e = 1; e < V; ++e) mm = fminf(mm, sv[e]);
+          *dmin = fminf(*dmin, mm);
+#pragma unroll
+          for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(sv[e], su[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(screen_value(v[u][e]), su[e]);
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < V; ++e) qf[e] = screen_value(v[u][e]);
@@ -170,6 +203,7 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
       float m = qf[0];
 #pragma unroll
       for (int e = 1; e < V; ++e) m = fminf(m, qf[e]);
+      if (TRACK && !NJ) *dmin = fminf(*dmin, m);
       if (m <= thr) {
         // rare: exact float64 evaluation of the elements that passed the screen
 #pragma unroll

@@ -50,6 +50,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t agglom_workspace_bytes(int64_t n);
 int agglom_read_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *near_ties, int64_t *exact_ties);
+int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements);
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
                  size_t workspace_bytes, cudaStream_t stream);
@@ -142,6 +143,11 @@ size_t cas_agglom_workspace_bytes(int64_t n, int32_t algo, int32_t mode) {
 int cas_agglom_stats(const void *workspace, int64_t n, void *stream, int64_t *near_ties, int64_t *exact_ties) {
   CAS_REQUIRE(workspace, "null pointer argument");
   return agglom_read_stats(workspace, n, (cudaStream_t)stream, near_ties, exact_ties);
+}
+
+int cas_agglom_scanned_elements(const void *workspace, int64_t n, void *stream, int64_t *elements) {
+  CAS_REQUIRE(workspace, "null pointer argument");
+  return agglom_read_scanned(workspace, n, (cudaStream_t)stream, elements);
 }
 
 int cas_nj_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t mode, int64_t max_iters,

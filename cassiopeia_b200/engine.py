@@ -48,8 +48,9 @@ def device_info() -> dict:
             "total_bytes": tot.value}
 
 
-#: near-tie diagnostics of the most recent `agglomerate` call: {"near_ties": int, "exact_ties": int}
-last_stats = {"near_ties": 0, "exact_ties": 0}
+#: diagnostics of the most recent `agglomerate` call: near / exact ties and the number of map elements the
+#: pruned scan actually read (0 for the dense scan, which reads k(k-1)/2 per iteration)
+last_stats = {"near_ties": 0, "exact_ties": 0, "scanned_elements": 0}
 
 
 def last_launch_count() -> int:
@@ -151,6 +152,10 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     _lib.check(L.cas_agglom_stats(ws.data_ptr(), int(n), _stream_ptr(torch), ctypes.byref(near),
                                   ctypes.byref(exact)), "cas_agglom_stats")
     last_stats["near_ties"], last_stats["exact_ties"] = int(near.value), int(exact.value)
+    scanned = ctypes.c_int64(0)
+    _lib.check(L.cas_agglom_scanned_elements(ws.data_ptr(), int(n), _stream_ptr(torch), ctypes.byref(scanned)),
+               "cas_agglom_scanned_elements")
+    last_stats["scanned_elements"] = int(scanned.value)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     joins_h = joins[:done].cpu().numpy()
     last2_h = last2.cpu().numpy()

@@ -203,6 +203,12 @@ CAS_API int cas_update_map(const double *D_dev, int64_t n, int64_t ld, int32_t a
 CAS_API int cas_agglom_stats(const void *workspace_dev, int64_t n, void *stream, int64_t *near_ties,
                      int64_t *exact_ties);
 
+/* Map elements the scan kernels of the last loop run with this workspace actually read (synchronises
+ * the stream).  The pruned scan (default for every mode but strict NJ; CAS_PRUNE=0 selects the dense
+ * scan) skips row segments whose lower bound proves they hold neither the minimum nor a near-tie; the
+ * dense scan reads k(k-1)/2 elements per iteration and reports 0 here. */
+CAS_API int cas_agglom_scanned_elements(const void *workspace_dev, int64_t n, void *stream, int64_t *elements);
+
 /* number of kernels the last cas_*_solve / cas_whd_map / cas_solve_host call on this
  * thread launched (bench.py's gpu_launches) */
 CAS_API int64_t cas_last_launch_count(void);
