@@ -27,7 +27,7 @@
 
 #include <vector>
 
-#include "agglom_common.cuh"
+#include "agglom_pruned.cuh"
 
 namespace cas {
 
@@ -171,6 +171,67 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) sh_scan_kernel(ShScanArgs a) 
   }
 }
 
+// Pruned scan of the local rows (same row body as the single-GPU scan_pruned_kernel, agglom_pruned.cuh):
+// bounds, gbest and the candidate pool are per rank and never cross the link -- a rank's bound is the value
+// of one of its own real pairs, which is an upper bound of the global minimum as well.
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanArgs a, PruneArgs p) {
+  __shared__ Cand sCand[SCAN_WARPS];
+  __shared__ bool sLast;
+  __shared__ unsigned long long sRead[SCAN_WARPS];
+  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_CH * 32];
+  const T *__restrict__ D = static_cast<const T *>(a.Dloc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = a.k;
+  RowScan<T, NJ> rs;
+  rs.R = a.R; rs.ids = a.ids; rs.tinv = a.tinv;
+  rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
+  rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
+  PruneWarp pw;
+  pw.gb_seen = INFINITY; pw.nread = 0;
+  const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
+  const int nloc = sh_count(k, a.r, a.G);
+  for (int lr = nloc - 1 - gw; lr >= 0; lr -= W) {
+    const int i = sh_slot(lr, a.r, a.G);
+    if (i < 1) continue;
+    rs.set_row(i, NJ ? a.R[i] : 0.0);
+    prune_row<T, NJ>(rs, pw, D + (int64_t)lr * a.ld, p.LB + (int64_t)lr * p.stride, i, a.tinv, p, sList[warp],
+                     lane);
+  }
+  if (lane == 0) sRead[warp] = pw.nread;
+  Cand c = block_best(rs.bq, rs.bi, rs.bj, rs.b2, a.ids, sCand);
+  if (threadIdx.x == 0) {
+    a.cand[blockIdx.x] = c;
+    unsigned long long tot = 0;
+    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) tot += sRead[w2];
+    p.cta_read[blockIdx.x] = tot;
+    __threadfence();
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
+  {
+    unsigned long long tot = 0;
+    for (int x = threadIdx.x; x < (int)gridDim.x; x += SCAN_THREADS) tot += __ldcg(p.cta_read + x);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if (lane == 0 && tot) atomicAdd(p.scanned, tot);
+  }
+  if (a.peers.ex[0] != nullptr) {
+    if (threadIdx.x < a.G) {
+      ShExHeader *h = ex_header(a.peers.ex[threadIdx.x]);
+      h->cand[a.r] = c;
+      __threadfence_system();
+      post_flag(&h->flag1[a.r], a.tag);
+    }
+  } else if (threadIdx.x == 0) {
+    *a.out = c;
+  }
+}
+
 struct ShColsArgs {
   const void *Dloc;
   int64_t ld;
@@ -186,6 +247,8 @@ struct ShColsArgs {
   ShPeers peers;
   unsigned long long tag;
   unsigned *counter;
+  // pruned scan (or null): the joined rows' bounds become unknown, Rsub / gbest are cleared for the merge
+  unsigned *LB; int64_t lb_stride; unsigned *Rsub; unsigned long long *gbest;
 };
 
 template <typename T>
@@ -203,6 +266,16 @@ __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
   const Cand c = reduce_candidates(cand_all, a.G, sCand);
   const int lo = min(c.si, c.sj), hi = max(c.si, c.sj), last = a.k - 1;
   const T *__restrict__ D = static_cast<const T *>(a.Dloc);
+  if (a.LB && blockIdx.x == 0) {
+    const int nsk = (a.k + SW - 1) / SW;
+    const bool own_lo = sh_owner(lo, a.G) == a.r, own_hi = sh_owner(hi, a.G) == a.r;
+    for (int sgm = threadIdx.x; sgm < nsk; sgm += 256) {
+      if (own_lo) a.LB[(int64_t)sh_local(lo, a.G) * a.lb_stride + sgm] = enc_f32(-INFINITY);
+      if (own_hi) a.LB[(int64_t)sh_local(hi, a.G) * a.lb_stride + sgm] = enc_f32(-INFINITY);
+      a.Rsub[sgm] = enc_f32(-INFINITY);
+    }
+    if (threadIdx.x == 0) *a.gbest = enc_f64(INFINITY);
+  }
   const int lr = blockIdx.x * 256 + threadIdx.x;
   if (lr < sh_count(a.k, a.r, a.G)) {
     const T *row = D + (int64_t)lr * a.ld;
@@ -266,7 +339,43 @@ struct ShMergeArgs {
   int maintain_R;
   ShPeers peers;
   unsigned long long tag;
+  // pruned scan (or null), see MergeArgs in agglom.cu
+  unsigned *LB; int64_t lb_stride; unsigned *Rsub; float *uf; double tinv_next;
+  const Cand *cand; int ncand; unsigned long long *gbest; int32_t *pool;
 };
+
+// Per-rank warm start of the pruned scan's bound (cf. warm_start_gbest in agglom.cu): only pairs whose row
+// this rank owns can be evaluated here, and only those enter its pool.
+template <typename T, bool NJ>
+__device__ __forceinline__ void sh_warm_start(const ShMergeArgs &a, int lo, int hi, int last) {
+  const T *D = static_cast<const T *>(a.Dloc);
+  auto eval = [&](int x, int y, int &si, int &sj) -> double {
+    si = -1; sj = -1;
+    if (x < 0 || y < 0 || x == lo || y == lo || x == hi || y == hi) return INFINITY;
+    if (x == last) x = hi;
+    if (y == last) y = hi;
+    if (x >= last || y >= last) return INFINITY;
+    const int ri = max(x, y), cj = min(x, y);
+    if (sh_owner(ri, a.G) != a.r) return INFINITY;
+    si = ri; sj = cj;
+    double q = (double)__ldcg(D + (int64_t)sh_local(ri, a.G) * a.ld + cj);
+    if (NJ) q = __dsub_rn(q, __dmul_rn(a.tinv_next, __dadd_rn(__ldcg(a.R + ri), __ldcg(a.R + cj))));
+    return q;
+  };
+  double best = INFINITY;
+  for (int x = threadIdx.x; x < POOL; x += MERGE_THREADS) {
+    int pi, pj, ci = -1, cj = -1;
+    const double qp = eval(a.pool[2 * x], a.pool[2 * x + 1], pi, pj);
+    double qc = INFINITY;
+    if (x < a.ncand) qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
+    if (qc < qp) { a.pool[2 * x] = ci; a.pool[2 * x + 1] = cj; }
+    else { a.pool[2 * x] = pi; a.pool[2 * x + 1] = pj; }
+    best = fmin(best, fmin(qp, qc));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if ((threadIdx.x & 31) == 0 && best < INFINITY) atomicMin(a.gbest, enc_f64(best));
+}
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) {
@@ -302,6 +411,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
 
   const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
   double contrib = 0.0, mine = 0.0;
+  float r_up = -INFINITY;
   if (v < k) {
     const bool own_v = sh_owner(v, G) == a.r;
     T *row_v = own_v ? D + (int64_t)sh_local(v, G) * ld : nullptr;
@@ -326,6 +436,21 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
       }
       if (own_lo) row_lo[v] = nvs;
       if (own_v) row_v[lo] = nvs;
+      if (a.LB) {
+        const bool moves = (v == last && hi != last);  // this node ends up in slot hi (bounds unknown there)
+        if (own_v && !moves) {
+          unsigned *lbv = a.LB + (int64_t)sh_local(v, G) * a.lb_stride;
+          if (v > lo) atomicMin(lbv + lo / SW, enc_f32(screen_value(nvs)));
+          if (hi != last && v > hi) atomicMin(lbv + hi / SW, enc_f32(screen_value(gathered(2, v))));
+        }
+        if (a.maintain_R) {
+          const int ve = moves ? hi : v;
+          const float ru = __double2float_ru(Rv);
+          a.uf[ve] = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
+          if (!moves) r_up = ru;
+          else atomicMax(a.Rsub + ve / SW, enc_f32(ru));
+        }
+      }
       if (v == last && hi != last) {
         a.ids[hi] = a.ids[last];
         if (a.sizes) a.sizes[hi] = a.sizes[last];
@@ -335,6 +460,21 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
         mine = Rv;
       }
     }
+  }
+  if (a.LB && a.maintain_R) {
+    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(r_up));
+    if ((threadIdx.x & 31) == 0 && m != enc_f32(-INFINITY)) atomicMax(a.Rsub + (v / SW), m);
+  }
+  if (a.LB && !a.maintain_R) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+      sLast = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sLast) sh_warm_start<T, NJ>(a, lo, hi, last);
+    return;
   }
   if (!a.maintain_R) return;
   warp_atomic_absmax(a.rmax_bits, mine);
@@ -357,7 +497,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
     for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
     a.R[lo] = sum;
     atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
+    if (a.LB) {
+      atomicMax(a.Rsub + lo / SW, enc_f32(__double2float_ru(sum)));
+      a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
+    }
   }
+  if (sLast && a.LB) sh_warm_start<T, NJ>(a, lo, hi, last);
 }
 
 // initial row sums of the local rows (same lane-strided order as rowsum_init_kernel)
@@ -402,7 +547,7 @@ __global__ void __launch_bounds__(256) sh_rowsum_kernel(const T *__restrict__ D,
 
 __global__ void sh_rscatter_kernel(const double *gath, int chunk, int k, int G, int r,
                                    double *__restrict__ R, unsigned long long *rmax_bits, ShPeers peers,
-                                   unsigned long long tag) {
+                                   unsigned long long tag, unsigned *Rsub, float *uf, double tinv) {
   if (peers.ex[0] != nullptr) {
     ShExHeader *own = ex_header(peers.ex[r]);
     if (threadIdx.x < G) wait_flag(&own->flag2[threadIdx.x], tag, &own->error);
@@ -414,6 +559,10 @@ __global__ void sh_rscatter_kernel(const double *gath, int chunk, int k, int G, 
   if (v < k) {
     s = gath[(int64_t)sh_owner(v, G) * chunk + sh_local(v, G)];
     R[v] = s;
+    if (Rsub) {
+      atomicMax(Rsub + v / SW, enc_f32(__double2float_ru(s)));
+      uf[v] = __double2float_rn(__dmul_rn(tinv, s));
+    }
   }
   warp_atomic_absmax(rmax_bits, s);
 }
@@ -424,6 +573,16 @@ __global__ void sh_init_kernel(int n, int32_t *ids, int32_t *sizes, unsigned *co
   if (v < n) { ids[v] = v; sizes[v] = 1; }
   if (v < 8) counters[v] = 0;
   if (v == 0) *rmax_bits = 0ull;
+}
+
+__global__ void sh_prune_init_kernel(unsigned *LB, int64_t count, unsigned *Rsub, int nsub, unsigned long long *gbest,
+                                     unsigned long long *scanned, int32_t *pool) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned ninf = enc_f32(-INFINITY);
+  for (int64_t e = x; e < count; e += (int64_t)gridDim.x * blockDim.x) LB[e] = ninf;
+  for (int64_t e = x; e < nsub; e += (int64_t)gridDim.x * blockDim.x) Rsub[e] = ninf;
+  if (x < 2 * POOL) pool[x] = -1;
+  if (x == 0) { *gbest = enc_f64(INFINITY); *scanned = 0ull; }
 }
 
 __global__ void sh_last2_kernel(const int32_t *ids, int32_t *last2) {
@@ -499,6 +658,9 @@ struct ShWorkspace {
   unsigned long long *rmax_bits;
   char *gath;  // max(G*3*chunk*esz, G*chunk*8) bytes
   size_t gath_bytes;
+  // pruned scan
+  unsigned *LB; unsigned *Rsub; float *uf; unsigned long long *gbest; unsigned long long *scanned;
+  unsigned long long *cta_read; int32_t *pool; int64_t lb_stride;
   size_t bytes;
 };
 
@@ -519,6 +681,14 @@ static ShWorkspace sh_carve(void *base, int64_t n, int G, size_t esz) {
   if (per < chunk * 8) per = chunk * 8;
   w.gath_bytes = per * G;
   w.gath = c.take<char>(w.gath_bytes);
+  w.lb_stride = ((n + SW - 1) / SW + 31) / 32 * 32;
+  w.LB = c.take<unsigned>((size_t)w.lb_stride * chunk);
+  w.Rsub = c.take<unsigned>((size_t)w.lb_stride + 32);
+  w.uf = c.take<float>((size_t)n + 32);
+  w.gbest = c.take<unsigned long long>(2);
+  w.scanned = w.gbest + 1;
+  w.cta_read = c.take<unsigned long long>(MAX_SCAN_CTAS);
+  w.pool = c.take<int32_t>(2 * POOL);
   w.bytes = c.used();
   return w;
 }
@@ -548,10 +718,17 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
   const unsigned long long tag0 = epoch << 32;
   Cand *cand_all = ranks[0].w.cand_all;
   char *gath = ranks[0].w.gath;
+  const char *pe = getenv("CAS_PRUNE");
+  const bool prune = !(pe && pe[0] == '0') && n > 2;  // exact pruned scan (agglom_pruned.cuh); CAS_PRUNE=0: dense
   for (auto &rk : ranks) {
     sh_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)n, rk.w.ids, rk.w.sizes,
                                                                     rk.w.counters, rk.w.rmax_bits);
     CAS_LAUNCH_CHECK();
+    if (prune) {
+      sh_prune_init_kernel<<<sms * 4, 256, 0, stream>>>(rk.w.LB, rk.w.lb_stride * sh_chunk((int)n, G), rk.w.Rsub,
+                                                        (int)rk.w.lb_stride, rk.w.gbest, rk.w.scanned, rk.w.pool);
+      CAS_LAUNCH_CHECK();
+    }
   }
   if (NJ && n > 2) {
     const int chunk = sh_chunk((int)n, G);
@@ -570,11 +747,13 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     }
     for (auto &rk : ranks) {
       const double *buf = reinterpret_cast<const double *>(emu ? gath : rk.w.gath);
-      sh_rscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(buf, chunk, (int)n, G, rk.r, rk.w.R,
-                                                                          rk.w.rmax_bits, peers, tag0 + 1);
+      sh_rscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+          buf, chunk, (int)n, G, rk.r, rk.w.R, rk.w.rmax_bits, peers, tag0 + 1, prune ? rk.w.Rsub : nullptr,
+          rk.w.uf, 1.0 / (double)(n - 2));
       CAS_LAUNCH_CHECK();
     }
   }
+  int rk_grid[SH_MAXG] = {0};
   for (int64_t t = 0; t + 2 < n; ++t) {
     if (max_iters >= 0 && t >= max_iters) break;
     const int k = (int)(n - t);
@@ -601,8 +780,20 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
       if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
       if (grid < 1) grid = 1;
-      sh_scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+      if (prune) {
+        PruneArgs pa;
+        pa.LB = rk.w.LB; pa.stride = rk.w.lb_stride; pa.Rsub = rk.w.Rsub; pa.uf = rk.w.uf; pa.gbest = rk.w.gbest;
+        pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;
+        grid = (nloc + SCAN_WARPS - 1) / SCAN_WARPS;
+        if (grid > sms * 3) grid = sms * 3;
+        if (grid > POOL) grid = POOL;
+        if (grid < 1) grid = 1;
+        sh_scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
+      } else {
+        sh_scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+      }
       CAS_LAUNCH_CHECK();
+      rk_grid[rk.r % SH_MAXG] = grid;
     }
     // --- C1: candidates
     if (!emu && !p2p) {
@@ -618,6 +809,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ca.ids = rk.w.ids; ca.sizes = NJ ? nullptr : rk.w.sizes; ca.sel = rk.w.sel;
       ca.joins = joins; ca.t = (int)t;
       ca.peers = peers; ca.tag = tag; ca.counter = rk.w.counters + 2;
+      ca.LB = prune ? rk.w.LB : nullptr; ca.lb_stride = rk.w.lb_stride; ca.Rsub = rk.w.Rsub; ca.gbest = rk.w.gbest;
       const int nloc = sh_count(k, rk.r, G);
       sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
       CAS_LAUNCH_CHECK();
@@ -637,6 +829,9 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.partial = rk.w.partial; ma.counter = rk.w.counters + 1; ma.rmax_bits = rk.w.rmax_bits;
       ma.new_id = (int)(n + t); ma.maintain_R = NJ ? 1 : 0;
       ma.peers = peers; ma.tag = tag;
+      ma.LB = prune ? rk.w.LB : nullptr; ma.lb_stride = rk.w.lb_stride; ma.Rsub = rk.w.Rsub; ma.uf = rk.w.uf;
+      ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
+      ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.gbest = rk.w.gbest; ma.pool = rk.w.pool;
       sh_merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
       CAS_LAUNCH_CHECK();
     }

@@ -1,0 +1,58 @@
+"""Pruned scan (default; lower bounds per row x 128-column sub-segment) == dense scan (CAS_PRUNE=0):
+identical join lists, remaining pair and near-tie diagnostics; and both == the CPU oracle's joins where the
+arithmetic is the reference's (UPGMA float64)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _map(n, m, S, dtype, rate, miss, weighted, seed):
+    from cassiopeia_b200 import engine
+    from cassiopeia_b200.synthetic import simulate_character_matrix
+
+    cm, priors, table = simulate_character_matrix(n, m, S, seed=seed, mutation_rate=rate, missing_fraction=miss)
+    cm = np.vstack([cm, np.zeros((1, m), dtype=cm.dtype)])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        w = np.nan_to_num(-np.log(table), nan=0.0, posinf=0.0)
+    return engine.whd_map(cm, -1, w if weighted else None, S, dtype=dtype, method="exact"), n + 1
+
+
+def _run(D, n, algo, mode, prune, monkeypatch):
+    from cassiopeia_b200 import engine
+
+    monkeypatch.setenv("CAS_PRUNE", "1" if prune else "0")
+    joins, last2 = engine.agglomerate(D.clone(), n, algo, mode)
+    return joins, last2, dict(engine.last_stats)
+
+
+@pytest.mark.parametrize("n,m,S,rate,miss", [(3, 5, 3, 0.5, 0.0), (130, 20, 5, 0.7, 0.1), (700, 40, 50, 0.1, 0.2),
+                                             (2500, 30, 10, 0.4, 0.3), (4200, 60, 100, 0.1, 0.2)])
+@pytest.mark.parametrize("algo,mode,dtype,weighted", [("nj", "fast", "f32", True), ("nj", "fast", "f64", True),
+                                                      ("upgma", "fast", "f32", True),
+                                                      ("upgma", "strict", "f64", False)])
+def test_pruned_equals_dense(n, m, S, rate, miss, algo, mode, dtype, weighted, monkeypatch):
+    D, nn = _map(n, m, S, dtype, rate, miss, weighted, seed=n)
+    jd, ld, sd = _run(D, nn, algo, mode, False, monkeypatch)
+    jp, lp, sp = _run(D, nn, algo, mode, True, monkeypatch)
+    assert np.array_equal(jd, jp) and np.array_equal(ld, lp)
+    assert (sd["near_ties"], sd["exact_ties"]) == (sp["near_ties"], sp["exact_ties"])
+    assert sd["scanned_elements"] == 0
+    dense = sum(k * (k - 1) // 2 for k in range(3, nn + 1))
+    assert 0 < sp["scanned_elements"] <= dense
+    if algo == "upgma" and mode == "strict" and nn <= 1000:
+        # float64 UPGMA has no reductions: the GPU loop is the reference's arithmetic
+        oj, ol = po.upgma(D[:, :nn].cpu().numpy())
+        assert np.array_equal(jp, oj)
+
+
+def test_pruned_scan_reads_less_at_size(monkeypatch):
+    """At 12k cells the pruned NJ scan reads a small fraction of the dense scan's elements."""
+    D, nn = _map(12000, 40, 50, "f32", 0.7, 0.1, True, seed=2)
+    jp, lp, sp = _run(D, nn, "nj", "fast", True, monkeypatch)
+    jd, ld, sd = _run(D, nn, "nj", "fast", False, monkeypatch)
+    assert np.array_equal(jd, jp) and np.array_equal(ld, lp)
+    dense = sum(k * (k - 1) // 2 for k in range(3, nn + 1))
+    assert sp["scanned_elements"] < 0.25 * dense
