@@ -57,11 +57,13 @@ struct RowScan {
   }
   // one 128-bit vector of row i starting at column j; columns >= jend are not part of the triangle.
   // Returns the minimum of the float32 (rounded-down) dissimilarities of the valid columns.
+  // GUARD = false: every column of the vector is known to be < jend (interior sub-segments).
+  template <bool GUARD = true>
   __device__ __forceinline__ float vec(const T (&v)[V], const float (&su)[V], int j, int jend) {
     float sv[V], qf[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      sv[e] = (j + e < jend) ? screen_value(v[e]) : INFINITY;
+      sv[e] = (!GUARD || j + e < jend) ? screen_value(v[e]) : INFINITY;
       qf[e] = NJ ? __fsub_rn(sv[e], su[e]) : sv[e];
     }
     float m = qf[0], dm = sv[0];
@@ -70,7 +72,7 @@ struct RowScan {
     if (m <= thr) {
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        if (qf[e] <= thr && j + e < jend) {
+        if (qf[e] <= thr && (!GUARD || j + e < jend)) {
           double q = (double)v[e];
           if (NJ) q = __dsub_rn(q, __dmul_rn(tinv, __dadd_rn(Ri, R[j + e])));
           if (q <= bq || bi < 0) {
@@ -104,15 +106,21 @@ __device__ __forceinline__ void prune_row(RowScan<T, NJ> &rs, PruneWarp &pw, con
   constexpr int LOADS = SW / (32 * V);  // 128-bit loads per lane and sub-segment (1 float, 2 double)
   constexpr int G = 8 / LOADS;          // sub-segments in flight: eight 128-bit loads per lane
   constexpr int CH = PRUNE_CH;          // chunks of 32 sub-segments decided together (32768 columns)
-  const int nsub = (i + SW - 1) / SW;   // sub-segments holding a column < i
+  const int nsub = (i + SW - 1) / SW;   // sub-segments holding a column < i; the last one ends at the diagonal
   double &gb_seen = pw.gb_seen;
-  unsigned long long &nread = pw.nread;
   bool scanned_any = false;
   for (int sb = 0; sb < nsub; sb += CH * 32) {
-    // ---- decide: lane l looks at sub-segments sb + 32 c + l, c < CH (coalesced 128-byte loads)
+    // ---- decide: lane l looks at sub-segments sb + 32 c + l, c < CH (coalesced 128-byte loads).
+    // Float arithmetic; every rounding is covered by the relative slack, which only makes the test
+    // scan a little more:  skip  <=>  lb - us > (gbest + window) + u_i + slack.
     const double gb = dec_f64(__ldcg(p.gbest));
     gb_seen = gb;
     rs.set_cap(gb);
+    const float gbw = __double2float_ru(gb + RowScan<T, NJ>::window(gb));
+    const float uif = NJ ? __double2float_ru(rs.ui) : 0.f;
+    const float tinvf = (float)tinv_;
+    const float base = gbw + uif;
+    const float mag0 = fabsf(gbw) + fabsf(uif);
     unsigned lbv[CH], rsv[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -124,53 +132,52 @@ __device__ __forceinline__ void prune_row(RowScan<T, NJ> &rs, PruneWarp &pw, con
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       if (sb + c * 32 >= nsub) break;  // warp-uniform: no sub-segment of this chunk exists
-      const double lb = (double)dec_f32(lbv[c]);
-      double bound = lb, mag = fabs(lb) + fabs(gb);
-      if (NJ) {
-        const double us = tinv_ * (double)dec_f32(rsv[c]);
-        bound = lb - (rs.ui + us);
-        mag += fabs(rs.ui) + fabs(us);
-      }
-      // near-tie window + rounding slack of the bound
-      const double window = RowScan<T, NJ>::window(gb) + 1e-9 * mag;
-      const bool nd = (sb + c * 32 + lane < nsub) && !(bound > gb + window);  // true while gb = +inf / lb = -inf
+      const float lb = dec_f32(lbv[c]);
+      const float us = NJ ? tinvf * dec_f32(rsv[c]) : 0.f;
+      const float mag = mag0 + fabsf(lb) + fabsf(us);
+      // false while gbest = +inf or lb = -inf (unknown): then the sub-segment is read
+      const bool skip = (lb - us) > base + 1e-6f * mag;
+      const bool nd = (sb + c * 32 + lane < nsub) && !skip;
       flags |= (nd ? 1u : 0u) << c;
     }
-    // ---- compact the needed sub-segments into the warp's list
-    const int cnt = __popc(flags);
-    int pre = cnt;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, pre, off);
-      if (lane >= off) pre += o;
-    }
-    const int total = __shfl_sync(0xffffffffu, pre, 31);
-    if (total == 0) continue;
+    // the diagonal sub-segment needs per-column guards: it is handled apart from the interior ones
+    bool diag_needed = false;
     {
+      const int dsub = nsub - 1 - sb;  // position of the diagonal sub-segment in this round, if any
+      if (dsub >= 0 && dsub < CH * 32) {
+        const unsigned bit = (lane == (dsub & 31)) ? (1u << (dsub >> 5)) : 0u;
+        diag_needed = __any_sync(0xffffffffu, (flags & bit) != 0u);
+        flags &= ~bit;
+      }
+    }
+    // ---- compact the needed interior sub-segments into the warp's list
+    const int cnt = __popc(flags);
+    int total = 0;
+    if (__any_sync(0xffffffffu, cnt != 0)) {
+      int pre = cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, pre, off);
+        if (lane >= off) pre += o;
+      }
+      total = __shfl_sync(0xffffffffu, pre, 31);
       int wpos = pre - cnt;
 #pragma unroll
       for (int c = 0; c < CH; ++c)
         if ((flags >> c) & 1u) list[wpos++] = (unsigned short)(c * 32 + lane);
+      __syncwarp();
     }
-    __syncwarp();
-    // ---- read them, G at a time
-    for (int base = 0; base < total; base += G) {
+    if (total == 0 && !diag_needed) continue;
+    // ---- read them, G at a time (all columns valid: no guards)
+    for (int base_i = 0; base_i < total; base_i += G) {
       int sg[G];
       T v[G][LOADS][V];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        sg[g] = (base + g < total) ? sb + (int)list[base + g] : -1;
+        sg[g] = (base_i + g < total) ? sb + (int)list[base_i + g] : -1;
         if (sg[g] >= 0) {
 #pragma unroll
-          for (int l = 0; l < LOADS; ++l) {
-            const int j = sg[g] * SW + l * 32 * V + lane * V;
-            if (j < i) {
-              ld_stream<false>(row + j, v[g][l]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < V; ++e) v[g][l][e] = (T)INFINITY;
-            }
-          }
+          for (int l = 0; l < LOADS; ++l) ld_stream<false>(row + sg[g] * SW + l * 32 * V + lane * V, v[g][l]);
         }
       }
 #pragma unroll
@@ -183,16 +190,39 @@ __device__ __forceinline__ void prune_row(RowScan<T, NJ> &rs, PruneWarp &pw, con
           float su[V];
 #pragma unroll
           for (int e = 0; e < V; ++e) su[e] = 0.f;
-          if (NJ && j < i) {
+          if (NJ) {
             if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
             else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
           }
-          dm = fminf(dm, rs.vec(v[g][l], su, j, i));
+          dm = fminf(dm, rs.template vec<false>(v[g][l], su, j, i));
         }
         const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32(dm));
         if (lane == 0) lbrow[sg[g]] = m;
-        nread += (unsigned long long)(min(i, (sg[g] + 1) * SW) - sg[g] * SW);
       }
+    }
+    pw.nread += (unsigned long long)total * SW;
+    if (diag_needed) {
+      const int sgd = nsub - 1;
+      float dm = INFINITY;
+#pragma unroll
+      for (int l = 0; l < LOADS; ++l) {
+        const int j = sgd * SW + l * 32 * V + lane * V;
+        T v[V];
+        float su[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) { v[e] = (T)INFINITY; su[e] = 0.f; }
+        if (j < i) {
+          ld_stream<false>(row + j, v);
+          if (NJ) {
+            if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
+            else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
+          }
+        }
+        dm = fminf(dm, rs.template vec<true>(v, su, j, i));
+      }
+      const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32(dm));
+      if (lane == 0) lbrow[sgd] = m;
+      pw.nread += (unsigned long long)(i - sgd * SW);
     }
     scanned_any = true;
     __syncwarp();  // the list is rewritten by the next round

@@ -31,6 +31,8 @@
 
 namespace cas {
 
+bool prune_enabled(bool nj);  // agglom.cu
+
 constexpr int SHB = 64;  // rows per ownership block
 
 __host__ __device__ __forceinline__ int sh_owner(int slot, int G) { return (slot / SHB) % G; }
@@ -718,8 +720,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
   const unsigned long long tag0 = epoch << 32;
   Cand *cand_all = ranks[0].w.cand_all;
   char *gath = ranks[0].w.gath;
-  const char *pe = getenv("CAS_PRUNE");
-  const bool prune = !(pe && pe[0] == '0') && n > 2;  // exact pruned scan (agglom_pruned.cuh); CAS_PRUNE=0: dense
+  const bool prune = prune_enabled(NJ) && n > 2;  // exact pruned scan (agglom_pruned.cuh; policy in agglom.cu)
   for (auto &rk : ranks) {
     sh_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)n, rk.w.ids, rk.w.sizes,
                                                                     rk.w.counters, rk.w.rmax_bits);
