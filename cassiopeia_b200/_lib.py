@@ -38,6 +38,7 @@ EXPORTS = (
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
     "cas_sharded_workspace_bytes",
+    "cas_sharded_scanned_elements",
     "cas_whd_map_cyclic",
     "cas_nccl_unique_id",
     "cas_nccl_comm_create",
@@ -92,6 +93,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_nj_q.argtypes = [vp, i64, i64, vp, vp, vp]
     L.cas_update_map.restype = ctypes.c_int
     L.cas_update_map.argtypes = [vp, i64, i64, i32, i64, i64, i64, i64, vp, i64, vp]
+    L.cas_sharded_scanned_elements.restype = ctypes.c_int
+    L.cas_sharded_scanned_elements.argtypes = [vp, i64, i32, i32, vp, ctypes.POINTER(i64)]
     L.cas_sharded_local_rows.restype = i64
     L.cas_sharded_local_rows.argtypes = [i64, i32, i32]
     L.cas_sharded_local_capacity.restype = i64

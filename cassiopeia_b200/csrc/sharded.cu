@@ -873,6 +873,18 @@ int64_t cas_sharded_local_capacity(int64_t n, int32_t world) {
   return sh_chunk((int)n, world);
 }
 
+int cas_sharded_scanned_elements(const void *workspace, int64_t n, int32_t world, int32_t dtype, void *stream,
+                                 int64_t *elements) {
+  CAS_REQUIRE(workspace && elements, "null pointer argument");
+  ShWorkspace w = sh_carve(const_cast<void *>(workspace), n > 0 ? n : 1, world > 0 ? world : 1,
+                           dtype == CAS_F64 ? 8 : 4);
+  unsigned long long h = 0;
+  CAS_CUDA_TRY(cudaMemcpyAsync(&h, w.scanned, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  *elements = (int64_t)h;
+  return CAS_OK;
+}
+
 size_t cas_sharded_workspace_bytes(int64_t n, int32_t world, int32_t dtype) {
   return sh_carve(nullptr, n > 0 ? n : 1, world > 0 ? world : 1, dtype == CAS_F64 ? 8 : 4).bytes;
 }

@@ -205,6 +205,20 @@ class PeerGroup:
         self.ptrs = []
 
 
+#: map elements this rank's pruned scans read during its most recent sharded solve (0: dense scan)
+last_scanned_elements = 0
+
+
+def _record_scanned(L, torch, ws, n, world, code):
+    import ctypes
+
+    global last_scanned_elements
+    out = ctypes.c_int64(0)
+    _lib.check(L.cas_sharded_scanned_elements(ws.data_ptr(), int(n), int(world), code, engine._stream_ptr(torch),
+                                              ctypes.byref(out)), "cas_sharded_scanned_elements")
+    last_scanned_elements = int(out.value)
+
+
 def sharded_solve_p2p(shard, n: int, algo: str, group: PeerGroup, max_iters: int = -1):
     """P2P variant of ``sharded_solve``: NVLink stores + flags from inside the kernels, no NCCL."""
     torch = engine._torch()
@@ -223,6 +237,7 @@ def sharded_solve_p2p(shard, n: int, algo: str, group: PeerGroup, max_iters: int
                                  joins.data_ptr(), last2.data_ptr(), ws.data_ptr(), ws_bytes,
                                  engine._stream_ptr(torch))
     _lib.check(rc, "cas_sharded_solve_p2p")
+    _record_scanned(L, torch, ws, n, group.world, code)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     out = joins[:done].cpu().numpy(), last2.cpu().numpy()
     group.check()
@@ -245,6 +260,7 @@ def sharded_solve(shard, n: int, algo: str, group: NcclGroup, max_iters: int = -
                              int(max_iters), group.rank, group.world, group.handle, joins.data_ptr(),
                              last2.data_ptr(), ws.data_ptr(), ws_bytes, engine._stream_ptr(torch))
     _lib.check(rc, "cas_sharded_solve")
+    _record_scanned(L, torch, ws, n, group.world, code)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     return joins[:done].cpu().numpy(), last2.cpu().numpy()
 

@@ -146,6 +146,10 @@ CAS_API int cas_upgma_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, i
  * collective (shared gather buffers) -- the same kernels, used to test the sharded path. */
 CAS_API int64_t cas_sharded_local_rows(int64_t n, int32_t rank, int32_t world);
 CAS_API int64_t cas_sharded_local_capacity(int64_t n, int32_t world);
+/* map elements this rank's pruned scans read during the last sharded solve with this workspace
+ * (0 for the dense scan); synchronises the stream */
+CAS_API int cas_sharded_scanned_elements(const void *workspace_dev, int64_t n, int32_t world, int32_t dtype,
+                                 void *stream, int64_t *elements);
 CAS_API size_t cas_sharded_workspace_bytes(int64_t n, int32_t world, int32_t dtype);
 CAS_API int cas_whd_map_cyclic(const int32_t *cm_dev, int64_t n, int32_t m, int32_t missing,
                        const double *w_dev, int32_t n_states, void *D_local_dev, int64_t ld,

@@ -53,12 +53,16 @@ hmax, hmin = h.clone(), h.clone()
 dist.all_reduce(hmax, op=dist.ReduceOp.MAX); dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
 flags = torch.tensor([int(ok_map), int(ok_tree)], device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+scanned = torch.tensor([sharded.last_scanned_elements], dtype=torch.int64, device="cuda")
+dist.all_reduce(scanned, op=dist.ReduceOp.SUM)
 if rank == 0:
     peak = bench.peaks()[0]
     b_alg = bench.scan_bytes(n, 4)
     out = {"config": f"NJ {a.cells} cells x {a.chars} chars x {a.states} states, priors, 10% missing, implicit root; "
                      f"row-sharded over {world} B200 (P2P exchange)",
            "map_seconds": t1 - t0, "loop_seconds": t3 - t2, "solve_seconds": (t1 - t0) + (t3 - t2),
+           "scan": "pruned (exact lower bounds)" if int(scanned.item()) else "dense",
+           "elements_read_fraction_of_dense": int(scanned.item()) * 4 / b_alg,
            "loop_algorithmic_GBps": b_alg / (t3 - t2) / 1e9, "roofline_frac_of_measured_hbm": b_alg / (t3 - t2) / 1e9 / (peak * world),
            "sampled_map_rows_bit_exact_vs_cpu_oracle": bool(flags[0].item()), "join_list_is_a_valid_tree": bool(flags[1].item()),
            "ranks_agree_on_join_list": bool(torch.equal(hmax, hmin)), "first_joins": joins[:3].tolist()}
