@@ -7,7 +7,8 @@ CUDA kernels behind the C ABI of ``include/cas_b200.h``.
 """
 from . import data, mixins, solver
 from .data import CassiopeiaTree
-from .solver import NeighborJoiningSolver, UPGMASolver
+from .solver import NeighborJoiningSolver, SharedMutationJoiningSolver, UPGMASolver
 
 __version__ = "0.1.0"
-__all__ = ["data", "mixins", "solver", "CassiopeiaTree", "NeighborJoiningSolver", "UPGMASolver"]
+__all__ = ["data", "mixins", "solver", "CassiopeiaTree", "NeighborJoiningSolver", "UPGMASolver",
+           "SharedMutationJoiningSolver"]

@@ -26,6 +26,8 @@ EXPORTS = (
     "cas_whd_workspace_bytes",
     "cas_whd_map",
     "cas_pairwise_map",
+    "cas_smj_workspace_bytes",
+    "cas_smj_solve",
     "cas_agglom_workspace_bytes",
     "cas_nj_solve",
     "cas_upgma_solve",
@@ -80,6 +82,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_whd_map.argtypes = [vp, i64, i32, i32, vp, i32, vp, i64, i32, i64, i64, i32, vp, sz, vp]
     L.cas_pairwise_map.restype = ctypes.c_int
     L.cas_pairwise_map.argtypes = [i32, i32, vp, i64, i32, i32, vp, i32, vp, i64, i32, i64, i64, vp, sz, vp]
+    L.cas_smj_workspace_bytes.restype = sz
+    L.cas_smj_workspace_bytes.argtypes = [i64, i32]
+    L.cas_smj_solve.restype = ctypes.c_int
+    L.cas_smj_solve.argtypes = [vp, i64, i32, i32, vp, i32, i32, vp, i64, i64, vp, vp, vp, sz, vp]
     L.cas_agglom_workspace_bytes.restype = sz
     L.cas_agglom_workspace_bytes.argtypes = [i64, i32, i32]
     for fn in (L.cas_nj_solve, L.cas_upgma_solve):

@@ -750,6 +750,187 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
   return CAS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-Mutation-Joining loop.
+//
+// Restates cassiopeia/solver/SharedMutationJoiningSolver.py:176-205 (`while N > 1`): find_cherry (:211-228)
+// = first row-major arg-MAX of the similarity map = lexicographic minimum of (-s, id_lo, id_hi), so the
+// map is stored negated and the UPGMA instance of the scan kernel picks the pair;
+// update_similarity_map_and_character_matrix (:230-303) gives the new node the Camin-Sokal LCA of the two
+// joined character rows (data/utilities.py:29-97) and recomputes its similarity to every live sample with
+// the pair function (:338-343) -- float64 in character order, like the map kernel, so the loop is
+// bit-identical to the reference.  Slots, swap compaction and ids as in the NJ / UPGMA loops; the
+// character rows live transposed ([m][cap]) so that thread v reads a coalesced column.
+struct SmjArgs {
+  double *D;
+  int64_t ld;
+  int k;
+  const Sel *sel;
+  int32_t *ids;
+  int new_id;
+  int32_t *chars;   // [m][cap] compact state codes by slot
+  int64_t cap;
+  int m;
+  int32_t missing;
+  const double *w;  // [m][S+1] or null
+  int S;
+  int fn;           // CAS_FN_*
+  int32_t *lca;     // [m] scratch: character row of the new node
+};
+
+__global__ void smj_transpose_kernel(const int32_t *__restrict__ cm, int64_t n, int m, int32_t *__restrict__ chars,
+                                     int64_t cap) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * m) return;
+  const int64_t r = idx / m;
+  const int c = (int)(idx - r * m);
+  chars[(int64_t)c * cap + r] = cm[idx];
+}
+
+__global__ void smj_negate_kernel(double *D, int64_t count) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    D[e] = -D[e];
+}
+
+// LCA row of the joined pair: all missing -> missing; one missing -> the other; equal -> that; else 0
+__global__ void smj_lca_kernel(SmjArgs a) {
+  const Sel s = *a.sel;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.m; c += gridDim.x * blockDim.x) {
+    const int32_t x = a.chars[(int64_t)c * a.cap + s.lo], y = a.chars[(int64_t)c * a.cap + s.hi];
+    a.lca[c] = (x == a.missing) ? y : (y == a.missing) ? x : (x == y ? x : 0);
+  }
+}
+
+// one pair value: f(row of slot v, lca), cassiopeia/solver/dissimilarity_functions.py (see whd_exact.cu)
+__device__ __forceinline__ double smj_pair(const SmjArgs &a, int v) {
+  double d = 0.0;
+  int num_present = 0;
+  const int W = a.S + 1;
+  for (int c = 0; c < a.m; ++c) {
+    const int32_t x = a.chars[(int64_t)c * a.cap + v], y = a.lca[c];
+    if (x == a.missing || y == a.missing) continue;
+    num_present += 1;
+    if (a.fn == CAS_FN_WEIGHTED_HAMMING_DISTANCE || a.fn == CAS_FN_EXPONENTIAL_NEGATIVE_HAMMING_DISTANCE) {
+      if (x != y) {
+        if (a.w) {
+          const double wx = x != 0 ? a.w[(int64_t)c * W + x] : 0.0, wy = y != 0 ? a.w[(int64_t)c * W + y] : 0.0;
+          d = __dadd_rn(d, __dadd_rn(wx, wy));
+        } else {
+          d += (x != 0 ? 1.0 : 0.0) + (y != 0 ? 1.0 : 0.0);
+        }
+      }
+    } else if (a.fn == CAS_FN_WEIGHTED_HAMMING_SIMILARITY) {
+      if (x == y) {
+        if (x != 0) d = __dadd_rn(d, a.w ? __dmul_rn(2.0, a.w[(int64_t)c * W + x]) : 2.0);
+        else if (!a.w) d += 1.0;
+      }
+    } else {  // the two hamming similarities
+      if (x != 0 && y != 0 && x == y) d = __dadd_rn(d, a.w ? a.w[(int64_t)c * W + x] : 1.0);
+    }
+  }
+  if (a.fn == CAS_FN_HAMMING_SIMILARITY_WITHOUT_MISSING) return d;
+  if (num_present == 0) return 0.0;
+  d = __ddiv_rn(d, (double)num_present);
+  if (a.fn == CAS_FN_EXPONENTIAL_NEGATIVE_HAMMING_DISTANCE) d = exp(-d);
+  return d;
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS) smj_update_kernel(SmjArgs a) {
+  const Sel s = *a.sel;
+  const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1;
+  const int64_t ld = a.ld;
+  double *__restrict__ D = a.D;
+  const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
+  if (v >= k) return;
+  if (v == lo) {
+    D[(int64_t)lo * ld + lo] = 0.0;
+    a.ids[lo] = a.new_id;
+    // only this thread reads or writes column lo of the character rows in this launch
+    for (int c = 0; c < a.m; ++c) a.chars[(int64_t)c * a.cap + lo] = a.lca[c];
+  } else if (v == hi) {
+    D[(int64_t)hi * ld + hi] = 0.0;
+    if (hi != last)
+      for (int c = 0; c < a.m; ++c) a.chars[(int64_t)c * a.cap + hi] = a.chars[(int64_t)c * a.cap + last];
+  } else {
+    const double nv = -smj_pair(a, v);  // the map holds negated similarities
+    if (hi != last && v != last) {
+      const double l = D[(int64_t)last * ld + v];
+      D[(int64_t)hi * ld + v] = l;
+      D[(int64_t)v * ld + hi] = l;
+    }
+    D[(int64_t)lo * ld + v] = nv;
+    D[(int64_t)v * ld + lo] = nv;
+    if (v == last && hi != last) {
+      D[(int64_t)hi * ld + lo] = nv;
+      D[(int64_t)lo * ld + hi] = nv;
+      D[(int64_t)hi * ld + hi] = 0.0;
+      a.ids[hi] = a.ids[last];
+    }
+  }
+}
+
+size_t smj_workspace_bytes(int64_t n, int32_t m) {
+  Carver c(nullptr);
+  c.take<char>(agglom_workspace_bytes(n));
+  c.take<int32_t>((size_t)m * (size_t)(n > 0 ? n : 1));
+  c.take<int32_t>((size_t)m + 32);
+  return c.used();
+}
+
+// D: [n, ld] float64, holds the similarity map on entry (any pair function), destroyed.
+int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w, int32_t n_states,
+              int32_t fn, double *D, int64_t ld, int64_t max_iters, int32_t *joins, int32_t *last2,
+              void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  CAS_REQUIRE(workspace_bytes >= smj_workspace_bytes(n, m), "workspace too small for the SMJ loop");
+  CAS_REQUIRE(fn >= 0 && fn <= 5 && fn != CAS_FN_HAMMING_DISTANCE, "pair function %d cannot drive the SMJ loop", fn);
+  Carver carve(workspace);
+  void *aws = carve.take<char>(agglom_workspace_bytes(n));
+  int32_t *chars = carve.take<int32_t>((size_t)m * (size_t)n);
+  int32_t *lca = carve.take<int32_t>((size_t)m + 32);
+  AgglomWorkspace wk = carve_workspace(aws, n);
+  const int sms = sm_count();
+  const int target_ctas = sms * 4;
+  {
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    init_state_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>((int)n, wk.ids, nullptr, nullptr, nullptr, wk.counters,
+                                                               wk.rmax_bits);
+    CAS_LAUNCH_CHECK();
+    const int64_t nm = n * (int64_t)m;
+    smj_transpose_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, stream>>>(cm, n, m, chars, n);
+    CAS_LAUNCH_CHECK();
+    smj_negate_kernel<<<sms * 8, 256, 0, stream>>>(D, n * ld);
+    CAS_LAUNCH_CHECK();
+    CAS_CUDA_TRY(cudaMemsetAsync(wk.scanned, 0, sizeof(unsigned long long), stream));
+  }
+  int64_t k_final = n;
+  for (int64_t t = 0; t + 2 < n; ++t) {
+    if (max_iters >= 0 && t >= max_iters) break;
+    const int k = (int)(n - t);
+    k_final = k - 1;
+    ScanArgs sa;
+    sa.D = D; sa.ld = ld; sa.k = k;
+    plan_scan(k, target_ctas, sa.tr, sa.nrb, sa.ncb, sa.ntiles);
+    sa.R = wk.R; sa.ids = wk.ids; sa.sizes = nullptr; sa.tinv = 0.0; sa.rmax_bits = wk.rmax_bits;
+    sa.stats = wk.stats; sa.cand = wk.cand; sa.counter = wk.counters + 0; sa.sel = wk.sel; sa.joins = joins;
+    sa.t = (int)t;
+    int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
+    if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
+    if (grid < 1) grid = 1;
+    scan_kernel<double, false><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+    CAS_LAUNCH_CHECK();
+    SmjArgs ua;
+    ua.D = D; ua.ld = ld; ua.k = k; ua.sel = wk.sel; ua.ids = wk.ids; ua.new_id = (int)(n + t);
+    ua.chars = chars; ua.cap = n; ua.m = m; ua.missing = missing; ua.w = w; ua.S = n_states; ua.fn = fn; ua.lca = lca;
+    smj_lca_kernel<<<(unsigned)((m + 127) / 128), 128, 0, stream>>>(ua);
+    CAS_LAUNCH_CHECK();
+    smj_update_kernel<<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ua);
+    CAS_LAUNCH_CHECK();
+  }
+  last2_kernel<<<1, 32, 0, stream>>>(wk.ids, (int)(k_final < 2 ? k_final : 2), last2, nullptr);
+  CAS_LAUNCH_CHECK();
+  return CAS_OK;
+}
+
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
                  size_t workspace_bytes, cudaStream_t stream) {

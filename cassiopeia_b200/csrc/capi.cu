@@ -50,6 +50,10 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t agglom_workspace_bytes(int64_t n);
 int agglom_read_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *near_ties, int64_t *exact_ties);
+size_t smj_workspace_bytes(int64_t n, int32_t m);
+int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w, int32_t n_states,
+              int32_t fn, double *D, int64_t ld, int64_t max_iters, int32_t *joins, int32_t *last2,
+              void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements);
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
@@ -143,6 +147,20 @@ size_t cas_agglom_workspace_bytes(int64_t n, int32_t algo, int32_t mode) {
 int cas_agglom_stats(const void *workspace, int64_t n, void *stream, int64_t *near_ties, int64_t *exact_ties) {
   CAS_REQUIRE(workspace, "null pointer argument");
   return agglom_read_stats(workspace, n, (cudaStream_t)stream, near_ties, exact_ties);
+}
+
+size_t cas_smj_workspace_bytes(int64_t n, int32_t m) { return smj_workspace_bytes(n, m); }
+
+int cas_smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w, int32_t n_states,
+                  int32_t fn, double *S_map, int64_t ld, int64_t max_iters, int32_t *joins, int32_t *last2,
+                  void *workspace, size_t workspace_bytes, void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(cm && S_map && joins && last2 && workspace, "null pointer argument");
+  CAS_REQUIRE(n >= 1 && m >= 1 && n < (int64_t)1 << 30, "bad sizes (n=%lld, m=%d)", (long long)n, m);
+  CAS_REQUIRE(ld >= n && ld % 32 == 0, "ld=%lld must be >= n and a multiple of 32", (long long)ld);
+  CAS_REQUIRE(((uintptr_t)S_map & 15) == 0, "the map must be 16-byte aligned");
+  return smj_solve(cm, n, m, missing, w, n_states, fn, S_map, ld, max_iters, joins, last2, workspace,
+                   workspace_bytes, (cudaStream_t)stream);
 }
 
 int cas_agglom_scanned_elements(const void *workspace, int64_t n, void *stream, int64_t *elements) {

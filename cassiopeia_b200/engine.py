@@ -164,6 +164,38 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     return joins_h, last2_h
 
 
+def smj_solve(cm, missing: int, weights: Optional[np.ndarray], n_states: int,
+              function: str = "hamming_similarity_without_missing", max_iters: int = -1):
+    """Shared-Mutation-Joining loop (``cas_smj_solve``) on the int32 [n, m] matrix of compact codes `cm`, rows
+    as given: the float64 similarity map is built with ``cas_pairwise_map`` and consumed on the device.
+
+    Returns (joins [n-2, 2] int32 numpy in id space, last2 [2]); the reference's last join (its root) is
+    the pair `last2`."""
+    torch = _torch()
+    L = _lib.load()
+    if function == "hamming_distance":
+        raise ValueError("hamming_distance has no (s1, s2, missing, weights) signature and cannot drive the loop")
+    cm_t = (torch.from_numpy(np.ascontiguousarray(cm, dtype=np.int32)).cuda() if isinstance(cm, np.ndarray)
+            else cm.to(device="cuda", dtype=torch.int32).contiguous())
+    n, m = int(cm_t.shape[0]), int(cm_t.shape[1])
+    S_map = whd_map(cm_t, missing, weights, n_states, dtype="f64", method="exact", function=function)
+    w_t = None
+    if weights is not None:
+        w_t = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).cuda()
+    njoin = max(n - 2, 0)
+    joins = torch.full((njoin + 1, 2), -1, dtype=torch.int32, device="cuda")
+    last2 = torch.full((2,), -1, dtype=torch.int32, device="cuda")
+    ws_bytes = int(L.cas_smj_workspace_bytes(n, m))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    rc = L.cas_smj_solve(cm_t.data_ptr(), n, m, int(missing), w_t.data_ptr() if w_t is not None else None,
+                         int(n_states), PAIR_FUNCTIONS[function], S_map.data_ptr(), int(S_map.stride(0)),
+                         int(max_iters), joins.data_ptr(), last2.data_ptr(), ws.data_ptr(), ws_bytes,
+                         _stream_ptr(torch))
+    _lib.check(rc, "cas_smj_solve")
+    done = njoin if max_iters < 0 else min(njoin, int(max_iters))
+    return joins[:done].cpu().numpy(), last2.cpu().numpy()
+
+
 def solve_host(cm: np.ndarray, missing: int, weights: Optional[np.ndarray], n_states: int,
                algo: str, mode: str, method: str = "exact"):
     """End to end from HOST buffers through ``cas_solve_host`` (H2D/D2H inside the call).

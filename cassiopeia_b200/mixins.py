@@ -8,8 +8,8 @@ from __future__ import annotations
 
 try:  # pragma: no cover - depends on the environment
     from cassiopeia.mixins.errors import (CassiopeiaError, CassiopeiaTreeError, DistanceSolverError,
-                                          PriorTransformationError)
-    from cassiopeia.mixins.warnings import CassiopeiaTreeWarning
+                                          PriorTransformationError, SharedMutationJoiningSolverError)
+    from cassiopeia.mixins.warnings import CassiopeiaTreeWarning, SharedMutationJoiningSolverWarning
 except Exception:  # reference package absent (e.g. on the GPU box)
 
     class CassiopeiaError(Exception):
@@ -24,8 +24,14 @@ except Exception:  # reference package absent (e.g. on the GPU box)
     class PriorTransformationError(CassiopeiaError):
         """Invalid prior transformation or prior value."""
 
+    class SharedMutationJoiningSolverError(CassiopeiaError):
+        """Errors of the SharedMutationJoiningSolver (cassiopeia/mixins/errors.py:77)."""
+
     class CassiopeiaTreeWarning(UserWarning):
         """Warnings of the tree container."""
+
+    class SharedMutationJoiningSolverWarning(UserWarning):
+        """Warnings of the SharedMutationJoiningSolver (cassiopeia/mixins/warnings.py:14)."""
 
 
 def is_ambiguous_state(state) -> bool:

@@ -136,6 +136,22 @@ CAS_API int cas_nj_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int3
 CAS_API int cas_upgma_solve(void *D_dev, int64_t n, int64_t ld, int32_t dtype, int32_t mode,
                     int64_t max_iters, int32_t *joins_dev, int32_t *last2_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);
+/* ---- Shared-Mutation-Joining loop ------------------------------------------------------------
+ * Replaces the `while N > 1` loop of cassiopeia/solver/SharedMutationJoiningSolver.py:176-205:
+ * find_cherry (:211-228, first row-major arg-max of the similarity map) and
+ * update_similarity_map_and_character_matrix (:230-343: the new node gets the Camin-Sokal LCA of the two
+ * joined character rows, its similarities are recomputed with the pair function `fn`).
+ * cm_dev   : [n, m] int32 compact state codes (as for cas_whd_map), rows in map order
+ * S_dev    : [n, ld] float64 similarity map of those rows (e.g. from cas_pairwise_map with the same fn),
+ *            destroyed
+ * joins_dev: [max(n-2,0), 2] ids as for cas_nj_solve; last2_dev: the two clusters left, which the
+ *            reference joins last (its root).  Bit-identical to the reference's float64 arithmetic. */
+CAS_API size_t cas_smj_workspace_bytes(int64_t n, int32_t m);
+CAS_API int cas_smj_solve(const int32_t *cm_dev, int64_t n, int32_t m, int32_t missing, const double *w_dev,
+                  int32_t n_states, int32_t fn, double *S_dev, int64_t ld, int64_t max_iters,
+                  int32_t *joins_dev, int32_t *last2_dev, void *workspace_dev, size_t workspace_bytes,
+                  void *stream);
+
 /* ---- row-sharded loop (n^2 map larger than one GPU; no reference counterpart) ----------
  * Slots are dealt to ranks in 64-row blocks, block-cyclically; a rank stores its rows in local
  * order, [cas_sharded_local_capacity(n, world), ld].  cas_whd_map_cyclic fills such a shard

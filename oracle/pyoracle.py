@@ -41,6 +41,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_pairwise_map_rows.restype = None
         L.oracle_pairwise_map_rows.argtypes = [ctypes.c_int, ctypes.c_int, vp, i64, ctypes.c_int, i64, vp,
                                                ctypes.c_int, i64, i64, vp, ctypes.c_int]
+        L.oracle_smj.restype = ctypes.c_int
+        L.oracle_smj.argtypes = [ctypes.c_int, vp, i64, ctypes.c_int, i64, vp, ctypes.c_int, vp, vp]
         L.oracle_nj.restype = ctypes.c_int
         L.oracle_nj.argtypes = [vp, i64, vp, vp, i64, ctypes.c_int]
         L.oracle_upgma.restype = ctypes.c_int
@@ -208,3 +210,20 @@ def nj(D: np.ndarray, max_iters: int = -1, threads: int = 0):
 
 def upgma(D: np.ndarray, max_iters: int = -1, threads: int = 0):
     return _loop(lib().oracle_upgma, D, max_iters, threads)
+
+
+def smj(fn: str, cm: np.ndarray, missing: int = -1, table: Optional[np.ndarray] = None):
+    """Join list (ids, n-1 joins: the last one is the root) of the reference's SharedMutationJoiningSolver loop
+    with the similarity function `fn` on the rows of `cm` as given (the solver does not de-duplicate)."""
+    cm = np.ascontiguousarray(cm, dtype=np.int64)
+    n, m = cm.shape
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.float64)
+    S = pairwise_map(fn, cm, missing, table)
+    joins = np.full((max(n - 1, 0), 2), -1, dtype=np.int32)
+    rc = lib().oracle_smj(PAIR_FUNCTIONS[fn], cm.ctypes.data, n, m, int(missing),
+                          table.ctypes.data if table is not None else None,
+                          int(table.shape[1]) if table is not None else 0, S.ctypes.data, joins.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle smj failed rc={rc}")
+    return joins

@@ -93,6 +93,8 @@ def load_reference():
     ds = importlib.import_module("cassiopeia.solver.DistanceSolver")
     nj = importlib.import_module("cassiopeia.solver.NeighborJoiningSolver")
     up = importlib.import_module("cassiopeia.solver.UPGMASolver")
+    cs = importlib.import_module("cassiopeia.solver.CassiopeiaSolver")
+    solver.CassiopeiaSolver = cs
     dfn = importlib.import_module("cassiopeia.solver.dissimilarity_functions")
     sut = importlib.import_module("cassiopeia.solver.solver_utilities")
     solver.dissimilarity_functions = dfn
@@ -101,6 +103,8 @@ def load_reference():
     solver.NeighborJoiningSolver = nj.NeighborJoiningSolver
     solver.UPGMASolver = up.UPGMASolver
     solver.DistanceSolver = ds.DistanceSolver
+    smj = importlib.import_module("cassiopeia.solver.SharedMutationJoiningSolver")
+    solver.SharedMutationJoiningSolver = smj.SharedMutationJoiningSolver
 
     sim = sys.modules["cassiopeia.simulator"]
     cbs = importlib.import_module("cassiopeia.simulator.CompleteBinarySimulator")
@@ -115,6 +119,7 @@ def load_reference():
         DistanceSolver=ds.DistanceSolver,
         NeighborJoiningSolver=nj.NeighborJoiningSolver,
         UPGMASolver=up.UPGMASolver,
+        SharedMutationJoiningSolver=smj.SharedMutationJoiningSolver,
         dissimilarity_functions=dfn,
         solver_utilities=sut,
         CompleteBinarySimulator=cbs.CompleteBinarySimulator,
@@ -153,6 +158,16 @@ class _JoinRecorder:
         ids.append(self._rec_next)
         self._rec_next += 1
         return i, j
+
+
+def recording_smj_solver():
+    """Reference SharedMutationJoiningSolver subclass that exposes ``recorded_joins`` (n-1 joins)."""
+    ref = load_reference()
+
+    class RecSMJ(_JoinRecorder, ref.SharedMutationJoiningSolver):
+        pass
+
+    return RecSMJ
 
 
 def recording_solvers():
