@@ -135,15 +135,12 @@ template <> __device__ __forceinline__ double round_to<double>(double v) { retur
 // Scans columns [c0, jend) of one matrix row (slot i) with one warp: float32 screen against the
 // staged u_j block `sU`, exact float64 re-evaluation of the survivors.  (bq, bi, bj) is the
 // lane's running best (value, row slot, column slot).
-//
-// TRACK: additionally returns in `dmin` the lane's minimum of the float32 (rounded-down) dissimilarities
-// it read -- the pruned scan stores the segment minimum as the next iterations' lower bound.
-template <typename T, bool NJ, bool COH = false, bool TRACK = false>
+template <typename T, bool NJ, bool COH = false>
 __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, int jend,
                                                  int lane, const float *sU, const double *R,
                                                  double Ri, double tinv, double umax,
                                                  const int32_t *ids, double &bq, int &bi,
-                                                 int &bj, double &b2, float *dmin = nullptr) {
+                                                 int &bj, double &b2) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;          // independent 128-bit loads in flight per lane
   constexpr int STEP = 32 * V;  // elements per warp-wide load
@@ -182,20 +179,8 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
         float su[V];
         if (V == 4) *reinterpret_cast<float4 *>(su) = *reinterpret_cast<const float4 *>(&sU[j - c0]);
         else *reinterpret_cast<float2 *>(su) = *reinterpret_cast<const float2 *>(&sU[j - c0]);
-        if (TRACK) {
-          float sv[V];
 #pragma unroll
-          for (int e = 0; e < V; ++e) sv[e] = screen_value(v[u][e]);
-          float mm = sv[0];
-#pragma unroll
-          for (int e = 1; e < V; ++e) mm = fminf(mm, sv[e]);
-          *dmin = fminf(*dmin, mm);
-#pragma unroll
-          for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(sv[e], su[e]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(screen_value(v[u][e]), su[e]);
-        }
+        for (int e = 0; e < V; ++e) qf[e] = __fsub_rn(screen_value(v[u][e]), su[e]);
       } else {
 #pragma unroll
         for (int e = 0; e < V; ++e) qf[e] = screen_value(v[u][e]);
@@ -203,7 +188,6 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
       float m = qf[0];
 #pragma unroll
       for (int e = 1; e < V; ++e) m = fminf(m, qf[e]);
-      if (TRACK && !NJ) *dmin = fminf(*dmin, m);
       if (m <= thr) {
         // rare: exact float64 evaluation of the elements that passed the screen
 #pragma unroll
