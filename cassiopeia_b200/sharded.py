@@ -349,6 +349,9 @@ def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
     e2e_s = torch.tensor([_time.perf_counter() - t_e2e0], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     assert np.array_equal(j_e2e, joins)
+    scanned = torch.tensor([last_scanned_elements], dtype=torch.int64, device="cuda")
+    dist.all_reduce(scanned, op=dist.ReduceOp.SUM)
+    scanned = int(scanned.item())
     if rank == 0:
         peak, peak_src = peaks()
         ms_per_step = total_ms / args.steps
@@ -360,8 +363,12 @@ def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
             "vs_baseline": None, "dtype": dt, "data": "synthetic",
             "config": workload_config(args, world, "fast/exact-map"),
             "clocks": clocks, "gpu_launches": int(launches[0]),
-            "roofline": {"bound": "hbm", "kernel": "sh_scan_kernel<float,NJ>", "achieved": achieved,
-                         "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
+            "roofline": {"bound": "hbm",
+                         "kernel": ("sh_scan_pruned_kernel" if scanned else "sh_scan_kernel") + "<float,NJ>",
+                         "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         # bytes the pruned scans of all ranks actually read per iteration (kernel counters)
+                         "traffic": (scanned * 4 / max(n - 2, 1)) if scanned else None,
+                         "read_fraction_of_algorithmic": (scanned * 4 / b_alg) if scanned else None,
                          "peak_source": peak_src + f" x {world} GPUs", "loop_ms": loop_ms,
                          "exchange_per_iteration": ("P2P NVLink stores + tagged flags from inside the scan/cols kernels"
                                                     if exchange == "p2p" else "2 NCCL all-gathers")
