@@ -411,21 +411,30 @@ struct Gemm2Params {
   int64_t n;
   void *D;
   int64_t ld;
+  int mchars;                // characters (int8 float path: side of the quotient table), 0 = no table
 };
 
-template <typename TO>
+// QTAB floats of shared memory hold the table of correctly rounded quotients num / den of the unweighted
+// float32 epilogue (num <= 2m, den <= m): one LDS replaces two conversions and an IEEE division per pair.
+template <typename TO, int PW>
 struct __align__(1024) Gemm2Smem {
   static constexpr int NSLOT = sizeof(TO) == 4 ? 10 : 8;
   static constexpr int HALF = 32;
+  static constexpr int QTAB = (sizeof(TO) == 4 && PW == 1) ? 7680 : 1;
   uint8_t tile[NSLOT][TILE_BYTES];
   TO stage[8][32][HALF + 1];
-  unsigned long long pm[256][MAXPW];
+  float qtab[QTAB];
+  unsigned long long pm[256][PW];
   uint64_t full[NSLOT];
   uint64_t empty[NSLOT];
   uint64_t tfull[2];
   uint64_t tempty[2];
   uint32_t tmem_base;
 };
+
+static_assert(sizeof(Gemm2Smem<float, 1>) + 1024 <= 227 * 1024 && sizeof(Gemm2Smem<double, 8>) + 1024 <= 227 * 1024 &&
+                  sizeof(Gemm2Smem<float, 8>) + 1024 <= 227 * 1024,
+              "SM-pair kernel: shared memory exceeds 227 KB");
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {
   uint32_t out;
@@ -518,7 +527,7 @@ template <bool I8, typename TO, int PW>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm2_kernel(const __grid_constant__ Gemm2Params p,
                                                                     const int64_t nwork) {
   using P = Prog<I8>;
-  using SM = Gemm2Smem<TO>;
+  using SM = Gemm2Smem<TO, PW>;
   constexpr int NSLOT = SM::NSLOT;
   constexpr int N2 = I8 ? 256 : 128;
   constexpr int NACC = I8 ? 2 : 1;
@@ -539,6 +548,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm2_kernel(const __grid
     for (int i = 0; i < (I8 ? 2 : 4); ++i) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[i]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps_half[i]) : "memory");
+    }
+  }
+  constexpr bool CAN_TAB = I8 && sizeof(TO) == 4 && PW == 1;
+  const int mp1 = p.mchars + 1;
+  const bool use_tab = CAN_TAB && p.mchars > 0;
+  if (use_tab) {
+    const int total = (2 * p.mchars + 1) * mp1;
+    for (int x = threadIdx.x; x < total; x += GEMM_THREADS) {
+      const int num = x / mp1, den = x - num * mp1;
+      sm.qtab[x] = den > 0 ? __fdiv_rn((float)num, (float)den) : 0.f;
     }
   }
   if (warp == 1) {
@@ -660,25 +679,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm2_kernel(const __grid
           }
           tmem_ld_wait();
           TO *mir = D + ((int64_t)col0 + cb) * p.ld + gi;
+          // position of the diagonal inside this 16-column block (or outside [0, 16))
+          const int64_t dd64 = gi - ((int64_t)col0 + cb);
+          const int dd = (dd64 >= 0 && dd64 < 16) ? (int)dd64 : -1;
+          const int below = gi < p.n ? (int)min((int64_t)16, max((int64_t)0, dd64)) : 0;  // columns e < below: gj < gi
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             int den = 0;
 #pragma unroll
             for (int w = 0; w < PW; ++w) den += __popcll(mrow[w] & sm.pm[cb + e][w]);
-            double num;
-            if (I8) num = (double)(int)v0[e];
-            else num = ((double)__uint_as_float(v0[e]) + (double)__uint_as_float(v1[e])) + (double)__uint_as_float(v2[e]);
             TO d = (TO)0;
-            if (den > 0) {
-              if (sizeof(TO) == 8) d = (TO)__ddiv_rn(num, (double)den);
-              else if (I8) d = (TO)__fdiv_rn((float)num, (float)den);
-              else d = (TO)__double2float_rn(__ddiv_rn(num, (double)den));
+            if (CAN_TAB && use_tab) {
+              // correctly rounded num / den from the table (den == 0 -> 0); num <= 2 m by construction
+              d = (TO)sm.qtab[(int)v0[e] * mp1 + den];
+            } else if (den > 0) {
+              if (I8) {
+                if (sizeof(TO) == 8) d = (TO)__ddiv_rn((double)(int)v0[e], (double)den);
+                else d = (TO)__fdiv_rn((float)(int)v0[e], (float)den);
+              } else {
+                const double num = ((double)__uint_as_float(v0[e]) + (double)__uint_as_float(v1[e])) +
+                                   (double)__uint_as_float(v2[e]);
+                if (sizeof(TO) == 8) d = (TO)__ddiv_rn(num, (double)den);
+                else d = (TO)__double2float_rn(__ddiv_rn(num, (double)den));
+              }
             }
-            const int64_t gj = (int64_t)col0 + cb + e;
-            if (gj == gi) d = (TO)0;
+            if (e == dd) d = (TO)0;
             stage[lane][(cb - cbase) + e] = d;
             // every unordered pair is produced once: only elements on or below the diagonal are used
-            if (whole || (gi < p.n && gj < gi)) mir[(int64_t)e * p.ld] = d;
+            if (whole || e < below) mir[(int64_t)e * p.ld] = d;
           }
         }
         if (part + HALF == WCOLS) {
@@ -914,6 +942,8 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     Gemm2Params q;
     memset(&q, 0, sizeof(q));
     q.n = n; q.D = D; q.ld = ld; q.pw = pw; q.pmask = pmask; q.chunks = p.chunks;
+    // quotient table of the unweighted float32 epilogue, when it fits (m <= 60)
+    q.mchars = (!weighted && dtype == CAS_F32 && pw == 1 && (2 * (int64_t)m + 1) * ((int64_t)m + 1) <= 7680) ? m : 0;
     const int nmaps = weighted ? 4 : 2;
     const int esz = weighted ? 2 : 1;
     const int64_t kcols = weighted ? L.Kx : L.Kp;
@@ -929,7 +959,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     const int64_t nwork = tile2_count(q.nrow_tiles, 256 / N2, q.ncol_tiles);
 #define LAUNCH_GEMM2(I8, TO, PWV)                                                                  \
   do {                                                                                             \
-    const size_t smem = sizeof(Gemm2Smem<TO>) + 1024;                                              \
+    const size_t smem = sizeof(Gemm2Smem<TO, PWV>) + 1024;                                         \
     CAS_CUDA_TRY(cudaFuncSetAttribute(whd_gemm2_kernel<I8, TO, PWV>,                               \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     cudaLaunchConfig_t cfg;                                                                        \
