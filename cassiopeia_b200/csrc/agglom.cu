@@ -129,35 +129,37 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pruned scan (exact): SURVEY §8(f) rank 4, "exact accelerated NJ beyond the dense scan".
-//
-// LB[i][s] (float, order-preserving encoding, row-major) is a LOWER bound of d(i, j) over the live columns
-// j < i of sub-segment s (SW = 128 columns).  For NJ, Rsub[s] is an UPPER bound of the row sums of the slots
-// of sub-segment s, so every pair of (row i, sub-segment s) has
-//     q = d - tinv (R_i + R_j)  >=  LB[i][s] - tinv (R_i + Rsub[s])      (UPGMA: q = d >= LB[i][s]).
-// `gbest` is the exact criterion value of some real live pair -- warm-started by the previous merge from the
-// previous scan's per-CTA winners re-evaluated with the new row sums, lowered by every warp that finds a
-// better pair -- hence an upper bound of the minimum.  A sub-segment whose bound exceeds gbest by more than
-// the near-tie window can hold neither the minimum nor a tie nor a near-tie and is skipped without touching
-// the map; everything else is screened and evaluated exactly as in the dense kernel, so the selected pair
-// and the near-tie diagnostics are IDENTICAL to the dense scan's whatever the timing of the gbest updates.
-// Bounds are kept valid, not tight:
-//   * a scanned sub-segment stores its exact minimum (self-healing: loose bounds get scanned, then are tight);
-//   * the merge lowers the bounds of the rewritten column entries (new values in column lo, moved values in
-//     column hi) with atomicMin and rebuilds Rsub with atomicMax; removed elements only leave a bound loose;
-//   * the launch's last CTA marks rows lo and hi unknown (-inf: they are rescanned once, 2k elements) and
-//     clears Rsub / gbest for the merge.
-// Initially every bound is -inf, so the first iteration is a dense scan that fills LB.
-// One warp owns a row: lane = sub-segment, so the bounds of 4096 columns are one coalesced 128-byte load
-// and one ballot; needed sub-segments are read four at a time (four 128-bit loads in flight per lane).
-// u_j = fl32(tinv R_j) comes from the global array `uf` the merge maintains (L1-resident) instead of the
-// dense kernel's shared-memory staging, because neighbouring warps work on unrelated columns.
+// Pruned scan (exact): SURVEY §8(f) rank 4, "exact accelerated NJ beyond the dense scan".  The bounds, their
+// invariants and the per-unit work are in agglom_pruned.cuh; per iteration the loop launches
+//   prune_rowtest_kernel : thread = row.  Folds the two columns the previous merge rewrote into the row's
+//                          bounds, tests the row against gbest, queues the rows that may hold a competitive
+//                          pair (initially, and for the two rewritten rows, "unknown" = always);
+//   scan_pruned_kernel   : the queued rows' work units (row, 64 sub-segments) are dealt to all warps; the
+//                          last CTA reduces the candidates, publishes the pair, commits the drift and marks the
+//                          two rows the merge is about to rewrite unknown;
+//   merge_kernel         : as before, plus uf / drift maintenance and the warm start of gbest.
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(256) prune_rowtest_kernel(PruneArgs p, const T *__restrict__ D, int64_t ld, int k,
+                                                            const double *__restrict__ R, double tinv,
+                                                            const Sel *prev, int has_prev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i >= 1 && i < k;
+  int plo = -1, phi = -1;
+  bool moved = false;
+  if (has_prev) {
+    plo = prev->lo; phi = prev->hi;
+    moved = phi != k;  // the previous iteration's last slot was k: a node moved into slot hi unless hi was last
+  }
+  prune_rowtest<T, NJ>(p, valid, i, i, D + (int64_t)(valid ? i : 0) * ld, (valid && NJ) ? R[i] : 0.0, tinv, plo, phi,
+                       moved);
+}
+
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a, PruneArgs p) {
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
   __shared__ unsigned long long sRead[SCAN_WARPS];
-  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_CH * 32];  // per warp: needed sub-segments of the round
+  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_UNIT];  // per warp: needed sub-segments of the unit
 
   const T *__restrict__ D = static_cast<const T *>(a.D);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,17 +168,27 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   rs.R = a.R; rs.ids = a.ids; rs.tinv = a.tinv;
   rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
   rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
+  rs.sbest = INFINITY; rs.ssi = -1; rs.ssj = -1; rs.uif = 0.f;
   PruneWarp pw;
   pw.gb_seen = INFINITY; pw.nread = 0;
   const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
-
-  // rows are dealt to warps from the bottom (longest first)
-  for (int i = k - 1 - gw; i >= 1; i -= W) {
-    rs.set_row(i, NJ ? a.R[i] : 0.0);
-    prune_row<T, NJ>(rs, pw, D + (int64_t)i * a.ld, p.LB + (int64_t)i * p.stride, i, a.tinv, p, sList[warp], lane);
+  const float cnow = prune_cnow(p);
+  {
+    // work units (queued row, 64 sub-segments), round-robin over all warps
+    const long long upr = (((long long)k - 1 + SW - 1) / SW + PRUNE_UNIT - 1) / PRUNE_UNIT;  // units per row
+    const long long nunits = (long long)__ldcg(p.wcount) * upr;
+    for (long long u = gw; u < nunits; u += W) {
+      const int i = p.worklist[u / upr];
+      const int sb = (int)(u % upr) * PRUNE_UNIT;
+      if ((long long)sb * SW >= i) continue;  // the row ends before this unit's first column
+      rs.set_row(i, NJ ? a.R[i] : 0.0);
+      prune_unit<T, NJ>(rs, pw, D + (int64_t)i * a.ld, p.E + (int64_t)i * p.stride, i, i, sb, cnow, p, sList[warp],
+                        lane);
+    }
   }
 
   if (lane == 0) sRead[warp] = pw.nread;
+  prune_publish_suggestion<T, NJ>(rs, p);
   Cand c = block_best(rs.bq, rs.bi, rs.bj, rs.b2, a.ids, sCand);  // contains a __syncthreads
   if (threadIdx.x == 0) {
     a.cand[blockIdx.x] = c;
@@ -207,7 +219,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     const double gap = c.q2 - c.q;
     if (gap <= 1e-6 * fmax(1.0, fabs(c.q))) atomicAdd(a.stats + 0, 1ull);
     if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
+    // every other CTA has finished (counter): clear the per-iteration state, commit the drift
     *p.gbest = enc_f64(INFINITY);
+    *p.wcount = 0u;
+    prune_commit(p);
+    p.beta[lo] = enc_f32(-INFINITY);
+    p.beta[hi] = enc_f32(-INFINITY);
   }
   {
     unsigned long long tot = 0;
@@ -216,12 +233,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
     if (lane == 0 && tot) atomicAdd(p.scanned, tot);
   }
-  // rows lo and hi are rewritten by the merge: bounds unknown.  Every other CTA has finished (counter).
+  // rows lo and hi are rewritten by the merge: bounds unknown
   const int nsk = (k + SW - 1) / SW;
   for (int sgm = threadIdx.x; sgm < nsk; sgm += SCAN_THREADS) {
-    p.LB[(int64_t)lo * p.stride + sgm] = enc_f32(-INFINITY);
-    p.LB[(int64_t)hi * p.stride + sgm] = enc_f32(-INFINITY);
-    if (NJ) p.Rsub[sgm] = enc_f32(-INFINITY);
+    p.E[(int64_t)lo * p.stride + sgm] = enc_f32(-INFINITY);
+    p.E[(int64_t)hi * p.stride + sgm] = enc_f32(-INFINITY);
   }
 }
 
@@ -241,10 +257,10 @@ struct MergeArgs {
   // strict NJ: live slots in id order, double buffered
   const int32_t *order_old; const int32_t *pos_old;
   int32_t *order_new; int32_t *pos_new;
-  // pruned scan (or null): lower bounds [row][sub-segment], per-sub-segment row-sum maxima and
-  // fl32(tinv_next * R) (NJ), last scan's per-CTA winners (warm start of gbest)
-  unsigned *LB; int64_t lb_stride; unsigned *Rsub; float *uf; double tinv_next;
-  const Cand *cand; int ncand; unsigned long long *gbest; int32_t *pool;
+  // pruned scan (prune != 0): fl32(tinv_next * R) by slot and its largest increase (NJ), last scan's
+  // per-CTA winners / suggestions and the persistent pool (warm start of gbest)
+  int prune; float *uf; double tinv_next; unsigned *dmax;
+  const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool;
 };
 
 // Pruned scan: upper bound of the next iteration's minimum = the smallest criterion value, under the NEW
@@ -272,7 +288,12 @@ __device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int
     int pi, pj, ci = -1, cj = -1;
     const double qp = eval(a.pool[2 * x], a.pool[2 * x + 1], pi, pj);
     double qc = INFINITY;
-    if (x < a.ncand) qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
+    if (x < a.ncand) {
+      qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
+      int ui2, uj2;
+      const double qs = eval(__ldcg(a.sugg + 2 * x), __ldcg(a.sugg + 2 * x + 1), ui2, uj2);
+      if (qs < qc) { qc = qs; ci = ui2; cj = uj2; }
+    }
     if (qc < qp) { a.pool[2 * x] = ci; a.pool[2 * x + 1] = cj; }
     else { a.pool[2 * x] = pi; a.pool[2 * x + 1] = pj; }
     best = fmin(best, fmin(qp, qc));
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
   const int64_t ld = a.ld;
   const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
   double contrib = 0.0;
-  float r_up = -INFINITY;       // pruned scan: this thread's new row sum, rounded up
+  float uf_up = 0.f;            // pruned scan: increase of this slot's fl32(u) (columns that keep their node)
 
   if (v < k) {
     if (v == lo) {
@@ -328,20 +349,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       }
       D[(int64_t)lo * ld + v] = nvs;
       D[(int64_t)v * ld + lo] = nvs;
-      if (a.LB) {
-        // lower bounds follow the values: pair (ve, lo) gets nvs, pair (v, hi) gets the moved value;
-        // rows lo and hi themselves were marked unknown by the scan's last CTA
-        const int ve = (v == last && hi != last) ? hi : v;
-        if (ve > lo && ve != hi)
-          atomicMin(a.LB + (int64_t)ve * a.lb_stride + lo / SW, enc_f32(screen_value(nvs)));
-        if (hi != last && v != last && v > hi)
-          atomicMin(a.LB + (int64_t)v * a.lb_stride + hi / SW, enc_f32(screen_value(moved)));
-        if (a.maintain_R) {
-          const float ru = __double2float_ru(Rv);
-          a.uf[ve] = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
-          if (ve == v) r_up = ru;
-          else atomicMax(a.Rsub + ve / SW, enc_f32(ru));
-        }
+      if (a.prune && a.maintain_R) {
+        // u of the next scan, and its increase for the columns that keep their node (the new node's column
+        // and the moved node's column are folded into the bounds exactly by the next row test)
+        const bool moves = (v == last && hi != last);
+        const float un = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
+        if (!moves) uf_up = un - a.uf[v];
+        a.uf[moves ? hi : v] = un;
       }
       if (v == last && hi != last) {
         D[(int64_t)hi * ld + lo] = nvs;
@@ -372,12 +386,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     }
   }
 
-  if (a.LB && a.maintain_R) {
-    // one atomic per warp: its 32 slots lie in one sub-segment (SW % 32 == 0)
-    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(r_up));
-    if ((threadIdx.x & 31) == 0 && m != enc_f32(-INFINITY)) atomicMax(a.Rsub + (v / SW), m);
+  if (a.prune && a.maintain_R) {
+    // largest upward drift of any column's u: one atomic per warp, skipped unless it raises the maximum
+    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(uf_up));
+    if ((threadIdx.x & 31) == 0 && m > __ldcg(a.dmax)) atomicMax(a.dmax, m);
   }
-  if (a.LB && !a.maintain_R) {
+  if (a.prune && !a.maintain_R) {
     // UPGMA: no row sums; the last CTA to finish warm-starts gbest
     __shared__ bool sLastU;
     __syncthreads();
@@ -417,12 +431,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
     a.R[lo] = sum;
     atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
-    if (a.LB) {
-      atomicMax(a.Rsub + lo / SW, enc_f32(__double2float_ru(sum)));
-      a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
-    }
+    if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
   }
-  if (sLast && a.LB) warm_start_gbest<T, NJ>(a, lo, hi, last);
+  if (sLast && a.prune) warm_start_gbest<T, NJ>(a, lo, hi, last);
 }
 
 // strict NJ: R[c] = ((0 + d[o_0][c]) + d[o_1][c]) + ... over live nodes in id order.
@@ -494,8 +505,8 @@ __global__ void __launch_bounds__(RS_THREADS) rowsum_seq_kernel(const double *__
 template <typename T>
 __global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ D, int64_t ld, int k,
                                                           double *__restrict__ R,
-                                                          unsigned long long *rmax_bits, unsigned *Rsub,
-                                                          float *uf, double tinv) {
+                                                          unsigned long long *rmax_bits, float *uf,
+                                                          double tinv) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= k) return;
@@ -507,21 +518,26 @@ __global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ 
   if (lane == 0) {
     R[row] = s;
     atomicMax(rmax_bits, (unsigned long long)__double_as_longlong(fabs(s)));
-    if (Rsub) {
-      atomicMax(Rsub + row / SW, enc_f32(__double2float_ru(s)));
-      uf[row] = __double2float_rn(__dmul_rn(tinv, s));
-    }
+    if (uf) uf[row] = __double2float_rn(__dmul_rn(tinv, s));
   }
 }
 
-// pruned scan: every bound starts at -inf ("unknown": the first iteration scans everything)
-__global__ void prune_init_kernel(unsigned *LB, int64_t count, unsigned *Rsub, int nsub, unsigned long long *gbest,
-                                  unsigned long long *scanned) {
+// pruned scan: every bound starts at -inf ("unknown": the first iteration reads everything)
+__global__ void prune_init_kernel(unsigned *E, int64_t count, unsigned *beta, int64_t nrows, float *hdr,
+                                  unsigned *dmax, unsigned long long *gbest, unsigned *wcount,
+                                  unsigned long long *scanned, int32_t *pool) {
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned ninf = enc_f32(-INFINITY);
-  for (int64_t e = x; e < count; e += (int64_t)gridDim.x * blockDim.x) LB[e] = ninf;
-  for (int64_t e = x; e < nsub; e += (int64_t)gridDim.x * blockDim.x) Rsub[e] = ninf;
-  if (x == 0) { *gbest = enc_f64(INFINITY); *scanned = 0ull; }
+  for (int64_t e = x; e < count; e += (int64_t)gridDim.x * blockDim.x) E[e] = ninf;
+  for (int64_t e = x; e < nrows; e += (int64_t)gridDim.x * blockDim.x) beta[e] = ninf;
+  if (x < 2 * POOL) pool[x] = -1;
+  if (x == 0) {
+    hdr[0] = 0.f;
+    *dmax = enc_f32(0.f);
+    *gbest = enc_f64(INFINITY);
+    *wcount = 0u;
+    *scanned = 0ull;
+  }
 }
 
 __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *order, int32_t *pos,
@@ -571,9 +587,9 @@ struct AgglomWorkspace {
   unsigned *counters;
   unsigned long long *rmax_bits;
   unsigned long long *stats;
-  unsigned *LB; unsigned *Rsub; float *uf; unsigned long long *gbest; unsigned long long *scanned;
-  unsigned long long *cta_read;
-  int32_t *pool;
+  unsigned *E; unsigned *beta; float *uf; float *hdr; unsigned *dmax; unsigned long long *gbest;
+  unsigned long long *scanned; unsigned long long *cta_read;
+  int32_t *pool; int32_t *worklist; unsigned *wcount; int32_t *sugg;
   int64_t lb_stride;
   size_t bytes;
 };
@@ -596,13 +612,18 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.stats = w.rmax_bits + 2;
   w.candx = c.take<char>(persistent_cand_bytes());
   w.lb_stride = ((n + SW - 1) / SW + 31) / 32 * 32;
-  w.LB = c.take<unsigned>((size_t)w.lb_stride * (size_t)n);
-  w.Rsub = c.take<unsigned>((size_t)w.lb_stride + 32);
+  w.E = c.take<unsigned>((size_t)w.lb_stride * (size_t)n);
+  w.beta = c.take<unsigned>((size_t)n + 32);
   w.uf = c.take<float>((size_t)n + 32);
+  w.hdr = c.take<float>(8);
+  w.dmax = c.take<unsigned>(4);
+  w.wcount = w.dmax + 1;
   w.gbest = c.take<unsigned long long>(2);
   w.scanned = w.gbest + 1;
   w.cta_read = c.take<unsigned long long>(MAX_SCAN_CTAS);
   w.pool = c.take<int32_t>(2 * POOL);
+  w.worklist = c.take<int32_t>((size_t)n + 32);
+  w.sugg = c.take<int32_t>(2 * MAX_SCAN_CTAS);
   w.bytes = c.used();
   return w;
 }
@@ -668,16 +689,15 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
   // the opt-in persistent experiment (CAS_PERSISTENT=1) keeps its dense scan
   const bool prune = !strict_nj && prune_enabled(NJ) && n > 2 && !persistent_enabled();
   if (prune) {
-    prune_init_kernel<<<sms * 4, 256, 0, stream>>>(w.LB, w.lb_stride * n, w.Rsub, (int)w.lb_stride, w.gbest,
-                                                   w.scanned);
+    prune_init_kernel<<<sms * 4, 256, 0, stream>>>(w.E, w.lb_stride * n, w.beta, n, w.hdr, w.dmax, w.gbest, w.wcount,
+                                                   w.scanned, w.pool);
     CAS_LAUNCH_CHECK();
-    CAS_CUDA_TRY(cudaMemsetAsync(w.pool, 0xFF, 2 * POOL * sizeof(int32_t), stream));  // all -1
   } else {
     CAS_CUDA_TRY(cudaMemsetAsync(w.scanned, 0, sizeof(unsigned long long), stream));
   }
   if (fast_nj && n > 2) {
     rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>((const T *)D, ld, (int)n, w.R, w.rmax_bits,
-                                                                        prune ? w.Rsub : nullptr, w.uf,
+                                                                        prune ? w.uf : nullptr,
                                                                         1.0 / (double)(n - 2));
     CAS_LAUNCH_CHECK();
   }
@@ -719,11 +739,13 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     if (grid < 1) grid = 1;
     if (prune) {
       PruneArgs pa;
-      pa.LB = w.LB; pa.stride = w.lb_stride; pa.Rsub = w.Rsub; pa.uf = w.uf; pa.gbest = w.gbest;
+      pa.E = w.E; pa.stride = w.lb_stride; pa.beta = w.beta; pa.uf = w.uf; pa.hdr = w.hdr; pa.dmax = w.dmax;
+      pa.gbest = w.gbest; pa.worklist = w.worklist; pa.wcount = w.wcount; pa.sugg = w.sugg;
       pa.scanned = w.scanned; pa.cta_read = w.cta_read;
-      // one warp per row: enough CTAs to give every SM four, never more warps than rows
-      grid = (k + SCAN_WARPS - 1) / SCAN_WARPS;
-      if (grid > sms * 3) grid = sms * 3;  // three resident CTAs per SM (80 registers)
+      prune_rowtest_kernel<T, NJ><<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(pa, (const T *)D, ld, k, w.R,
+                                                                                  sa.tinv, w.sel, t > 0 ? 1 : 0);
+      CAS_LAUNCH_CHECK();
+      grid = sms * 3;  // three resident CTAs per SM (register budget of the unit loop)
       if (grid > POOL) grid = POOL;
       scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
     } else {
@@ -739,9 +761,9 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.pos_old = strict_nj ? w.pos[cur] : nullptr;
     ma.order_new = strict_nj ? w.order[cur ^ 1] : nullptr;
     ma.pos_new = strict_nj ? w.pos[cur ^ 1] : nullptr;
-    ma.LB = prune ? w.LB : nullptr; ma.lb_stride = w.lb_stride; ma.Rsub = w.Rsub; ma.uf = w.uf;
+    ma.prune = prune ? 1 : 0; ma.uf = w.uf; ma.dmax = w.dmax;
     ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
-    ma.cand = w.cand; ma.ncand = grid; ma.gbest = w.gbest; ma.pool = w.pool;
+    ma.cand = w.cand; ma.ncand = grid; ma.sugg = w.sugg; ma.gbest = w.gbest; ma.pool = w.pool;
     merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
     CAS_LAUNCH_CHECK();
   }

@@ -1,25 +1,54 @@
 // Building blocks of the exact pruned scan, shared by the single-GPU loop (agglom.cu) and the row-sharded
-// loop (sharded.cu).  See the comment above scan_pruned_kernel in agglom.cu for the invariants.
+// loop (sharded.cu).
+//
+// Bounds.  For NJ the criterion of a pair is q = d_ij - u_i - u_j with u = tinv * R (UPGMA: q = d, u = 0).
+// For every row i and every 128-column sub-segment s of its lower-triangle part the scan keeps
+//     E[i][s]  <=  min_j ( d_ij - uf_j ) + C          (uf_j = fl32(u_j), j live, j < i, j in s)
+// where C is the cumulative UPWARD drift of the uf_j: every merge measures the largest increase of any
+// column's uf and adds it to C, so a bound written at drift C0 as (min + C0) stays valid for ever as
+// (E - C): the columns' uf can only have grown by C - C0 since then.  The two columns a merge rewrites (the
+// new node in slot lo, the node that moved into slot hi) are excluded from the drift and folded into the
+// bounds with their exact values by the next iteration's row-test kernel; the two rewritten rows are marked
+// unknown (-inf) and rescanned once.  beta[i] = min_s E[i][s] gives a one-load test per row.
+//
+// A pair can only win, tie or be a near-tie runner-up if q <= gbest + window, where gbest is the exact
+// criterion of some real pair (warm-started by the previous merge from a persistent pool of good pairs,
+// lowered by every warp that finds a better one).  Rows / sub-segments whose bound says "impossible" are
+// never read; everything else goes through the same float32 screen + exact float64 evaluation +
+// (value, id_lo, id_hi) rule as the dense scan.  Hence the selected pair and the near-tie diagnostics are
+// IDENTICAL to the dense scan's, whatever the timing of the gbest updates.
 #pragma once
 
 #include "agglom_common.cuh"
 
 namespace cas {
 
-constexpr int PRUNE_CH = 8;  // chunks of 32 sub-segments a warp decides together
-
-constexpr int SW = 128;  // columns per lower bound
-constexpr int POOL = 512;  // pairs kept to warm-start the bound (>= CTAs of the pruned scan)
+constexpr int SW = 128;        // columns per bound (sub-segment)
+constexpr int PRUNE_CH = 2;    // chunks of 32 sub-segments per work unit
+constexpr int PRUNE_UNIT = PRUNE_CH * 32;  // sub-segments per work unit (8192 columns): one warp, one round
+constexpr int POOL = 512;      // pairs kept to warm-start gbest (>= CTAs of the pruned scan)
 
 struct PruneArgs {
-  unsigned *LB;               // [n][stride]
+  unsigned *E;                // [rows][stride] encoded float bounds (see above)
   int64_t stride;             // sub-segments per row, multiple of 32
-  unsigned *Rsub;             // [stride] encoded float, NJ only
-  const float *uf;            // [n] fl32(tinv * R_j), NJ only
+  unsigned *beta;             // [rows] encoded float, min over the row's E
+  const float *uf;            // [n] fl32(tinv * R_j) by slot (NJ; unused for UPGMA)
+  float *hdr;                 // [0] = C as of the previous scan
+  unsigned *dmax;             // encoded float: largest uf increase measured by the last merge
   unsigned long long *gbest;  // encoded double
-  unsigned long long *scanned;  // statistics: map elements actually read
-  unsigned long long *cta_read; // [gridDim] per-CTA element counts of this launch (summed by the last CTA)
+  int32_t *worklist;          // rows that failed this iteration's row test (row indices)
+  unsigned *wcount;
+  int32_t *sugg;              // [gridDim][2] per-CTA suggestion (slots) for the pool
+  unsigned long long *scanned;   // statistics: map elements actually read
+  unsigned long long *cta_read;  // [gridDim] per-CTA counts of this launch (summed by the last CTA)
 };
+
+// C as of THIS scan: identical in every thread of every kernel of the iteration (two scalar loads)
+__device__ __forceinline__ float prune_cnow(const PruneArgs &p) {
+  // directed rounding: C must never under-estimate the true cumulative drift
+  const float d = fmaxf(dec_f32(__ldcg(p.dmax)), 0.f);
+  return __fadd_ru(p.hdr[0], __fmul_ru(d, 1.000001f));
+}
 
 template <typename T, bool NJ>
 struct RowScan {
@@ -31,14 +60,14 @@ struct RowScan {
   int bi, bj;
   int i;
   double Ri, ui;
-  double cap;  // gbest + margin: exact evaluation (and candidate recording) stops above it.  The margin is
-               // the near-tie window or 1 % of |gbest|, whichever is larger: pairs above the window cannot
-               // win, tie or be a near-tie runner-up; the extra 1 % keeps the per-CTA winners that warm-start
-               // the next iteration's bound plentiful at negligible cost
-  float thr;
+  double cap;  // gbest + near-tie window: pairs above it cannot win, tie or be a near-tie runner-up, so the
+               // (slow, serial) exact evaluation stops there
+  float thr, uif;
+  // cheap "suggestion" for the pool: the lane's smallest float32-screened criterion over everything it read
+  float sbest;
+  int ssi, ssj;
   // near-tie window of the diagnostics (1e-6 relative, absolute below 1) around the value x
   static __device__ __forceinline__ double window(double x) { return 1.0000001e-6 * fmax(1.0, fabs(x)); }
-  // the lane's own best is usually far looser than the global bound (a lane sees few elements per launch)
   __device__ __forceinline__ float threshold() const {
     const double best = bi >= 0 ? fmin(bq, cap) : cap;
     if (best == INFINITY) return INFINITY;
@@ -47,28 +76,35 @@ struct RowScan {
     return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + 1e-300);
   }
   __device__ __forceinline__ void set_cap(double gb) {
-    const double c = gb + fmax(window(gb), 0.01 * fabs(gb)) + 1e-9 * fabs(gb);
+    const double c = gb + window(gb) + 1e-9 * fabs(gb);
     if (c < cap) { cap = c; thr = threshold(); }
   }
   __device__ __forceinline__ void set_row(int row, double ri) {
     i = row; Ri = ri;
     ui = NJ ? __dmul_rn(tinv, Ri) : 0.0;
+    uif = (float)ui;
     thr = threshold();
   }
-  // one 128-bit vector of row i starting at column j; columns >= jend are not part of the triangle.
-  // Returns the minimum of the float32 (rounded-down) dissimilarities of the valid columns.
-  // GUARD = false: every column of the vector is known to be < jend (interior sub-segments).
-  template <bool GUARD = true>
+  // one 128-bit vector of row i starting at column j; columns >= jend are not part of the triangle
+  // (GUARD = false: all columns are known to be valid).  Returns min (fl32(d) - uf_j) over the valid columns.
+  template <bool GUARD>
   __device__ __forceinline__ float vec(const T (&v)[V], const float (&su)[V], int j, int jend) {
-    float sv[V], qf[V];
+    float qf[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      sv[e] = (!GUARD || j + e < jend) ? screen_value(v[e]) : INFINITY;
-      qf[e] = NJ ? __fsub_rn(sv[e], su[e]) : sv[e];
+      const float sv = (!GUARD || j + e < jend) ? screen_value(v[e]) : INFINITY;
+      qf[e] = NJ ? __fsub_rn(sv, su[e]) : sv;
     }
-    float m = qf[0], dm = sv[0];
+    float m = qf[0];
 #pragma unroll
-    for (int e = 1; e < V; ++e) { m = fminf(m, qf[e]); dm = fminf(dm, sv[e]); }
+    for (int e = 1; e < V; ++e) m = fminf(m, qf[e]);
+    if (m - uif < sbest) {
+      sbest = m - uif;
+      ssi = i;
+#pragma unroll
+      for (int e = V - 1; e >= 0; --e)
+        if (qf[e] == m) ssj = j + e;
+    }
     if (m <= thr) {
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -84,160 +120,231 @@ struct RowScan {
         }
       }
     }
-    return dm;
+    return m;
   }
 };
 
-// Scan state of one warp that persists over the rows it handles in a launch.
+// "a row / sub-segment with bound b (already minus C) and own u cannot hold a competitive pair":
+// false while gbest = +inf or the bound is -inf (unknown)
+template <typename T, bool NJ>
+__device__ __forceinline__ bool prune_impossible(float e, float cnow, float uif, double gb) {
+  const float gbw = __double2float_ru(gb + RowScan<T, NJ>::window(gb));
+  const float mag = fabsf(gbw) + fabsf(uif) + fabsf(e) + cnow;
+  return (e - cnow) > (gbw + uif) + 2e-6f * mag;
+}
+
+// Row-test kernel body (thread = row): fold the two columns the previous merge rewrote into the row's
+// bounds, test the row, queue it if it may hold a competitive pair.  `row` = the row's map elements,
+// prev_* = slots of the previous join (prev_lo < 0: none yet; prev_moved: a node moved into slot prev_hi).
+template <typename T, bool NJ>
+__device__ __forceinline__ void prune_rowtest(const PruneArgs &p, bool valid, int64_t ridx, int i, const T *row,
+                                              double Ri, double tinv, int prev_lo, int prev_hi, bool prev_moved) {
+  const float cnow = prune_cnow(p);
+  bool unsafe = false;
+  if (valid) {
+    unsigned b = p.beta[ridx];
+    if (prev_lo >= 0 && i != prev_lo && i != prev_hi) {
+      unsigned *erow = p.E + ridx * p.stride;
+      if (i > prev_lo) {
+        const float x = screen_value(row[prev_lo]);
+        const float q = x - (NJ ? p.uf[prev_lo] : 0.f);
+        const unsigned e = enc_f32((q + cnow) - 1e-6f * (fabsf(x) + fabsf(q) + cnow));
+        erow[prev_lo / SW] = min(erow[prev_lo / SW], e);
+        b = min(b, e);
+      }
+      if (prev_moved && i > prev_hi) {
+        const float x = screen_value(row[prev_hi]);
+        const float q = x - (NJ ? p.uf[prev_hi] : 0.f);
+        const unsigned e = enc_f32((q + cnow) - 1e-6f * (fabsf(x) + fabsf(q) + cnow));
+        erow[prev_hi / SW] = min(erow[prev_hi / SW], e);
+        b = min(b, e);
+      }
+    }
+    const double gb = dec_f64(__ldcg(p.gbest));
+    unsafe = !prune_impossible<T, NJ>(dec_f32(b), cnow, NJ ? (float)(tinv * Ri) : 0.f, gb);
+    // an unsafe row's beta is rebuilt by its work units (atomicMin)
+    p.beta[ridx] = unsafe ? enc_f32(INFINITY) : b;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, unsafe);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(p.wcount, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (unsafe) p.worklist[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)ridx;
+  }
+}
+
+// Scan state of one warp that persists over the work units it handles in a launch.
 struct PruneWarp {
   double gb_seen;             // latest value of gbest this warp has read or written
   unsigned long long nread;   // map elements read
 };
 
-// One row of the pruned scan, handled by one warp: decide from the row's lower bounds which sub-segments
-// can hold the minimum (or a near-tie), read exactly those, refresh their bounds, publish improvements of
-// the global bound.  `row` / `lbrow` point at the row's map elements / bounds, `i` is its slot (columns
-// [0, i) belong to the lower triangle), `list` is the warp's shared-memory scratch (CH * 32 entries).
+// One work unit = sub-segments [sb, sb + PRUNE_UNIT) of one row, handled by one warp: decide from the bounds
+// which sub-segments can hold a competitive pair, read exactly those (eight 128-bit loads in flight per
+// lane), refresh their bounds, lower the row bound, publish improvements of gbest.  `row` / `erow` point at
+// the row's map elements / bounds, `i` is its slot (columns [0, i) are the lower triangle), `list` is the
+// warp's shared-memory scratch (PRUNE_UNIT entries).
 template <typename T, bool NJ>
-__device__ __forceinline__ void prune_row(RowScan<T, NJ> &rs, PruneWarp &pw, const T *__restrict__ row,
-                                          unsigned *lbrow, int i, double tinv_, const PruneArgs &p,
-                                          unsigned short *list, int lane) {
+__device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, const T *__restrict__ row,
+                                           unsigned *erow, int64_t ridx, int i, int sb, float cnow,
+                                           const PruneArgs &p, unsigned short *list, int lane) {
   constexpr int V = VecOf<T>::N;
   constexpr int LOADS = SW / (32 * V);  // 128-bit loads per lane and sub-segment (1 float, 2 double)
-  constexpr int G = 8 / LOADS;          // sub-segments in flight: eight 128-bit loads per lane
-  constexpr int CH = PRUNE_CH;          // chunks of 32 sub-segments decided together (32768 columns)
+  constexpr int G = 8 / LOADS;          // sub-segments in flight
+  constexpr int CH = PRUNE_CH;
   const int nsub = (i + SW - 1) / SW;   // sub-segments holding a column < i; the last one ends at the diagonal
-  double &gb_seen = pw.gb_seen;
-  bool scanned_any = false;
-  for (int sb = 0; sb < nsub; sb += CH * 32) {
-    // ---- decide: lane l looks at sub-segments sb + 32 c + l, c < CH (coalesced 128-byte loads).
-    // Float arithmetic; every rounding is covered by the relative slack, which only makes the test
-    // scan a little more:  skip  <=>  lb - us > (gbest + window) + u_i + slack.
-    const double gb = dec_f64(__ldcg(p.gbest));
-    gb_seen = gb;
-    rs.set_cap(gb);
-    const float gbw = __double2float_ru(gb + RowScan<T, NJ>::window(gb));
-    const float uif = NJ ? __double2float_ru(rs.ui) : 0.f;
-    const float tinvf = (float)tinv_;
-    const float base = gbw + uif;
-    const float mag0 = fabsf(gbw) + fabsf(uif);
-    unsigned lbv[CH], rsv[CH];
+  // ---- decide: lane l looks at sub-segments sb + 32 c + l (coalesced 128-byte loads of the bounds)
+  const double gb = dec_f64(__ldcg(p.gbest));
+  pw.gb_seen = gb;
+  rs.set_cap(gb);
+  unsigned flags = 0;
+  unsigned kept = enc_f32(INFINITY);  // lane: smallest bound it looked at and skipped
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int sgm = sb + c * 32 + lane;
-      lbv[c] = sgm < nsub ? lbrow[sgm] : enc_f32(INFINITY);
-      rsv[c] = (NJ && sgm < nsub) ? p.Rsub[sgm] : enc_f32(0.f);
+  for (int c = 0; c < CH; ++c) {
+    const int sgm = sb + c * 32 + lane;
+    if (sb + c * 32 >= nsub) break;  // warp-uniform
+    const bool exists = sgm < nsub;
+    const unsigned e = exists ? erow[sgm] : enc_f32(INFINITY);
+    const bool skip = prune_impossible<T, NJ>(dec_f32(e), cnow, rs.uif, gb);
+    flags |= ((exists && !skip) ? 1u : 0u) << c;
+    if (exists && skip) kept = min(kept, e);
+  }
+  // the diagonal sub-segment needs per-column guards: it is handled apart from the interior ones
+  bool diag_needed = false;
+  {
+    const int dsub = nsub - 1 - sb;
+    if (dsub >= 0 && dsub < CH * 32) {
+      const unsigned bit = (lane == (dsub & 31)) ? (1u << (dsub >> 5)) : 0u;
+      diag_needed = __any_sync(0xffffffffu, (flags & bit) != 0u);
+      flags &= ~bit;
     }
-    unsigned flags = 0;
+  }
+  // ---- compact the needed interior sub-segments into the warp's list
+  const int cnt = __popc(flags);
+  int total = 0;
+  if (__any_sync(0xffffffffu, cnt != 0)) {
+    int pre = cnt;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      if (sb + c * 32 >= nsub) break;  // warp-uniform: no sub-segment of this chunk exists
-      const float lb = dec_f32(lbv[c]);
-      const float us = NJ ? tinvf * dec_f32(rsv[c]) : 0.f;
-      const float mag = mag0 + fabsf(lb) + fabsf(us);
-      // false while gbest = +inf or lb = -inf (unknown): then the sub-segment is read
-      const bool skip = (lb - us) > base + 1e-6f * mag;
-      const bool nd = (sb + c * 32 + lane < nsub) && !skip;
-      flags |= (nd ? 1u : 0u) << c;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, pre, off);
+      if (lane >= off) pre += o;
     }
-    // the diagonal sub-segment needs per-column guards: it is handled apart from the interior ones
-    bool diag_needed = false;
-    {
-      const int dsub = nsub - 1 - sb;  // position of the diagonal sub-segment in this round, if any
-      if (dsub >= 0 && dsub < CH * 32) {
-        const unsigned bit = (lane == (dsub & 31)) ? (1u << (dsub >> 5)) : 0u;
-        diag_needed = __any_sync(0xffffffffu, (flags & bit) != 0u);
-        flags &= ~bit;
+    total = __shfl_sync(0xffffffffu, pre, 31);
+    int wpos = pre - cnt;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if ((flags >> c) & 1u) list[wpos++] = (unsigned short)(c * 32 + lane);
+    __syncwarp();
+  }
+  unsigned fresh = enc_f32(INFINITY);  // warp: smallest refreshed bound
+  // ---- read them, G at a time (all columns valid: no guards)
+  for (int base_i = 0; base_i < total; base_i += G) {
+    int sg[G];
+    T v[G][LOADS][V];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      sg[g] = (base_i + g < total) ? sb + (int)list[base_i + g] : -1;
+      if (sg[g] >= 0) {
+#pragma unroll
+        for (int l = 0; l < LOADS; ++l) ld_stream<false>(row + sg[g] * SW + l * 32 * V + lane * V, v[g][l]);
       }
     }
-    // ---- compact the needed interior sub-segments into the warp's list
-    const int cnt = __popc(flags);
-    int total = 0;
-    if (__any_sync(0xffffffffu, cnt != 0)) {
-      int pre = cnt;
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, pre, off);
-        if (lane >= off) pre += o;
-      }
-      total = __shfl_sync(0xffffffffu, pre, 31);
-      int wpos = pre - cnt;
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if ((flags >> c) & 1u) list[wpos++] = (unsigned short)(c * 32 + lane);
-      __syncwarp();
-    }
-    if (total == 0 && !diag_needed) continue;
-    // ---- read them, G at a time (all columns valid: no guards)
-    for (int base_i = 0; base_i < total; base_i += G) {
-      int sg[G];
-      T v[G][LOADS][V];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        sg[g] = (base_i + g < total) ? sb + (int)list[base_i + g] : -1;
-        if (sg[g] >= 0) {
-#pragma unroll
-          for (int l = 0; l < LOADS; ++l) ld_stream<false>(row + sg[g] * SW + l * 32 * V + lane * V, v[g][l]);
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (sg[g] < 0) continue;  // warp-uniform
-        float dm = INFINITY;
-#pragma unroll
-        for (int l = 0; l < LOADS; ++l) {
-          const int j = sg[g] * SW + l * 32 * V + lane * V;
-          float su[V];
-#pragma unroll
-          for (int e = 0; e < V; ++e) su[e] = 0.f;
-          if (NJ) {
-            if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
-            else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
-          }
-          dm = fminf(dm, rs.template vec<false>(v[g][l], su, j, i));
-        }
-        const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32(dm));
-        if (lane == 0) lbrow[sg[g]] = m;
-      }
-    }
-    pw.nread += (unsigned long long)total * SW;
-    if (diag_needed) {
-      const int sgd = nsub - 1;
+    for (int g = 0; g < G; ++g) {
+      if (sg[g] < 0) continue;  // warp-uniform
       float dm = INFINITY;
 #pragma unroll
       for (int l = 0; l < LOADS; ++l) {
-        const int j = sgd * SW + l * 32 * V + lane * V;
-        T v[V];
+        const int j = sg[g] * SW + l * 32 * V + lane * V;
         float su[V];
 #pragma unroll
-        for (int e = 0; e < V; ++e) { v[e] = (T)INFINITY; su[e] = 0.f; }
-        if (j < i) {
-          ld_stream<false>(row + j, v);
-          if (NJ) {
-            if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
-            else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
-          }
+        for (int e = 0; e < V; ++e) su[e] = 0.f;
+        if (NJ) {
+          if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
+          else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
         }
-        dm = fminf(dm, rs.template vec<true>(v, su, j, i));
+        dm = fminf(dm, rs.template vec<false>(v[g][l], su, j, i));
       }
-      const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32(dm));
-      if (lane == 0) lbrow[sgd] = m;
-      pw.nread += (unsigned long long)(i - sgd * SW);
+      // bound in the drifting frame, rounded down by more than the float operations can have rounded up
+      const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32((dm + cnow) - 1e-6f * (fabsf(dm) + cnow)));
+      if (lane == 0) erow[sg[g]] = m;
+      fresh = min(fresh, m);
     }
-    scanned_any = true;
-    __syncwarp();  // the list is rewritten by the next round
   }
-  if (scanned_any) {
+  pw.nread += (unsigned long long)total * SW;
+  if (diag_needed) {
+    const int sgd = nsub - 1;
+    float dm = INFINITY;
+#pragma unroll
+    for (int l = 0; l < LOADS; ++l) {
+      const int j = sgd * SW + l * 32 * V + lane * V;
+      T v[V];
+      float su[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) { v[e] = (T)INFINITY; su[e] = 0.f; }
+      if (j < i) {
+        ld_stream<false>(row + j, v);
+        if (NJ) {
+          if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
+          else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
+        }
+      }
+      dm = fminf(dm, rs.template vec<true>(v, su, j, i));
+    }
+    const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32((dm + cnow) - 1e-6f * (fabsf(dm) + cnow)));
+    if (lane == 0) erow[sgd] = m;
+    fresh = min(fresh, m);
+    pw.nread += (unsigned long long)(i - sgd * SW);
+  }
+  // the row bound: every sub-segment of the unit was either kept or refreshed
+  {
+    const unsigned bm = min(__reduce_min_sync(0xffffffffu, kept), fresh);
+    if (lane == 0) atomicMin(p.beta + ridx, bm);
+  }
+  if (total > 0 || diag_needed) {
     double wb = rs.bq;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, off));
     // publish only real improvements of the global bound (one address: keep the atomics rare)
-    if (wb < gb_seen) {
+    if (wb < pw.gb_seen) {
       if (lane == 0) atomicMin(p.gbest, enc_f64(wb));
-      gb_seen = wb;
+      pw.gb_seen = wb;
       rs.set_cap(wb);
     }
+    __syncwarp();  // the list is rewritten by the warp's next unit
   }
+}
+
+// Per-CTA suggestion = the smallest float-screened value any lane saw, with its pair.  All threads call it.
+template <typename T, bool NJ>
+__device__ __forceinline__ void prune_publish_suggestion(const RowScan<T, NJ> &rs, const PruneArgs &p) {
+  __shared__ float sSv[SCAN_WARPS];
+  __shared__ int sSi[SCAN_WARPS], sSj[SCAN_WARPS];
+  float v = rs.sbest;
+  int si = rs.ssi, sj = rs.ssj;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, si, off), oj = __shfl_xor_sync(0xffffffffu, sj, off);
+    if (ov < v) { v = ov; si = oi; sj = oj; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sSv[warp] = v; sSi[warp] = si; sSj[warp] = sj; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SCAN_WARPS; ++w)
+      if (sSv[w] < v) { v = sSv[w]; si = sSi[w]; sj = sSj[w]; }
+    p.sugg[2 * blockIdx.x] = v < INFINITY ? si : -1;
+    p.sugg[2 * blockIdx.x + 1] = v < INFINITY ? sj : -1;
+  }
+}
+
+// After every CTA of a scan has finished: commit the drift (C := C as of this scan, dmax := 0).  One thread.
+__device__ __forceinline__ void prune_commit(const PruneArgs &p) {
+  p.hdr[0] = prune_cnow(p);
+  *p.dmax = enc_f32(0.f);
 }
 
 }  // namespace cas

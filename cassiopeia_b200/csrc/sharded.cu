@@ -173,15 +173,33 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) sh_scan_kernel(ShScanArgs a) 
   }
 }
 
-// Pruned scan of the local rows (same row body as the single-GPU scan_pruned_kernel, agglom_pruned.cuh):
-// bounds, gbest and the candidate pool are per rank and never cross the link -- a rank's bound is the value
-// of one of its own real pairs, which is an upper bound of the global minimum as well.
+// Pruned scan of the local rows (agglom_pruned.cuh): bounds, gbest and the pool are per rank and never cross
+// the link -- a rank's bound is the value of one of its own real pairs, an upper bound of the global minimum
+// as well.  Row indices in the work list, E and beta are LOCAL rows.
+template <typename T, bool NJ>
+__global__ void __launch_bounds__(256) sh_rowtest_kernel(PruneArgs p, const T *__restrict__ Dloc, int64_t ld, int k,
+                                                         int G, int r, const double *__restrict__ R, double tinv,
+                                                         const Sel *prev, int has_prev) {
+  const int lr = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nloc = sh_count(k, r, G);
+  const int i = lr < nloc ? sh_slot(lr, r, G) : 0;
+  const bool valid = lr < nloc && i >= 1;
+  int plo = -1, phi = -1;
+  bool moved = false;
+  if (has_prev) {
+    plo = prev->lo; phi = prev->hi;
+    moved = phi != k;
+  }
+  prune_rowtest<T, NJ>(p, valid, lr, i, Dloc + (int64_t)(valid ? lr : 0) * ld, (valid && NJ) ? R[i] : 0.0, tinv, plo,
+                       phi, moved);
+}
+
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanArgs a, PruneArgs p) {
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
   __shared__ unsigned long long sRead[SCAN_WARPS];
-  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_CH * 32];
+  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_UNIT];
   const T *__restrict__ D = static_cast<const T *>(a.Dloc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
@@ -189,18 +207,26 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanA
   rs.R = a.R; rs.ids = a.ids; rs.tinv = a.tinv;
   rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
   rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
+  rs.sbest = INFINITY; rs.ssi = -1; rs.ssj = -1; rs.uif = 0.f;
   PruneWarp pw;
   pw.gb_seen = INFINITY; pw.nread = 0;
   const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
-  const int nloc = sh_count(k, a.r, a.G);
-  for (int lr = nloc - 1 - gw; lr >= 0; lr -= W) {
-    const int i = sh_slot(lr, a.r, a.G);
-    if (i < 1) continue;
-    rs.set_row(i, NJ ? a.R[i] : 0.0);
-    prune_row<T, NJ>(rs, pw, D + (int64_t)lr * a.ld, p.LB + (int64_t)lr * p.stride, i, a.tinv, p, sList[warp],
-                     lane);
+  const float cnow = prune_cnow(p);
+  {
+    const long long upr = (((long long)k - 1 + SW - 1) / SW + PRUNE_UNIT - 1) / PRUNE_UNIT;  // units per row
+    const long long nunits = (long long)__ldcg(p.wcount) * upr;
+    for (long long u = gw; u < nunits; u += W) {
+      const int lr = p.worklist[u / upr];
+      const int i = sh_slot(lr, a.r, a.G);
+      const int sb = (int)(u % upr) * PRUNE_UNIT;
+      if ((long long)sb * SW >= i) continue;
+      rs.set_row(i, NJ ? a.R[i] : 0.0);
+      prune_unit<T, NJ>(rs, pw, D + (int64_t)lr * a.ld, p.E + (int64_t)lr * p.stride, lr, i, sb, cnow, p,
+                        sList[warp], lane);
+    }
   }
   if (lane == 0) sRead[warp] = pw.nread;
+  prune_publish_suggestion<T, NJ>(rs, p);
   Cand c = block_best(rs.bq, rs.bi, rs.bj, rs.b2, a.ids, sCand);
   if (threadIdx.x == 0) {
     a.cand[blockIdx.x] = c;
@@ -221,6 +247,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanA
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
     if (lane == 0 && tot) atomicAdd(p.scanned, tot);
+  }
+  if (threadIdx.x == 0) {
+    // every other CTA of this rank has finished (counter): clear the per-iteration state, commit the drift
+    *p.gbest = enc_f64(INFINITY);
+    *p.wcount = 0u;
+    prune_commit(p);
   }
   if (a.peers.ex[0] != nullptr) {
     if (threadIdx.x < a.G) {
@@ -249,8 +281,8 @@ struct ShColsArgs {
   ShPeers peers;
   unsigned long long tag;
   unsigned *counter;
-  // pruned scan (or null): the joined rows' bounds become unknown, Rsub / gbest are cleared for the merge
-  unsigned *LB; int64_t lb_stride; unsigned *Rsub; unsigned long long *gbest;
+  // pruned scan (or E == null): the bounds of the two rows the merge rewrites become unknown
+  unsigned *E; int64_t e_stride; unsigned *beta;
 };
 
 template <typename T>
@@ -268,15 +300,17 @@ __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
   const Cand c = reduce_candidates(cand_all, a.G, sCand);
   const int lo = min(c.si, c.sj), hi = max(c.si, c.sj), last = a.k - 1;
   const T *__restrict__ D = static_cast<const T *>(a.Dloc);
-  if (a.LB && blockIdx.x == 0) {
+  if (a.E && blockIdx.x == 0) {
     const int nsk = (a.k + SW - 1) / SW;
     const bool own_lo = sh_owner(lo, a.G) == a.r, own_hi = sh_owner(hi, a.G) == a.r;
     for (int sgm = threadIdx.x; sgm < nsk; sgm += 256) {
-      if (own_lo) a.LB[(int64_t)sh_local(lo, a.G) * a.lb_stride + sgm] = enc_f32(-INFINITY);
-      if (own_hi) a.LB[(int64_t)sh_local(hi, a.G) * a.lb_stride + sgm] = enc_f32(-INFINITY);
-      a.Rsub[sgm] = enc_f32(-INFINITY);
+      if (own_lo) a.E[(int64_t)sh_local(lo, a.G) * a.e_stride + sgm] = enc_f32(-INFINITY);
+      if (own_hi) a.E[(int64_t)sh_local(hi, a.G) * a.e_stride + sgm] = enc_f32(-INFINITY);
     }
-    if (threadIdx.x == 0) *a.gbest = enc_f64(INFINITY);
+    if (threadIdx.x == 0) {
+      if (own_lo) a.beta[sh_local(lo, a.G)] = enc_f32(-INFINITY);
+      if (own_hi) a.beta[sh_local(hi, a.G)] = enc_f32(-INFINITY);
+    }
   }
   const int lr = blockIdx.x * 256 + threadIdx.x;
   if (lr < sh_count(a.k, a.r, a.G)) {
@@ -341,9 +375,9 @@ struct ShMergeArgs {
   int maintain_R;
   ShPeers peers;
   unsigned long long tag;
-  // pruned scan (or null), see MergeArgs in agglom.cu
-  unsigned *LB; int64_t lb_stride; unsigned *Rsub; float *uf; double tinv_next;
-  const Cand *cand; int ncand; unsigned long long *gbest; int32_t *pool;
+  // pruned scan (prune != 0), see MergeArgs in agglom.cu
+  int prune; float *uf; double tinv_next; unsigned *dmax;
+  const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool;
 };
 
 // Per-rank warm start of the pruned scan's bound (cf. warm_start_gbest in agglom.cu): only pairs whose row
@@ -369,7 +403,12 @@ __device__ __forceinline__ void sh_warm_start(const ShMergeArgs &a, int lo, int 
     int pi, pj, ci = -1, cj = -1;
     const double qp = eval(a.pool[2 * x], a.pool[2 * x + 1], pi, pj);
     double qc = INFINITY;
-    if (x < a.ncand) qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
+    if (x < a.ncand) {
+      qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
+      int ui2, uj2;
+      const double qs = eval(__ldcg(a.sugg + 2 * x), __ldcg(a.sugg + 2 * x + 1), ui2, uj2);
+      if (qs < qc) { qc = qs; ci = ui2; cj = uj2; }
+    }
     if (qc < qp) { a.pool[2 * x] = ci; a.pool[2 * x + 1] = cj; }
     else { a.pool[2 * x] = pi; a.pool[2 * x + 1] = pj; }
     best = fmin(best, fmin(qp, qc));
@@ -413,7 +452,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
 
   const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
   double contrib = 0.0, mine = 0.0;
-  float r_up = -INFINITY;
+  float uf_up = 0.f;
   if (v < k) {
     const bool own_v = sh_owner(v, G) == a.r;
     T *row_v = own_v ? D + (int64_t)sh_local(v, G) * ld : nullptr;
@@ -438,20 +477,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
       }
       if (own_lo) row_lo[v] = nvs;
       if (own_v) row_v[lo] = nvs;
-      if (a.LB) {
-        const bool moves = (v == last && hi != last);  // this node ends up in slot hi (bounds unknown there)
-        if (own_v && !moves) {
-          unsigned *lbv = a.LB + (int64_t)sh_local(v, G) * a.lb_stride;
-          if (v > lo) atomicMin(lbv + lo / SW, enc_f32(screen_value(nvs)));
-          if (hi != last && v > hi) atomicMin(lbv + hi / SW, enc_f32(screen_value(gathered(2, v))));
-        }
-        if (a.maintain_R) {
-          const int ve = moves ? hi : v;
-          const float ru = __double2float_ru(Rv);
-          a.uf[ve] = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
-          if (!moves) r_up = ru;
-          else atomicMax(a.Rsub + ve / SW, enc_f32(ru));
-        }
+      if (a.prune && a.maintain_R) {
+        const bool moves = (v == last && hi != last);
+        const float un = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
+        if (!moves) uf_up = un - a.uf[v];
+        a.uf[moves ? hi : v] = un;
       }
       if (v == last && hi != last) {
         a.ids[hi] = a.ids[last];
@@ -463,11 +493,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
       }
     }
   }
-  if (a.LB && a.maintain_R) {
-    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(r_up));
-    if ((threadIdx.x & 31) == 0 && m != enc_f32(-INFINITY)) atomicMax(a.Rsub + (v / SW), m);
+  if (a.prune && a.maintain_R) {
+    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(uf_up));
+    if ((threadIdx.x & 31) == 0 && m > __ldcg(a.dmax)) atomicMax(a.dmax, m);
   }
-  if (a.LB && !a.maintain_R) {
+  if (a.prune && !a.maintain_R) {
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -499,12 +529,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
     for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
     a.R[lo] = sum;
     atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
-    if (a.LB) {
-      atomicMax(a.Rsub + lo / SW, enc_f32(__double2float_ru(sum)));
-      a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
-    }
+    if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
   }
-  if (sLast && a.LB) sh_warm_start<T, NJ>(a, lo, hi, last);
+  if (sLast && a.prune) sh_warm_start<T, NJ>(a, lo, hi, last);
 }
 
 // initial row sums of the local rows (same lane-strided order as rowsum_init_kernel)
@@ -549,7 +576,7 @@ __global__ void __launch_bounds__(256) sh_rowsum_kernel(const T *__restrict__ D,
 
 __global__ void sh_rscatter_kernel(const double *gath, int chunk, int k, int G, int r,
                                    double *__restrict__ R, unsigned long long *rmax_bits, ShPeers peers,
-                                   unsigned long long tag, unsigned *Rsub, float *uf, double tinv) {
+                                   unsigned long long tag, float *uf, double tinv) {
   if (peers.ex[0] != nullptr) {
     ShExHeader *own = ex_header(peers.ex[r]);
     if (threadIdx.x < G) wait_flag(&own->flag2[threadIdx.x], tag, &own->error);
@@ -561,10 +588,7 @@ __global__ void sh_rscatter_kernel(const double *gath, int chunk, int k, int G, 
   if (v < k) {
     s = gath[(int64_t)sh_owner(v, G) * chunk + sh_local(v, G)];
     R[v] = s;
-    if (Rsub) {
-      atomicMax(Rsub + v / SW, enc_f32(__double2float_ru(s)));
-      uf[v] = __double2float_rn(__dmul_rn(tinv, s));
-    }
+    if (uf) uf[v] = __double2float_rn(__dmul_rn(tinv, s));
   }
   warp_atomic_absmax(rmax_bits, s);
 }
@@ -577,14 +601,21 @@ __global__ void sh_init_kernel(int n, int32_t *ids, int32_t *sizes, unsigned *co
   if (v == 0) *rmax_bits = 0ull;
 }
 
-__global__ void sh_prune_init_kernel(unsigned *LB, int64_t count, unsigned *Rsub, int nsub, unsigned long long *gbest,
+__global__ void sh_prune_init_kernel(unsigned *E, int64_t count, unsigned *beta, int64_t nrows, float *hdr,
+                                     unsigned *dmax, unsigned long long *gbest, unsigned *wcount,
                                      unsigned long long *scanned, int32_t *pool) {
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned ninf = enc_f32(-INFINITY);
-  for (int64_t e = x; e < count; e += (int64_t)gridDim.x * blockDim.x) LB[e] = ninf;
-  for (int64_t e = x; e < nsub; e += (int64_t)gridDim.x * blockDim.x) Rsub[e] = ninf;
+  for (int64_t e = x; e < count; e += (int64_t)gridDim.x * blockDim.x) E[e] = ninf;
+  for (int64_t e = x; e < nrows; e += (int64_t)gridDim.x * blockDim.x) beta[e] = ninf;
   if (x < 2 * POOL) pool[x] = -1;
-  if (x == 0) { *gbest = enc_f64(INFINITY); *scanned = 0ull; }
+  if (x == 0) {
+    hdr[0] = 0.f;
+    *dmax = enc_f32(0.f);
+    *gbest = enc_f64(INFINITY);
+    *wcount = 0u;
+    *scanned = 0ull;
+  }
 }
 
 __global__ void sh_last2_kernel(const int32_t *ids, int32_t *last2) {
@@ -661,8 +692,9 @@ struct ShWorkspace {
   char *gath;  // max(G*3*chunk*esz, G*chunk*8) bytes
   size_t gath_bytes;
   // pruned scan
-  unsigned *LB; unsigned *Rsub; float *uf; unsigned long long *gbest; unsigned long long *scanned;
-  unsigned long long *cta_read; int32_t *pool; int64_t lb_stride;
+  unsigned *E; unsigned *beta; float *uf; float *hdr; unsigned *dmax; unsigned long long *gbest;
+  unsigned long long *scanned; unsigned long long *cta_read; int32_t *pool; int32_t *worklist; unsigned *wcount;
+  int32_t *sugg; int64_t lb_stride;
   size_t bytes;
 };
 
@@ -684,13 +716,18 @@ static ShWorkspace sh_carve(void *base, int64_t n, int G, size_t esz) {
   w.gath_bytes = per * G;
   w.gath = c.take<char>(w.gath_bytes);
   w.lb_stride = ((n + SW - 1) / SW + 31) / 32 * 32;
-  w.LB = c.take<unsigned>((size_t)w.lb_stride * chunk);
-  w.Rsub = c.take<unsigned>((size_t)w.lb_stride + 32);
+  w.E = c.take<unsigned>((size_t)w.lb_stride * chunk);
+  w.beta = c.take<unsigned>(chunk + 32);
   w.uf = c.take<float>((size_t)n + 32);
+  w.hdr = c.take<float>(8);
+  w.dmax = c.take<unsigned>(4);
+  w.wcount = w.dmax + 1;
   w.gbest = c.take<unsigned long long>(2);
   w.scanned = w.gbest + 1;
   w.cta_read = c.take<unsigned long long>(MAX_SCAN_CTAS);
   w.pool = c.take<int32_t>(2 * POOL);
+  w.worklist = c.take<int32_t>(chunk + 32);
+  w.sugg = c.take<int32_t>(2 * MAX_SCAN_CTAS);
   w.bytes = c.used();
   return w;
 }
@@ -726,8 +763,9 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
                                                                     rk.w.counters, rk.w.rmax_bits);
     CAS_LAUNCH_CHECK();
     if (prune) {
-      sh_prune_init_kernel<<<sms * 4, 256, 0, stream>>>(rk.w.LB, rk.w.lb_stride * sh_chunk((int)n, G), rk.w.Rsub,
-                                                        (int)rk.w.lb_stride, rk.w.gbest, rk.w.scanned, rk.w.pool);
+      sh_prune_init_kernel<<<sms * 4, 256, 0, stream>>>(rk.w.E, rk.w.lb_stride * sh_chunk((int)n, G), rk.w.beta,
+                                                        sh_chunk((int)n, G), rk.w.hdr, rk.w.dmax, rk.w.gbest,
+                                                        rk.w.wcount, rk.w.scanned, rk.w.pool);
       CAS_LAUNCH_CHECK();
     }
   }
@@ -749,8 +787,8 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     for (auto &rk : ranks) {
       const double *buf = reinterpret_cast<const double *>(emu ? gath : rk.w.gath);
       sh_rscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
-          buf, chunk, (int)n, G, rk.r, rk.w.R, rk.w.rmax_bits, peers, tag0 + 1, prune ? rk.w.Rsub : nullptr,
-          rk.w.uf, 1.0 / (double)(n - 2));
+          buf, chunk, (int)n, G, rk.r, rk.w.R, rk.w.rmax_bits, peers, tag0 + 1, prune ? rk.w.uf : nullptr,
+          1.0 / (double)(n - 2));
       CAS_LAUNCH_CHECK();
     }
   }
@@ -783,12 +821,14 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       if (grid < 1) grid = 1;
       if (prune) {
         PruneArgs pa;
-        pa.LB = rk.w.LB; pa.stride = rk.w.lb_stride; pa.Rsub = rk.w.Rsub; pa.uf = rk.w.uf; pa.gbest = rk.w.gbest;
-        pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;
-        grid = (nloc + SCAN_WARPS - 1) / SCAN_WARPS;
-        if (grid > sms * 3) grid = sms * 3;
+        pa.E = rk.w.E; pa.stride = rk.w.lb_stride; pa.beta = rk.w.beta; pa.uf = rk.w.uf; pa.hdr = rk.w.hdr;
+        pa.dmax = rk.w.dmax; pa.gbest = rk.w.gbest; pa.worklist = rk.w.worklist; pa.wcount = rk.w.wcount;
+        pa.sugg = rk.w.sugg; pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;
+        sh_rowtest_kernel<T, NJ><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(
+            pa, (const T *)rk.D, ld, k, G, rk.r, rk.w.R, sa.tinv, rk.w.sel, t > 0 ? 1 : 0);
+        CAS_LAUNCH_CHECK();
+        grid = sms * 3;
         if (grid > POOL) grid = POOL;
-        if (grid < 1) grid = 1;
         sh_scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
       } else {
         sh_scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
@@ -810,7 +850,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ca.ids = rk.w.ids; ca.sizes = NJ ? nullptr : rk.w.sizes; ca.sel = rk.w.sel;
       ca.joins = joins; ca.t = (int)t;
       ca.peers = peers; ca.tag = tag; ca.counter = rk.w.counters + 2;
-      ca.LB = prune ? rk.w.LB : nullptr; ca.lb_stride = rk.w.lb_stride; ca.Rsub = rk.w.Rsub; ca.gbest = rk.w.gbest;
+      ca.E = prune ? rk.w.E : nullptr; ca.e_stride = rk.w.lb_stride; ca.beta = rk.w.beta;
       const int nloc = sh_count(k, rk.r, G);
       sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
       CAS_LAUNCH_CHECK();
@@ -830,9 +870,10 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.partial = rk.w.partial; ma.counter = rk.w.counters + 1; ma.rmax_bits = rk.w.rmax_bits;
       ma.new_id = (int)(n + t); ma.maintain_R = NJ ? 1 : 0;
       ma.peers = peers; ma.tag = tag;
-      ma.LB = prune ? rk.w.LB : nullptr; ma.lb_stride = rk.w.lb_stride; ma.Rsub = rk.w.Rsub; ma.uf = rk.w.uf;
+      ma.prune = prune ? 1 : 0; ma.uf = rk.w.uf; ma.dmax = rk.w.dmax;
       ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
-      ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.gbest = rk.w.gbest; ma.pool = rk.w.pool;
+      ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.sugg = rk.w.sugg; ma.gbest = rk.w.gbest;
+      ma.pool = rk.w.pool;
       sh_merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
       CAS_LAUNCH_CHECK();
     }
