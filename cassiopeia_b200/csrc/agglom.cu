@@ -745,8 +745,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
       prune_rowtest_kernel<T, NJ><<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(pa, (const T *)D, ld, k, w.R,
                                                                                   sa.tinv, w.sel, t > 0 ? 1 : 0);
       CAS_LAUNCH_CHECK();
-      grid = sms * 3;  // three resident CTAs per SM (register budget of the unit loop)
-      if (grid > POOL) grid = POOL;
+      grid = sms * 2;  // few units per iteration in steady state: a small grid keeps the launch + tail short
       scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
     } else {
       scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);

@@ -24,8 +24,9 @@
 namespace cas {
 
 constexpr int SW = 128;        // columns per bound (sub-segment)
-constexpr int PRUNE_CH = 2;    // chunks of 32 sub-segments per work unit
-constexpr int PRUNE_UNIT = PRUNE_CH * 32;  // sub-segments per work unit (8192 columns): one warp, one round
+constexpr int PRUNE_UNIT = 8;  // sub-segments per work unit (1024 columns): one warp, one bound test (lanes
+                               // 0..7), at most one group of eight 128-bit loads per lane -- the critical
+                               // path of an iteration is one unit, so units are kept short
 constexpr int POOL = 512;      // pairs kept to warm-start gbest (>= CTAs of the pruned scan)
 
 struct PruneArgs {
@@ -193,49 +194,35 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
   constexpr int V = VecOf<T>::N;
   constexpr int LOADS = SW / (32 * V);  // 128-bit loads per lane and sub-segment (1 float, 2 double)
   constexpr int G = 8 / LOADS;          // sub-segments in flight
-  constexpr int CH = PRUNE_CH;
   const int nsub = (i + SW - 1) / SW;   // sub-segments holding a column < i; the last one ends at the diagonal
   // ---- decide: lane l looks at sub-segments sb + 32 c + l (coalesced 128-byte loads of the bounds)
   const double gb = dec_f64(__ldcg(p.gbest));
   pw.gb_seen = gb;
   rs.set_cap(gb);
-  unsigned flags = 0;
-  unsigned kept = enc_f32(INFINITY);  // lane: smallest bound it looked at and skipped
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int sgm = sb + c * 32 + lane;
-    if (sb + c * 32 >= nsub) break;  // warp-uniform
-    const bool exists = sgm < nsub;
+  unsigned kept = enc_f32(INFINITY);  // lane: the bound it looked at, if it skipped the sub-segment
+  bool need = false;
+  {
+    const int sgm = sb + lane;
+    const bool exists = lane < PRUNE_UNIT && sgm < nsub;
     const unsigned e = exists ? erow[sgm] : enc_f32(INFINITY);
     const bool skip = prune_impossible<T, NJ>(dec_f32(e), cnow, rs.uif, gb);
-    flags |= ((exists && !skip) ? 1u : 0u) << c;
-    if (exists && skip) kept = min(kept, e);
+    need = exists && !skip;
+    if (exists && skip) kept = e;
   }
   // the diagonal sub-segment needs per-column guards: it is handled apart from the interior ones
+  unsigned flags = __ballot_sync(0xffffffffu, need);
   bool diag_needed = false;
   {
     const int dsub = nsub - 1 - sb;
-    if (dsub >= 0 && dsub < CH * 32) {
-      const unsigned bit = (lane == (dsub & 31)) ? (1u << (dsub >> 5)) : 0u;
-      diag_needed = __any_sync(0xffffffffu, (flags & bit) != 0u);
-      flags &= ~bit;
+    if (dsub >= 0 && dsub < PRUNE_UNIT) {
+      diag_needed = (flags >> dsub) & 1u;
+      flags &= ~(1u << dsub);
     }
   }
-  // ---- compact the needed interior sub-segments into the warp's list
-  const int cnt = __popc(flags);
-  int total = 0;
-  if (__any_sync(0xffffffffu, cnt != 0)) {
-    int pre = cnt;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, pre, off);
-      if (lane >= off) pre += o;
-    }
-    total = __shfl_sync(0xffffffffu, pre, 31);
-    int wpos = pre - cnt;
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-      if ((flags >> c) & 1u) list[wpos++] = (unsigned short)(c * 32 + lane);
+  // ---- the needed interior sub-segments, in lane order
+  const int total = __popc(flags);
+  if (total > 0) {
+    if (need && ((flags >> lane) & 1u)) list[__popc(flags & ((1u << lane) - 1u))] = (unsigned short)lane;
     __syncwarp();
   }
   unsigned fresh = enc_f32(INFINITY);  // warp: smallest refreshed bound

@@ -827,8 +827,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
         sh_rowtest_kernel<T, NJ><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(
             pa, (const T *)rk.D, ld, k, G, rk.r, rk.w.R, sa.tinv, rk.w.sel, t > 0 ? 1 : 0);
         CAS_LAUNCH_CHECK();
-        grid = sms * 3;
-        if (grid > POOL) grid = POOL;
+        grid = sms * 2;
         sh_scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
       } else {
         sh_scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
