@@ -668,6 +668,12 @@ static inline void plan_scan(int k, int target_ctas, int &tr, int &nrb, int &ncb
   }
 }
 
+// live size below which the loop switches (one way) to the dense scan; CAS_PRUNE_MIN_K overrides (tests use 0)
+int prune_min_k() {
+  const char *e = getenv("CAS_PRUNE_MIN_K");
+  return e ? atoi(e) : 3072;
+}
+
 template <typename T, bool NJ>
 static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iters, int32_t *joins,
                       int32_t *last2, void *workspace, cudaStream_t stream) {
@@ -688,6 +694,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
   }
   // the opt-in persistent experiment (CAS_PERSISTENT=1) keeps its dense scan
   const bool prune = !strict_nj && prune_enabled(NJ) && n > 2 && !persistent_enabled();
+  const int min_k = prune_min_k();
   if (prune) {
     prune_init_kernel<<<sms * 4, 256, 0, stream>>>(w.E, w.lb_stride * n, w.beta, n, w.hdr, w.dmax, w.gbest, w.wcount,
                                                    w.scanned, w.pool);
@@ -737,7 +744,10 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
     if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
     if (grid < 1) grid = 1;
-    if (prune) {
+    // below ~3k live nodes the map is L2-resident and the dense scan's two launches per iteration
+    // beat the pruned scan's three; the switch is one-way, so the bounds need no further maintenance
+    const bool prune_it = prune && k > min_k;
+    if (prune_it) {
       PruneArgs pa;
       pa.E = w.E; pa.stride = w.lb_stride; pa.beta = w.beta; pa.uf = w.uf; pa.hdr = w.hdr; pa.dmax = w.dmax;
       pa.gbest = w.gbest; pa.worklist = w.worklist; pa.wcount = w.wcount; pa.sugg = w.sugg;
@@ -760,7 +770,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.pos_old = strict_nj ? w.pos[cur] : nullptr;
     ma.order_new = strict_nj ? w.order[cur ^ 1] : nullptr;
     ma.pos_new = strict_nj ? w.pos[cur ^ 1] : nullptr;
-    ma.prune = prune ? 1 : 0; ma.uf = w.uf; ma.dmax = w.dmax;
+    ma.prune = prune_it ? 1 : 0; ma.uf = w.uf; ma.dmax = w.dmax;
     ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
     ma.cand = w.cand; ma.ncand = grid; ma.sugg = w.sugg; ma.gbest = w.gbest; ma.pool = w.pool;
     merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);

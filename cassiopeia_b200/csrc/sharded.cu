@@ -32,6 +32,7 @@
 namespace cas {
 
 bool prune_enabled(bool nj);  // agglom.cu
+int prune_min_k();             // agglom.cu
 
 constexpr int SHB = 64;  // rows per ownership block
 
@@ -757,7 +758,8 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
   const unsigned long long tag0 = epoch << 32;
   Cand *cand_all = ranks[0].w.cand_all;
   char *gath = ranks[0].w.gath;
-  const bool prune = prune_enabled(NJ) && n > 2;  // exact pruned scan (agglom_pruned.cuh; policy in agglom.cu)
+  const bool prune = prune_enabled(NJ) && n > 2;
+  const int min_k = prune_min_k();  // exact pruned scan (agglom_pruned.cuh; policy in agglom.cu)
   for (auto &rk : ranks) {
     sh_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)n, rk.w.ids, rk.w.sizes,
                                                                     rk.w.counters, rk.w.rmax_bits);
@@ -799,6 +801,8 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     const int chunk = sh_chunk(k, G);
     const int ncb = (k + TC - 1) / TC;
     const unsigned long long tag = tag0 + 2 + (unsigned long long)t;
+    // one-way switch to the dense scan once a rank's share of the map is small (cf. PRUNE_MIN_K in agglom.cu)
+    const bool prune_it = prune && (double)k * (double)k > (double)min_k * (double)min_k * (double)G;
     // --- scan
     for (auto &rk : ranks) {
       ShScanArgs sa;
@@ -819,7 +823,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
       if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
       if (grid < 1) grid = 1;
-      if (prune) {
+      if (prune_it) {
         PruneArgs pa;
         pa.E = rk.w.E; pa.stride = rk.w.lb_stride; pa.beta = rk.w.beta; pa.uf = rk.w.uf; pa.hdr = rk.w.hdr;
         pa.dmax = rk.w.dmax; pa.gbest = rk.w.gbest; pa.worklist = rk.w.worklist; pa.wcount = rk.w.wcount;
@@ -849,7 +853,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ca.ids = rk.w.ids; ca.sizes = NJ ? nullptr : rk.w.sizes; ca.sel = rk.w.sel;
       ca.joins = joins; ca.t = (int)t;
       ca.peers = peers; ca.tag = tag; ca.counter = rk.w.counters + 2;
-      ca.E = prune ? rk.w.E : nullptr; ca.e_stride = rk.w.lb_stride; ca.beta = rk.w.beta;
+      ca.E = prune_it ? rk.w.E : nullptr; ca.e_stride = rk.w.lb_stride; ca.beta = rk.w.beta;
       const int nloc = sh_count(k, rk.r, G);
       sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
       CAS_LAUNCH_CHECK();
@@ -869,7 +873,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.partial = rk.w.partial; ma.counter = rk.w.counters + 1; ma.rmax_bits = rk.w.rmax_bits;
       ma.new_id = (int)(n + t); ma.maintain_R = NJ ? 1 : 0;
       ma.peers = peers; ma.tag = tag;
-      ma.prune = prune ? 1 : 0; ma.uf = rk.w.uf; ma.dmax = rk.w.dmax;
+      ma.prune = prune_it ? 1 : 0; ma.uf = rk.w.uf; ma.dmax = rk.w.dmax;
       ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
       ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.sugg = rk.w.sugg; ma.gbest = rk.w.gbest;
       ma.pool = rk.w.pool;

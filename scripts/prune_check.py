@@ -17,6 +17,8 @@ def build_map(n, m, S, dtype, rate, miss, weighted=True, seed=3):
 
 def run(D, n, algo, mode, prune):
     os.environ["CAS_PRUNE"] = "1" if prune else "0"
+    if os.environ.get("PRUNE_CHECK_DEFAULT_MIN_K") is None:
+        os.environ["CAS_PRUNE_MIN_K"] = "0"
     Dc = D.clone()
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

@@ -24,6 +24,7 @@ def _run(D, n, algo, mode, prune, monkeypatch):
     from cassiopeia_b200 import engine
 
     monkeypatch.setenv("CAS_PRUNE", "1" if prune else "0")
+    monkeypatch.setenv("CAS_PRUNE_MIN_K", "0")  # keep the pruned scan down to the last iteration
     joins, last2 = engine.agglomerate(D.clone(), n, algo, mode)
     return joins, last2, dict(engine.last_stats)
 
@@ -46,6 +47,19 @@ def test_pruned_equals_dense(n, m, S, rate, miss, algo, mode, dtype, weighted, m
         # float64 UPGMA has no reductions: the GPU loop is the reference's arithmetic
         oj, ol = po.upgma(D[:, :nn].cpu().numpy())
         assert np.array_equal(jp, oj)
+
+
+def test_default_policy_switches_to_dense_at_small_sizes(monkeypatch):
+    """Default: NJ prunes above 3072 live nodes and finishes with the dense scan; same joins either way."""
+    from cassiopeia_b200 import engine
+
+    D, nn = _map(9000, 30, 10, "f32", 0.4, 0.2, True, seed=4)
+    monkeypatch.delenv("CAS_PRUNE", raising=False)
+    monkeypatch.delenv("CAS_PRUNE_MIN_K", raising=False)
+    j_default, l_default = engine.agglomerate(D.clone(), nn, "nj", "fast")
+    assert engine.last_stats["scanned_elements"] > 0
+    jd, ld, sd = _run(D, nn, "nj", "fast", False, monkeypatch)
+    assert np.array_equal(j_default, jd) and np.array_equal(l_default, ld)
 
 
 def test_pruned_scan_reads_less_at_size(monkeypatch):

@@ -9,6 +9,21 @@ from conftest import Golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["pruned", "pruned-upgma-too", "dense"], autouse=True)
+def scan_policy(request, monkeypatch):
+    """Every sharded test runs with the pruned scan kept down to the last iteration (the default policy
+    switches to the dense scan below 3072 live nodes, which these fixtures never exceed), with pruning forced
+    for UPGMA as well, and with the dense scan."""
+    monkeypatch.setenv("CAS_PRUNE_MIN_K", "0")
+    if request.param == "dense":
+        monkeypatch.setenv("CAS_PRUNE", "0")
+    elif request.param == "pruned-upgma-too":
+        monkeypatch.setenv("CAS_PRUNE", "1")
+    else:
+        monkeypatch.delenv("CAS_PRUNE", raising=False)
+    return request.param
+
+
 def _inputs(g):
     w = g.weights
     if w is not None:
