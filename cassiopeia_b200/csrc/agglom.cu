@@ -339,13 +339,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       contrib = (double)nvs;
       double Rv = 0.0;
       if (a.maintain_R) Rv = __dadd_rn(__dsub_rn(__dsub_rn(a.R[v], da), db), contrib);
-      T moved = (T)0;
       if (hi != last && v != last) {
         // the node in the last live slot moves into slot hi
         const T l = D[(int64_t)last * ld + v];
         D[(int64_t)hi * ld + v] = l;
         D[(int64_t)v * ld + hi] = l;
-        moved = l;
       }
       D[(int64_t)lo * ld + v] = nvs;
       D[(int64_t)v * ld + lo] = nvs;
