@@ -263,44 +263,12 @@ struct MergeArgs {
   const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool;
 };
 
-// Pruned scan: upper bound of the next iteration's minimum = the smallest criterion value, under the NEW
-// row sums, of a persistent pool of good pairs: entry x keeps the better of its previous pair and the
-// winner CTA x found in the scan that just ended (pairs touching the joined slots are dropped, the moved
-// slot is renamed).  Called by every thread of the merge's last CTA; all other CTAs' writes are fenced.
 template <typename T, bool NJ>
 __device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int hi, int last) {
   const T *D = static_cast<const T *>(a.D);
-  // value of the pair (x, y), given in pre-merge slots, in the post-merge state; +inf if it no longer exists
-  auto eval = [&](int x, int y, int &si, int &sj) -> double {
-    si = -1; sj = -1;
-    if (x < 0 || y < 0 || x == lo || y == lo || x == hi || y == hi) return INFINITY;
-    if (x == last) x = hi;  // the node of the last slot moved into slot hi (hi != last here)
-    if (y == last) y = hi;
-    if (x >= last || y >= last) return INFINITY;
-    si = max(x, y); sj = min(x, y);
-    double q = (double)__ldcg(D + (int64_t)si * a.ld + sj);
-    if (NJ) q = __dsub_rn(q, __dmul_rn(a.tinv_next, __dadd_rn(__ldcg(a.R + si), __ldcg(a.R + sj))));
-    return q;
-  };
-  double best = INFINITY;
-  for (int x = threadIdx.x; x < POOL; x += MERGE_THREADS) {
-    // entry x of the persistent pool: the better of its old pair and CTA x's winner of the last scan
-    int pi, pj, ci = -1, cj = -1;
-    const double qp = eval(a.pool[2 * x], a.pool[2 * x + 1], pi, pj);
-    double qc = INFINITY;
-    if (x < a.ncand) {
-      qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
-      int ui2, uj2;
-      const double qs = eval(__ldcg(a.sugg + 2 * x), __ldcg(a.sugg + 2 * x + 1), ui2, uj2);
-      if (qs < qc) { qc = qs; ci = ui2; cj = uj2; }
-    }
-    if (qc < qp) { a.pool[2 * x] = ci; a.pool[2 * x + 1] = cj; }
-    else { a.pool[2 * x] = pi; a.pool[2 * x + 1] = pj; }
-    best = fmin(best, fmin(qp, qc));
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
-  if ((threadIdx.x & 31) == 0 && best < INFINITY) atomicMin(a.gbest, enc_f64(best));
+  const int64_t ld = a.ld;
+  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last,
+                                         [=](int si, int sj) { return D + (int64_t)si * ld + sj; });
 }
 
 template <typename T, bool NJ>

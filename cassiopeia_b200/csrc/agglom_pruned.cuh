@@ -328,6 +328,74 @@ __device__ __forceinline__ void prune_publish_suggestion(const RowScan<T, NJ> &r
   }
 }
 
+// Warm start of gbest for the next iteration (called by every thread of the merge's last CTA, after all
+// other CTAs' writes are fenced): entry x of the persistent pool keeps the best of its old pair, CTA x's exact
+// winner and CTA x's float32 suggestion of the scan that just ended, all re-evaluated exactly under the NEW
+// row sums; pairs touching the joined slots are dropped, the moved slot is renamed.  The smallest value is
+// an upper bound of the next minimum.  `addr(si, sj)` returns the address of d(si, sj) (si > sj) or null when
+// this rank cannot evaluate the pair.  The loads are issued in three independent waves (indices, values,
+// nothing dependent in between) so that the tail of the merge costs two memory round trips, not a dozen.
+template <typename T, bool NJ, int NTHREADS, typename Addr>
+__device__ __forceinline__ void prune_warm_start(int32_t *pool, const Cand *cand, int ncand, const int32_t *sugg,
+                                                 unsigned long long *gbest, const double *R, double tinv_next,
+                                                 int lo, int hi, int last, Addr addr) {
+  constexpr int EPT = (POOL + NTHREADS - 1) / NTHREADS;
+  int px[EPT][3], py[EPT][3];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int x = threadIdx.x + e * NTHREADS;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { px[e][c] = -1; py[e][c] = -1; }
+    if (x < POOL) {
+      px[e][0] = pool[2 * x]; py[e][0] = pool[2 * x + 1];
+      if (x < ncand) {
+        px[e][1] = __ldcg(&cand[x].si); py[e][1] = __ldcg(&cand[x].sj);
+        px[e][2] = __ldcg(sugg + 2 * x); py[e][2] = __ldcg(sugg + 2 * x + 1);
+      }
+    }
+  }
+  const T *pd[EPT][3];
+  double dv[EPT][3], ri[EPT][3], rj[EPT][3];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int x = px[e][c], y = py[e][c];
+      pd[e][c] = nullptr;
+      dv[e][c] = INFINITY; ri[e][c] = 0.0; rj[e][c] = 0.0;
+      if (x < 0 || y < 0 || x == lo || y == lo || x == hi || y == hi) continue;
+      if (x == last) x = hi;  // the node of the last slot moved into slot hi (hi != last here)
+      if (y == last) y = hi;
+      if (x >= last || y >= last) continue;
+      px[e][c] = max(x, y); py[e][c] = min(x, y);
+      pd[e][c] = addr(px[e][c], py[e][c]);
+      if (pd[e][c]) {
+        dv[e][c] = (double)__ldcg(pd[e][c]);
+        if (NJ) { ri[e][c] = __ldcg(R + px[e][c]); rj[e][c] = __ldcg(R + py[e][c]); }
+      }
+    }
+  }
+  double best = INFINITY;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int x = threadIdx.x + e * NTHREADS;
+    double qb = INFINITY;
+    int bi = -1, bj = -1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (!pd[e][c]) continue;
+      double q = dv[e][c];
+      if (NJ) q = __dsub_rn(q, __dmul_rn(tinv_next, __dadd_rn(ri[e][c], rj[e][c])));
+      if (q < qb) { qb = q; bi = px[e][c]; bj = py[e][c]; }
+    }
+    if (x < POOL) { pool[2 * x] = bi; pool[2 * x + 1] = bj; }
+    best = fmin(best, qb);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if ((threadIdx.x & 31) == 0 && best < INFINITY) atomicMin(gbest, enc_f64(best));
+}
+
 // After every CTA of a scan has finished: commit the drift (C := C as of this scan, dmax := 0).  One thread.
 __device__ __forceinline__ void prune_commit(const PruneArgs &p) {
   p.hdr[0] = prune_cnow(p);

@@ -381,42 +381,18 @@ struct ShMergeArgs {
   const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool;
 };
 
-// Per-rank warm start of the pruned scan's bound (cf. warm_start_gbest in agglom.cu): only pairs whose row
+// Per-rank warm start of the pruned scan's bound (prune_warm_start, agglom_pruned.cuh): only pairs whose row
 // this rank owns can be evaluated here, and only those enter its pool.
 template <typename T, bool NJ>
 __device__ __forceinline__ void sh_warm_start(const ShMergeArgs &a, int lo, int hi, int last) {
   const T *D = static_cast<const T *>(a.Dloc);
-  auto eval = [&](int x, int y, int &si, int &sj) -> double {
-    si = -1; sj = -1;
-    if (x < 0 || y < 0 || x == lo || y == lo || x == hi || y == hi) return INFINITY;
-    if (x == last) x = hi;
-    if (y == last) y = hi;
-    if (x >= last || y >= last) return INFINITY;
-    const int ri = max(x, y), cj = min(x, y);
-    if (sh_owner(ri, a.G) != a.r) return INFINITY;
-    si = ri; sj = cj;
-    double q = (double)__ldcg(D + (int64_t)sh_local(ri, a.G) * a.ld + cj);
-    if (NJ) q = __dsub_rn(q, __dmul_rn(a.tinv_next, __dadd_rn(__ldcg(a.R + ri), __ldcg(a.R + cj))));
-    return q;
-  };
-  double best = INFINITY;
-  for (int x = threadIdx.x; x < POOL; x += MERGE_THREADS) {
-    int pi, pj, ci = -1, cj = -1;
-    const double qp = eval(a.pool[2 * x], a.pool[2 * x + 1], pi, pj);
-    double qc = INFINITY;
-    if (x < a.ncand) {
-      qc = eval(__ldcg(&a.cand[x].si), __ldcg(&a.cand[x].sj), ci, cj);
-      int ui2, uj2;
-      const double qs = eval(__ldcg(a.sugg + 2 * x), __ldcg(a.sugg + 2 * x + 1), ui2, uj2);
-      if (qs < qc) { qc = qs; ci = ui2; cj = uj2; }
-    }
-    if (qc < qp) { a.pool[2 * x] = ci; a.pool[2 * x + 1] = cj; }
-    else { a.pool[2 * x] = pi; a.pool[2 * x + 1] = pj; }
-    best = fmin(best, fmin(qp, qc));
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
-  if ((threadIdx.x & 31) == 0 && best < INFINITY) atomicMin(a.gbest, enc_f64(best));
+  const int64_t ld = a.ld;
+  const int G = a.G, r = a.r;
+  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last,
+                                         [=](int si, int sj) -> const T * {
+                                           if (sh_owner(si, G) != r) return nullptr;
+                                           return D + (int64_t)sh_local(si, G) * ld + sj;
+                                         });
 }
 
 template <typename T, bool NJ>
