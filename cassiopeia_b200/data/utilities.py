@@ -67,7 +67,7 @@ def dissimilarity_map_frame_inputs(character_matrix, priors, missing_state_indic
         weights = solver_utilities.transform_priors(priors, prior_transformation)
     cm = host_prep.as_int_matrix(character_matrix)
     order = host_prep.reference_row_order(cm)
-    names = [character_matrix.index[i] for i in order.tolist()]
+    names = np.asarray(character_matrix.index, dtype=object)[order].tolist()  # one gather, not n __getitem__ calls
     D = device_map(cm[order], missing_state_indicator, weights, dtype=dtype, method=method, function=function)
     if to_host:
         n = cm.shape[0]
