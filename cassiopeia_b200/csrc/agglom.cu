@@ -142,6 +142,8 @@ template <typename T, bool NJ>
 __global__ void __launch_bounds__(256) prune_rowtest_kernel(PruneArgs p, const T *__restrict__ D, int64_t ld, int k,
                                                             const double *__restrict__ R, double tinv,
                                                             const Sel *prev, int has_prev) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i >= 1 && i < k;
   int plo = -1, phi = -1;
@@ -156,6 +158,8 @@ __global__ void __launch_bounds__(256) prune_rowtest_kernel(PruneArgs p, const T
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a, PruneArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
   __shared__ unsigned long long sRead[SCAN_WARPS];
@@ -273,6 +277,8 @@ __device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (the pruned loop)
+  pdl_launch_dependents();
   __shared__ double sPart[MERGE_THREADS / 32];
   __shared__ bool sLast;
   T *__restrict__ D = static_cast<T *>(a.D);
@@ -718,11 +724,11 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
       pa.E = w.E; pa.stride = w.lb_stride; pa.beta = w.beta; pa.uf = w.uf; pa.hdr = w.hdr; pa.dmax = w.dmax;
       pa.gbest = w.gbest; pa.worklist = w.worklist; pa.wcount = w.wcount; pa.sugg = w.sugg;
       pa.scanned = w.scanned; pa.cta_read = w.cta_read;
-      prune_rowtest_kernel<T, NJ><<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(pa, (const T *)D, ld, k, w.R,
-                                                                                  sa.tinv, w.sel, t > 0 ? 1 : 0);
+      CAS_CUDA_TRY(launch_pdl(prune_rowtest_kernel<T, NJ>, (unsigned)((k + 255) / 256), 256u, stream, pa,
+                              (const T *)D, ld, k, (const double *)w.R, sa.tinv, (const Sel *)w.sel, t > 0 ? 1 : 0));
       CAS_LAUNCH_CHECK();
       grid = sms * 2;  // few units per iteration in steady state: a small grid keeps the launch + tail short
-      scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
+      CAS_CUDA_TRY(launch_pdl(scan_pruned_kernel<T, NJ>, (unsigned)grid, (unsigned)SCAN_THREADS, stream, sa, pa));
     } else {
       scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
     }
@@ -739,7 +745,12 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.prune = prune_it ? 1 : 0; ma.uf = w.uf; ma.dmax = w.dmax;
     ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
     ma.cand = w.cand; ma.ncand = grid; ma.sugg = w.sugg; ma.gbest = w.gbest; ma.pool = w.pool;
-    merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
+    if (prune_it) {
+      CAS_CUDA_TRY(launch_pdl(merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
+                              (unsigned)MERGE_THREADS, stream, ma));
+    } else {
+      merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
+    }
     CAS_LAUNCH_CHECK();
   }
   last2_kernel<<<1, 32, 0, stream>>>(w.ids, (int)(k_final < 2 ? k_final : 2), last2, (const int *)(w.counters + 6));

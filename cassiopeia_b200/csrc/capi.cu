@@ -20,6 +20,11 @@ void set_error(const char *fmt, ...) {
 void count_launch(int64_t n) { g_launches += n; }
 void reset_launch_count() { g_launches = 0; }
 
+bool pdl_enabled() {
+  const char *e = getenv("CAS_PDL");
+  return !(e && e[0] == '0');
+}
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/cas_b200.h"
 
@@ -61,5 +62,33 @@ struct Carver {
 };
 
 int sm_count();
+
+
+// Programmatic dependent launch (sm_90+): the kernel may be scheduled while its predecessor in the stream is
+// still draining; it must execute pdl_wait() before touching anything the predecessor wrote, and both call
+// pdl_launch_dependents() early so that the NEXT kernel's launch latency overlaps their execution.  Used by the
+// three small kernels of a pruned NJ iteration, whose back-to-back launch latencies are a visible part of the
+// ~45 us iteration.  CAS_PDL=0 falls back to ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 }  // namespace cas

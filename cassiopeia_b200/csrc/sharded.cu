@@ -181,6 +181,8 @@ template <typename T, bool NJ>
 __global__ void __launch_bounds__(256) sh_rowtest_kernel(PruneArgs p, const T *__restrict__ Dloc, int64_t ld, int k,
                                                          int G, int r, const double *__restrict__ R, double tinv,
                                                          const Sel *prev, int has_prev) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lr = blockIdx.x * blockDim.x + threadIdx.x;
   const int nloc = sh_count(k, r, G);
   const int i = lr < nloc ? sh_slot(lr, r, G) : 0;
@@ -197,6 +199,8 @@ __global__ void __launch_bounds__(256) sh_rowtest_kernel(PruneArgs p, const T *_
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanArgs a, PruneArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
   __shared__ unsigned long long sRead[SCAN_WARPS];
@@ -288,6 +292,8 @@ struct ShColsArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
+  pdl_wait();  // no-ops unless launched with programmatic stream serialization (the pruned loop)
+  pdl_launch_dependents();
   __shared__ Cand sCand[8];
   __shared__ bool sLast;
   const bool p2p = a.peers.ex[0] != nullptr;
@@ -397,6 +403,8 @@ __device__ __forceinline__ void sh_warm_start(const ShMergeArgs &a, int lo, int 
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ double sPart[MERGE_THREADS / 32];
   __shared__ bool sLast;
   T *__restrict__ D = static_cast<T *>(a.Dloc);
@@ -804,11 +812,12 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
         pa.E = rk.w.E; pa.stride = rk.w.lb_stride; pa.beta = rk.w.beta; pa.uf = rk.w.uf; pa.hdr = rk.w.hdr;
         pa.dmax = rk.w.dmax; pa.gbest = rk.w.gbest; pa.worklist = rk.w.worklist; pa.wcount = rk.w.wcount;
         pa.sugg = rk.w.sugg; pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;
-        sh_rowtest_kernel<T, NJ><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(
-            pa, (const T *)rk.D, ld, k, G, rk.r, rk.w.R, sa.tinv, rk.w.sel, t > 0 ? 1 : 0);
+        CAS_CUDA_TRY(launch_pdl(sh_rowtest_kernel<T, NJ>, (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1),
+                                256u, stream, pa, (const T *)rk.D, ld, k, G, rk.r, (const double *)rk.w.R, sa.tinv,
+                                (const Sel *)rk.w.sel, t > 0 ? 1 : 0));
         CAS_LAUNCH_CHECK();
         grid = sms * 2;
-        sh_scan_pruned_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa, pa);
+        CAS_CUDA_TRY(launch_pdl(sh_scan_pruned_kernel<T, NJ>, (unsigned)grid, (unsigned)SCAN_THREADS, stream, sa, pa));
       } else {
         sh_scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
       }
@@ -831,7 +840,12 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ca.peers = peers; ca.tag = tag; ca.counter = rk.w.counters + 2;
       ca.E = prune_it ? rk.w.E : nullptr; ca.e_stride = rk.w.lb_stride; ca.beta = rk.w.beta;
       const int nloc = sh_count(k, rk.r, G);
-      sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
+      if (prune_it) {
+        CAS_CUDA_TRY(launch_pdl(sh_cols_kernel<T>, (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256u,
+                                stream, ca));
+      } else {
+        sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
+      }
       CAS_LAUNCH_CHECK();
     }
     // --- C2: rows lo, hi, last
@@ -853,7 +867,12 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
       ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.sugg = rk.w.sugg; ma.gbest = rk.w.gbest;
       ma.pool = rk.w.pool;
-      sh_merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
+      if (prune_it) {
+        CAS_CUDA_TRY(launch_pdl(sh_merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
+                                (unsigned)MERGE_THREADS, stream, ma));
+      } else {
+        sh_merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
+      }
       CAS_LAUNCH_CHECK();
     }
   }
