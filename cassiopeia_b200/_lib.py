@@ -37,6 +37,7 @@ EXPORTS = (
     "cas_update_map",
     "cas_agglom_stats",
     "cas_agglom_scanned_elements",
+    "cas_agglom_prune_diag",
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
     "cas_sharded_workspace_bytes",
@@ -95,6 +96,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_agglom_stats.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.cas_agglom_scanned_elements.restype = ctypes.c_int
     L.cas_agglom_scanned_elements.argtypes = [vp, i64, vp, ctypes.POINTER(i64)]
+    L.cas_agglom_prune_diag.restype = ctypes.c_int
+    L.cas_agglom_prune_diag.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]
     L.cas_nj_q.restype = ctypes.c_int
     L.cas_nj_q.argtypes = [vp, i64, i64, vp, vp, vp]
     L.cas_update_map.restype = ctypes.c_int

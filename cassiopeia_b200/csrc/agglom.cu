@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
     // every other CTA has finished (counter): clear the per-iteration state, commit the drift
     *p.gbest = enc_f64(INFINITY);
+    atomicAdd(a.stats + 2, (unsigned long long)*p.wcount);  // diagnostics: rows listed over the whole loop
     *p.wcount = 0u;
     prune_commit(p);
     p.beta[lo] = enc_f32(-INFINITY);
@@ -264,14 +265,14 @@ struct MergeArgs {
   // pruned scan (prune != 0): fl32(tinv_next * R) by slot and its largest increase (NJ), last scan's
   // per-CTA winners / suggestions and the persistent pool (warm start of gbest)
   int prune; float *uf; double tinv_next; unsigned *dmax;
-  const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool;
+  const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool; int rot;
 };
 
 template <typename T, bool NJ>
 __device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int hi, int last) {
   const T *D = static_cast<const T *>(a.D);
   const int64_t ld = a.ld;
-  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last,
+  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last, a.rot,
                                          [=](int si, int sj) { return D + (int64_t)si * ld + sj; });
 }
 
@@ -521,7 +522,7 @@ __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *
     if (order) { order[v] = v; pos[v] = v; }
   }
   if (v < 16) counters[v] = 0;
-  if (v == 0) { rmax_bits[0] = 0ull; rmax_bits[2] = 0ull; rmax_bits[3] = 0ull; }
+  if (v == 0) { rmax_bits[0] = 0ull; rmax_bits[2] = 0ull; rmax_bits[3] = 0ull; rmax_bits[4] = 0ull; }
 }
 
 __global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2, const int *error) {
@@ -745,6 +746,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.prune = prune_it ? 1 : 0; ma.uf = w.uf; ma.dmax = w.dmax;
     ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
     ma.cand = w.cand; ma.ncand = grid; ma.sugg = w.sugg; ma.gbest = w.gbest; ma.pool = w.pool;
+    ma.rot = (int)((t * 61) % POOL);
     if (prune_it) {
       CAS_CUDA_TRY(launch_pdl(merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
                               (unsigned)MERGE_THREADS, stream, ma));
@@ -969,6 +971,19 @@ int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, i
   CAS_CUDA_TRY(cudaMemcpyAsync(&h, w.scanned, sizeof(h), cudaMemcpyDeviceToHost, stream));
   CAS_CUDA_TRY(cudaStreamSynchronize(stream));
   if (elements) *elements = (int64_t)h;
+  return CAS_OK;
+}
+
+// pruned-scan diagnostics: rows put on the work list over the whole loop, and the final drift C
+int agglom_read_prune_diag(const void *workspace, int64_t n, cudaStream_t stream, int64_t *rows_listed, double *drift) {
+  AgglomWorkspace w = carve_workspace(const_cast<void *>(workspace), n > 0 ? n : 1);
+  unsigned long long h = 0;
+  float c = 0.f;
+  CAS_CUDA_TRY(cudaMemcpyAsync(&h, w.stats + 2, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaMemcpyAsync(&c, w.hdr, sizeof(c), cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (rows_listed) *rows_listed = (int64_t)h;
+  if (drift) *drift = (double)c;
   return CAS_OK;
 }
 

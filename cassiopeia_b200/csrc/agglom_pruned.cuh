@@ -335,10 +335,13 @@ __device__ __forceinline__ void prune_publish_suggestion(const RowScan<T, NJ> &r
 // an upper bound of the next minimum.  `addr(si, sj)` returns the address of d(si, sj) (si > sj) or null when
 // this rank cannot evaluate the pair.  The loads are issued in three independent waves (indices, values,
 // nothing dependent in between) so that the tail of the merge costs two memory round trips, not a dozen.
+// `rot` rotates which CTA feeds which entry from iteration to iteration: in steady state only the first few
+// CTAs of the scan have any work unit, and with a fixed mapping only their entries would ever be refreshed
+// while every join kills entries -- the pool would shrink to a handful of pairs and the bound would go loose.
 template <typename T, bool NJ, int NTHREADS, typename Addr>
 __device__ __forceinline__ void prune_warm_start(int32_t *pool, const Cand *cand, int ncand, const int32_t *sugg,
                                                  unsigned long long *gbest, const double *R, double tinv_next,
-                                                 int lo, int hi, int last, Addr addr) {
+                                                 int lo, int hi, int last, int rot, Addr addr) {
   constexpr int EPT = (POOL + NTHREADS - 1) / NTHREADS;
   int px[EPT][3], py[EPT][3];
 #pragma unroll
@@ -348,9 +351,10 @@ __device__ __forceinline__ void prune_warm_start(int32_t *pool, const Cand *cand
     for (int c = 0; c < 3; ++c) { px[e][c] = -1; py[e][c] = -1; }
     if (x < POOL) {
       px[e][0] = pool[2 * x]; py[e][0] = pool[2 * x + 1];
-      if (x < ncand) {
-        px[e][1] = __ldcg(&cand[x].si); py[e][1] = __ldcg(&cand[x].sj);
-        px[e][2] = __ldcg(sugg + 2 * x); py[e][2] = __ldcg(sugg + 2 * x + 1);
+      const int y = (x + rot) % POOL;  // the CTA whose winner / suggestion competes for this entry
+      if (y < ncand) {
+        px[e][1] = __ldcg(&cand[y].si); py[e][1] = __ldcg(&cand[y].sj);
+        px[e][2] = __ldcg(sugg + 2 * y); py[e][2] = __ldcg(sugg + 2 * y + 1);
       }
     }
   }

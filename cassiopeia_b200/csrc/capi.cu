@@ -60,6 +60,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
               int32_t fn, double *D, int64_t ld, int64_t max_iters, int32_t *joins, int32_t *last2,
               void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements);
+int agglom_read_prune_diag(const void *workspace, int64_t n, cudaStream_t stream, int64_t *rows_listed, double *drift);
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
                  size_t workspace_bytes, cudaStream_t stream);
@@ -171,6 +172,11 @@ int cas_smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
 int cas_agglom_scanned_elements(const void *workspace, int64_t n, void *stream, int64_t *elements) {
   CAS_REQUIRE(workspace, "null pointer argument");
   return agglom_read_scanned(workspace, n, (cudaStream_t)stream, elements);
+}
+
+int cas_agglom_prune_diag(const void *workspace, int64_t n, void *stream, int64_t *rows_listed, double *drift) {
+  CAS_REQUIRE(workspace, "null pointer argument");
+  return agglom_read_prune_diag(workspace, n, (cudaStream_t)stream, rows_listed, drift);
 }
 
 int cas_nj_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t mode, int64_t max_iters,

@@ -384,7 +384,7 @@ struct ShMergeArgs {
   unsigned long long tag;
   // pruned scan (prune != 0), see MergeArgs in agglom.cu
   int prune; float *uf; double tinv_next; unsigned *dmax;
-  const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool;
+  const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool; int rot;
 };
 
 // Per-rank warm start of the pruned scan's bound (prune_warm_start, agglom_pruned.cuh): only pairs whose row
@@ -394,7 +394,7 @@ __device__ __forceinline__ void sh_warm_start(const ShMergeArgs &a, int lo, int 
   const T *D = static_cast<const T *>(a.Dloc);
   const int64_t ld = a.ld;
   const int G = a.G, r = a.r;
-  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last,
+  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last, a.rot,
                                          [=](int si, int sj) -> const T * {
                                            if (sh_owner(si, G) != r) return nullptr;
                                            return D + (int64_t)sh_local(si, G) * ld + sj;
@@ -866,7 +866,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.prune = prune_it ? 1 : 0; ma.uf = rk.w.uf; ma.dmax = rk.w.dmax;
       ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
       ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.sugg = rk.w.sugg; ma.gbest = rk.w.gbest;
-      ma.pool = rk.w.pool;
+      ma.pool = rk.w.pool; ma.rot = (int)((t * 61) % POOL);
       if (prune_it) {
         CAS_CUDA_TRY(launch_pdl(sh_merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
                                 (unsigned)MERGE_THREADS, stream, ma));

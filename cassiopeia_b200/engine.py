@@ -50,7 +50,7 @@ def device_info() -> dict:
 
 #: diagnostics of the most recent `agglomerate` call: near / exact ties and the number of map elements the
 #: pruned scan actually read (0 for the dense scan, which reads k(k-1)/2 per iteration)
-last_stats = {"near_ties": 0, "exact_ties": 0, "scanned_elements": 0}
+last_stats = {"near_ties": 0, "exact_ties": 0, "scanned_elements": 0, "rows_listed": 0, "drift": 0.0}
 
 
 def last_launch_count() -> int:
@@ -156,6 +156,10 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     _lib.check(L.cas_agglom_scanned_elements(ws.data_ptr(), int(n), _stream_ptr(torch), ctypes.byref(scanned)),
                "cas_agglom_scanned_elements")
     last_stats["scanned_elements"] = int(scanned.value)
+    listed, drift = ctypes.c_int64(0), ctypes.c_double(0.0)
+    _lib.check(L.cas_agglom_prune_diag(ws.data_ptr(), int(n), _stream_ptr(torch), ctypes.byref(listed),
+                                       ctypes.byref(drift)), "cas_agglom_prune_diag")
+    last_stats["rows_listed"], last_stats["drift"] = int(listed.value), float(drift.value)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     joins_h = joins[:done].cpu().numpy()
     last2_h = last2.cpu().numpy()

@@ -229,6 +229,11 @@ CAS_API int cas_agglom_stats(const void *workspace_dev, int64_t n, void *stream,
  * dense scan reads k(k-1)/2 elements per iteration and reports 0 here. */
 CAS_API int cas_agglom_scanned_elements(const void *workspace_dev, int64_t n, void *stream, int64_t *elements);
 
+/* pruned-scan diagnostics of the last single-GPU loop run with this workspace (synchronises the stream): rows put
+ * on the work list summed over all iterations, and the final cumulative drift C of the bounds */
+CAS_API int cas_agglom_prune_diag(const void *workspace_dev, int64_t n, void *stream, int64_t *rows_listed,
+                          double *drift);
+
 /* number of kernels the last cas_*_solve / cas_whd_map / cas_solve_host call on this
  * thread launched (bench.py's gpu_launches) */
 CAS_API int64_t cas_last_launch_count(void);
