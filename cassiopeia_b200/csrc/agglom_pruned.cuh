@@ -51,6 +51,15 @@ __device__ __forceinline__ float prune_cnow(const PruneArgs &p) {
   return __fadd_ru(p.hdr[0], __fmul_ru(d, 1.000001f));
 }
 
+// Bound of a sub-segment whose smallest fl32(d) - uf_j is dm, in the drifting frame, rounded down by more
+// than the float operations can have rounded up.  A lane without a valid column carries dm = +inf: its
+// inf - inf would be a NaN, and the encoding of a NaN is not ordered (the compiler builds enc_f32 from
+// abs/neg, which may canonicalise the NaN to a pattern that decodes as -0.0 and wins the warp minimum --
+// a valid but uselessly low bound that kept every row's diagonal sub-segment on the work list).
+__device__ __forceinline__ unsigned prune_bound(float dm, float cnow) {
+  return dm == INFINITY ? enc_f32(INFINITY) : enc_f32((dm + cnow) - 1e-6f * (fabsf(dm) + cnow));
+}
+
 template <typename T, bool NJ>
 struct RowScan {
   static constexpr int V = VecOf<T>::N;
@@ -254,8 +263,7 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
         }
         dm = fminf(dm, rs.template vec<false>(v[g][l], su, j, i));
       }
-      // bound in the drifting frame, rounded down by more than the float operations can have rounded up
-      const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32((dm + cnow) - 1e-6f * (fabsf(dm) + cnow)));
+      const unsigned m = __reduce_min_sync(0xffffffffu, prune_bound(dm, cnow));
       if (lane == 0) erow[sg[g]] = m;
       fresh = min(fresh, m);
     }
@@ -280,7 +288,7 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
       }
       dm = fminf(dm, rs.template vec<true>(v, su, j, i));
     }
-    const unsigned m = __reduce_min_sync(0xffffffffu, enc_f32((dm + cnow) - 1e-6f * (fabsf(dm) + cnow)));
+    const unsigned m = __reduce_min_sync(0xffffffffu, prune_bound(dm, cnow));
     if (lane == 0) erow[sgd] = m;
     fresh = min(fresh, m);
     pw.nread += (unsigned long long)(i - sgd * SW);
