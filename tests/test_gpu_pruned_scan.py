@@ -70,3 +70,22 @@ def test_pruned_scan_reads_less_at_size(monkeypatch):
     assert np.array_equal(jd, jp) and np.array_equal(ld, lp)
     dense = sum(k * (k - 1) // 2 for k in range(3, nn + 1))
     assert sp["scanned_elements"] < 0.25 * dense
+
+
+def test_work_list_stays_short_as_the_drift_grows(monkeypatch):
+    """The rows listed per iteration must not grow with the cumulative drift C: a sub-segment bound that decodes
+    as 0 (an encoded NaN from the lanes past the triangle) is valid but puts every row on the list once
+    C > gbest + u_i, i.e. for the whole second half of a solve (agglom_pruned.cuh, prune_bound)."""
+    from cassiopeia_b200 import engine
+
+    D, nn = _map(8000, 60, 100, "f32", 0.1, 0.2, True, seed=6)
+    monkeypatch.setenv("CAS_PRUNE", "1")
+    monkeypatch.setenv("CAS_PRUNE_MIN_K", "0")
+    listed = {}
+    for frac in (0.5, 0.9):
+        engine.agglomerate(D.clone(), nn, "nj", "fast", max_iters=int(frac * nn))
+        listed[frac] = engine.last_stats["rows_listed"]
+        assert engine.last_stats["drift"] > 0.0
+    late = (listed[0.9] - listed[0.5]) / (0.4 * nn)    # rows listed per iteration between 50 % and 90 %
+    live = 0.3 * nn                                    # mean live rows in that window
+    assert late < 0.1 * live, (listed, late)
