@@ -144,6 +144,14 @@ class CassiopeiaTree:
     def populate_tree(self, tree: nx.DiGraph, layer: Optional[str] = None) -> None:
         if not isinstance(tree, nx.DiGraph):
             raise CassiopeiaTreeError("Please pass a Networkx DiGraph object.")
+        if tree.graph.pop("cas_b200_prepared", False):
+            # built by tree_tail.build_final_tree: string names, `character_states` = [] and `time` on every
+            # node, `length` on every edge -- exactly what the passes below would leave behind
+            self._network = tree
+            character_matrix = self.layers[layer] if layer else self.character_matrix
+            if character_matrix is not None:
+                self.set_character_states_at_leaves(layer=layer)
+            return
         if any(not isinstance(n, str) for n in tree.nodes):
             tree = nx.relabel_nodes(tree, {n: str(n) for n in tree.nodes})
         self._network = tree
@@ -179,10 +187,11 @@ class CassiopeiaTree:
         elif isinstance(character_matrix, dict):
             character_matrix = pd.DataFrame.from_dict(character_matrix, orient="index")
         leaves = self.leaves
-        if set(leaves) != set(character_matrix.index.values):
+        index = character_matrix.index.tolist()  # (iterating a pandas string index directly is 30x slower)
+        if set(leaves) != set(index):
             raise CassiopeiaTreeError("Character matrix index does not match set of leaves.")
         rows = character_matrix.to_numpy().tolist()
-        by_name = dict(zip(character_matrix.index.tolist(), rows))
+        by_name = dict(zip(index, rows))
         node_attrs = self._network._node
         for n in leaves:
             node_attrs[n]["character_states"] = by_name[n]

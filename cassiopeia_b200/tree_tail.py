@@ -33,6 +33,11 @@ import networkx as nx
 import numpy as np
 
 
+#: graph attribute set on trees whose node attributes (`character_states`, `time`) and edge `length`s are
+#: already what `populate_tree` would compute
+PREPARED = "cas_b200_prepared"
+
+
 def _lca2(a: np.ndarray, b: np.ndarray, missing: int) -> np.ndarray:
     """Camin-Sokal LCA of two state rows (reference data/utilities.py:29-97, unambiguous states)."""
     return np.where(a == missing, b, np.where(b == missing, a, np.where(a == b, a, 0)))
@@ -243,11 +248,17 @@ def build_final_tree(names: Sequence[str], internal_names: Sequence[str], joins:
         # networkx keeps {node: attrs}, {u: {v: attrs}}, {v: {u: attrs}} with the edge attribute dict shared
         # between the successor and the predecessor map; filling them directly skips the per-call checks of
         # add_nodes_from / add_edges_from (half of this function's time at 10^5 nodes)
+        # node attributes as populate_tree leaves them (CassiopeiaTree.py:174-203): an empty state list and
+        # the time = sum of the branch lengths from the root = depth in the uncollapsed tree.  The tree
+        # object's populate_tree recomputes the same values; ours skips its per-node passes when it finds
+        # the marker below.
         for v in kept_order:
             lv = label[v]
-            node[lv] = {}
+            node[lv] = {"character_states": [], "time": dl[v]}
             succ[lv] = {}
             pred[lv] = {}
+        if all(isinstance(x, str) for x in names):
+            g.graph[PREPARED] = True
         for v in kept_order:
             c = head[v]
             if c < 0:
