@@ -56,6 +56,9 @@ EXPORTS = (
     "cas_exchange_error",
     "cas_sharded_solve_p2p",
     "cas_sharded_solve_emulated_p2p",
+    "cas_tail_preorder",
+    "cas_tail_heights",
+    "cas_tail_successor_lists",
 )
 
 
@@ -98,6 +101,12 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_agglom_scanned_elements.argtypes = [vp, i64, vp, ctypes.POINTER(i64)]
     L.cas_agglom_prune_diag.restype = ctypes.c_int
     L.cas_agglom_prune_diag.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]
+    L.cas_tail_preorder.restype = i64
+    L.cas_tail_preorder.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.cas_tail_heights.restype = ctypes.c_int
+    L.cas_tail_heights.argtypes = [vp, i64, vp, vp, vp]
+    L.cas_tail_successor_lists.restype = ctypes.c_int
+    L.cas_tail_successor_lists.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     L.cas_nj_q.restype = ctypes.c_int
     L.cas_nj_q.argtypes = [vp, i64, i64, vp, vp, vp]
     L.cas_update_map.restype = ctypes.c_int

@@ -32,6 +32,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import networkx as nx
 import numpy as np
 
+from . import _lib
+
 
 #: graph attribute set on trees whose node attributes (`character_states`, `time`) and edge `length`s are
 #: already what `populate_tree` would compute
@@ -105,30 +107,53 @@ class RootedJoinTree:
     # ------------------------------------------------------------------ orders
     def preorder(self) -> Tuple[np.ndarray, np.ndarray]:
         """Depth-first preorder (first child first) = node insertion order of the reference's rooted
-        DiGraph, and the depth of every node."""
+        DiGraph, and the depth of every node (``cas_tail_preorder``)."""
         if self._preorder is None:
-            c0, c1 = self.child0.tolist(), self.child1.tolist()
-            depth = [0] * self.M
-            order: List[int] = []
-            stack = [self.root]
-            push, pop, out = stack.append, stack.pop, order.append
-            while stack:
-                v = pop()
-                out(v)
-                x, y = c0[v], c1[v]
-                if x >= 0:
-                    d = depth[v] + 1
-                    if y >= 0:
-                        depth[y] = d
-                        push(y)
-                    depth[x] = d
-                    push(x)
-            self._preorder = np.asarray(order, dtype=np.int64)
-            self._depth = np.asarray(depth, dtype=np.int64)
+            order = np.empty(self.M, dtype=np.int64)
+            depth = np.zeros(self.M, dtype=np.int64)
+            c0, c1 = np.ascontiguousarray(self.child0), np.ascontiguousarray(self.child1)
+            L = _lib.load()
+            count = int(L.cas_tail_preorder(c0.ctypes.data, c1.ctypes.data, self.M, self.root,
+                                            order.ctypes.data, depth.ctypes.data))
+            if count < 0:
+                _lib.check(count, "cas_tail_preorder")
+            if count != self.M:
+                raise ValueError("join list does not describe one tree")
+            self._preorder, self._depth = order, depth
         return self._preorder, self._depth
 
+    def preorder_py(self) -> Tuple[np.ndarray, np.ndarray]:
+        """Interpreter version of `preorder` (tests cross-check the two)."""
+        c0, c1 = self.child0.tolist(), self.child1.tolist()
+        depth = [0] * self.M
+        order: List[int] = []
+        stack = [self.root]
+        push, pop, out = stack.append, stack.pop, order.append
+        while stack:
+            v = pop()
+            out(v)
+            x, y = c0[v], c1[v]
+            if x >= 0:
+                d = depth[v] + 1
+                if y >= 0:
+                    depth[y] = d
+                    push(y)
+                depth[x] = d
+                push(x)
+        return np.asarray(order, dtype=np.int64), np.asarray(depth, dtype=np.int64)
+
     def heights(self) -> np.ndarray:
-        """Height above the deepest leaf (leaves 0); children precede parents in reverse preorder."""
+        """Height above the deepest leaf (leaves 0); children precede parents in reverse preorder
+        (``cas_tail_heights``)."""
+        order, _ = self.preorder()
+        h = np.zeros(self.M, dtype=np.int64)
+        c0, c1 = np.ascontiguousarray(self.child0), np.ascontiguousarray(self.child1)
+        L = _lib.load()
+        _lib.check(L.cas_tail_heights(order.ctypes.data, order.shape[0], c0.ctypes.data, c1.ctypes.data,
+                                      h.ctypes.data), "cas_tail_heights")
+        return h
+
+    def heights_py(self) -> np.ndarray:
         order, _ = self.preorder()
         c0, c1 = self.child0.tolist(), self.child1.tolist()
         h = [0] * self.M
@@ -161,6 +186,57 @@ class RootedJoinTree:
             else:
                 S[idx[two]] = _lca2(S[x[two]], S[y[two]], missing)
         return S
+
+
+def successor_lists(order: np.ndarray, child0: np.ndarray, child1: np.ndarray,
+                    removed: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(head, tail, next) linked lists of every node's successors once the `removed` nodes are spliced out
+    (``cas_tail_successor_lists``)."""
+    M = child0.shape[0]
+    head = np.full(M, -1, dtype=np.int64)
+    tail = np.full(M, -1, dtype=np.int64)
+    nxt = np.full(M, -1, dtype=np.int64)
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    c0, c1 = np.ascontiguousarray(child0, dtype=np.int64), np.ascontiguousarray(child1, dtype=np.int64)
+    rem = np.ascontiguousarray(removed, dtype=np.uint8)
+    L = _lib.load()
+    _lib.check(L.cas_tail_successor_lists(order.ctypes.data, order.shape[0], c0.ctypes.data, c1.ctypes.data,
+                                          rem.ctypes.data, head.ctypes.data, tail.ctypes.data, nxt.ctypes.data),
+               "cas_tail_successor_lists")
+    return head, tail, nxt
+
+
+def successor_lists_py(order: np.ndarray, child0: np.ndarray, child1: np.ndarray,
+                       removed: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Interpreter version of `successor_lists` (tests cross-check the two)."""
+    M = child0.shape[0]
+    head = [-1] * M
+    tail = [-1] * M
+    nxt = [-1] * M
+    rem = removed.tolist()
+    c0l, c1l = child0.tolist(), child1.tolist()
+    for v in order[::-1].tolist():       # children before parents
+        x = c0l[v]
+        if x < 0:
+            continue
+        kids = (x, c1l[v]) if c1l[v] >= 0 else (x,)
+        h = t = -1
+        for c in kids:                   # kept children, in order
+            if not rem[c]:
+                if h < 0:
+                    h = t = c
+                else:
+                    nxt[t] = c
+                    t = c
+        for c in kids:                   # then the spliced children's lists
+            if rem[c] and head[c] >= 0:
+                if h < 0:
+                    h, t = head[c], tail[c]
+                else:
+                    nxt[t] = head[c]
+                    t = tail[c]
+        head[v], tail[v] = h, t
+    return (np.asarray(head, dtype=np.int64), np.asarray(tail, dtype=np.int64), np.asarray(nxt, dtype=np.int64))
 
 
 def build_final_tree(names: Sequence[str], internal_names: Sequence[str], joins: np.ndarray, last2: Sequence[int],
@@ -213,32 +289,8 @@ def build_final_tree(names: Sequence[str], internal_names: Sequence[str], joins:
 
     # successor lists of kept nodes as linked lists: own kept children first, then the lists of removed
     # children, in child order (reference: add_edge appends, post-order splicing)
-    head = [-1] * M
-    tail = [-1] * M
-    nxt = [-1] * M
-    rem = removed.tolist()
-    c0l, c1l = c0.tolist(), c1.tolist()
-    for v in order[::-1].tolist():       # children before parents
-        x = c0l[v]
-        if x < 0:
-            continue
-        kids = (x, c1l[v]) if c1l[v] >= 0 else (x,)
-        h = t = -1
-        for c in kids:                   # kept children, in order
-            if not rem[c]:
-                if h < 0:
-                    h = t = c
-                else:
-                    nxt[t] = c
-                    t = c
-        for c in kids:                   # then the spliced children's lists
-            if rem[c] and head[c] >= 0:
-                if h < 0:
-                    h, t = head[c], tail[c]
-                else:
-                    nxt[t] = head[c]
-                    t = tail[c]
-        head[v], tail[v] = h, t
+    head, tail, nxt = successor_lists(order, c0, c1, removed)
+    head, nxt = head.tolist(), nxt.tolist()
 
     kept_order = order[~removed[order]].tolist()
     dl = depth.tolist()

@@ -238,6 +238,32 @@ CAS_API int cas_agglom_prune_diag(const void *workspace_dev, int64_t n, void *st
  * thread launched (bench.py's gpu_launches) */
 CAS_API int64_t cas_last_launch_count(void);
 
+/* ---- host passes of the array-based solve tail (no device work) ------------
+ * The reference finishes DistanceSolver.solve with per-node Python passes over the joined tree:
+ * root_tree's depth-first orientation (cassiopeia/solver/NeighborJoiningSolver.py:100-121,
+ * UPGMASolver.py:89-116), populate_tree's times (cassiopeia/data/CassiopeiaTree.py:141-203) and the
+ * post-order splicing of collapse_unifurcations / collapse_mutationless_edges (:1669-1775).
+ * cassiopeia_b200/tree_tail.py computes their result from integer arrays; these are its three
+ * per-node loops.  Trees are given as child0 / child1 arrays over node ids [0, n_nodes), -1 = none
+ * (a node has 0, 1 (child0 only) or 2 children). */
+
+/* Depth-first preorder, first child first (= node insertion order of the reference's rooted DiGraph)
+ * and the depth of every node reached.  Returns the number of nodes written to `order`, or < 0. */
+CAS_API int64_t cas_tail_preorder(const int64_t *child0, const int64_t *child1, int64_t n_nodes, int64_t root,
+                                  int64_t *order, int64_t *depth);
+
+/* height[v] above the deepest leaf below v (leaves 0), for the nodes of `order` (a preorder). */
+CAS_API int cas_tail_heights(const int64_t *order, int64_t n_order, const int64_t *child0, const int64_t *child1,
+                             int64_t *height);
+
+/* Successor lists after contracting the edges into the nodes flagged in `removed`, as linked lists
+ * (head / tail per node, next per list element; -1 terminated; `next` must come in filled with -1):
+ * a node's kept children first, then the lists of its removed children, in child order -- the order
+ * the reference's post-order splicing (add_edge appends) leaves in the successor dict. */
+CAS_API int cas_tail_successor_lists(const int64_t *order, int64_t n_order, const int64_t *child0,
+                                     const int64_t *child1, const uint8_t *removed, int64_t *head, int64_t *tail,
+                                     int64_t *next);
+
 /* ---- end to end from HOST buffers (synchronous) ----------------------------
  * Copies the character matrix (and weights) to the device, builds the map, runs the
  * loop and copies the join list back.  timings_ms (optional, [4]) receives device

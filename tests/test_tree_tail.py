@@ -130,3 +130,41 @@ def test_root_in_last_edge_and_overridden_hook(monkeypatch):
     tree = cb.CassiopeiaTree(character_matrix=pd.DataFrame(cm, index=names), root_sample_name="r")
     Custom().finish_tree(tree, names, joins, last2, None, False)
     assert calls == ["r"]
+
+
+@pytest.mark.parametrize("n,algo,seed", [(3, "nj", 0), (3, "upgma", 1), (40, "nj", 2), (257, "upgma", 3),
+                                         (2000, "nj", 4)])
+def test_native_passes_equal_interpreter_passes(n, algo, seed):
+    """cas_tail_preorder / cas_tail_heights / cas_tail_successor_lists against their Python twins, on random
+    join lists (including a caterpillar, whose depth is n) and random removal flags."""
+    from cassiopeia_b200 import tree_tail
+
+    rng = np.random.default_rng(seed)
+    for shape in ("random", "caterpillar"):
+        live = list(range(n))
+        joins = []
+        for t in range(n - 2):
+            if shape == "random":
+                i, j = sorted(rng.choice(len(live), size=2, replace=False).tolist())
+            else:
+                i, j = len(live) - 2, len(live) - 1
+            joins.append((live[i], live[j]))
+            del live[j]
+            del live[i]
+            live.append(n + t)
+        rt = tree_tail.RootedJoinTree(n, np.asarray(joins).reshape(-1, 2), live, algo,
+                                      None if algo == "upgma" else int(rng.integers(0, n)))
+        order, depth = rt.preorder()
+        order_py, depth_py = rt.preorder_py()
+        assert np.array_equal(order, order_py) and np.array_equal(depth, depth_py)
+        assert np.array_equal(rt.heights(), rt.heights_py())
+        removed = rng.random(rt.M) < 0.4
+        removed[rt.root] = False
+        removed[rt.child0 < 0] = False  # leaves are never spliced
+        got = tree_tail.successor_lists(order, rt.child0, rt.child1, removed)
+        want = tree_tail.successor_lists_py(order, rt.child0, rt.child1, removed)
+        kept = np.flatnonzero(~removed)
+        for a, b in zip(got, want):
+            # head / tail of removed leaves-of-lists and next of list tails are -1 in both
+            assert np.array_equal(a, b)
+        assert (got[0][kept[rt.child0[kept] >= 0]] >= -1).all()
