@@ -62,6 +62,42 @@ def test_row_order_random_against_loop_restatement():
         assert np.array_equal(host_prep.reference_row_order(cm), po.reference_row_order(cm))
 
 
+def test_row_order_survives_hash_collisions(monkeypatch):
+    """The row hash only proposes groups: with a degenerate hash (every row collides) the verification
+    step must notice and the exact byte-string sort must take over; negative and huge states hash too."""
+    rng = np.random.default_rng(5)
+    cm = rng.integers(-3, 4, size=(300, 6)).astype(np.int64)
+    cm[7] = cm[250]
+    cm[100, :] = np.iinfo(np.int64).max
+    cm[101, :] = np.iinfo(np.int64).min
+    want = po.reference_row_order(cm)
+    assert np.array_equal(host_prep.reference_row_order(cm), want)
+    assert np.array_equal(host_prep._first_occurrence(cm), host_prep._first_occurrence_exact(cm))
+    monkeypatch.setattr(host_prep, "_HASH_MULT", np.zeros_like(host_prep._HASH_MULT))
+    assert np.array_equal(host_prep.reference_row_order(cm), want)
+    # wider than the multiplier table: exact path
+    wide = rng.integers(0, 2, size=(20, host_prep._HASH_MULT.size + 1)).astype(np.int64)
+    wide[3] = wide[11]
+    assert np.array_equal(host_prep.reference_row_order(wide), po.reference_row_order(wide))
+
+
+def test_compact_states_missing_indicator_extremes():
+    """The present-state range is found without gathering the present entries: the indicator may be the
+    smallest or the largest value of the matrix, or collide with the code range."""
+    base = np.array([[0, 1, 2], [2, 1, 0], [1, 1, 1]], dtype=np.int64)
+    for miss in (-1, 7, 10**9, -10**9, 1):
+        cm = base.copy()
+        cm[0, 0] = miss
+        cm[2, 2] = miss
+        codes, mcode, table, S = host_prep.compact_states(cm, miss, None)
+        present = cm != miss
+        assert S == int(cm[present].max()) and np.array_equal(codes[present], cm[present])
+        assert (codes[~present] == mcode).all() and not (0 <= mcode <= S)
+    allmiss = np.full((2, 3), -1, dtype=np.int64)
+    codes, mcode, table, S = host_prep.compact_states(allmiss, -1, None)
+    assert (codes == mcode).all() and S == 1
+
+
 def test_compact_states_direct_and_remapped():
     cm = np.array([[0, 5, -1], [3, 5, 2], [3, 0, 2]], dtype=np.int64)
     codes, miss, table, S = host_prep.compact_states(cm, -1, None)
