@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
   __shared__ unsigned long long sRead[SCAN_WARPS];
-  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_UNIT];  // per warp: needed sub-segments of the unit
+  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_WIDE];  // per warp: needed sub-segments of the unit
 
   const T *__restrict__ D = static_cast<const T *>(a.D);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,16 +178,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
   const float cnow = prune_cnow(p);
   {
-    // work units (queued row, 64 sub-segments), round-robin over all warps
-    const long long upr = (((long long)k - 1 + SW - 1) / SW + PRUNE_UNIT - 1) / PRUNE_UNIT;  // units per row
-    const long long nunits = (long long)__ldcg(p.wcount) * upr;
+    // work units, round-robin over all warps.  Rows queued from the back of the list (bound unknown: the whole
+    // row is read -- the two rows the last merge rewrote, or every row in the first iteration) are cut into
+    // short units so that their reads spread over many warps; they come first because they are the critical
+    // path.  Rows queued from the front passed a bound test that will skip nearly all of their sub-segments:
+    // wide units, one coalesced load of 32 bounds per step.
+    const long long nsub_max = ((long long)k - 1 + SW - 1) / SW;
+    const long long upr_s = (nsub_max + PRUNE_UNIT - 1) / PRUNE_UNIT;  // units per row, short
+    const long long upr_w = (nsub_max + PRUNE_WIDE - 1) / PRUNE_WIDE;  // units per row, wide
+    const long long ushort = (long long)__ldcg(p.wcount + 1) * upr_s;
+    const long long nunits = ushort + (long long)__ldcg(p.wcount) * upr_w;
     for (long long u = gw; u < nunits; u += W) {
-      const int i = p.worklist[u / upr];
-      const int sb = (int)(u % upr) * PRUNE_UNIT;
+      const bool shrt = u < ushort;
+      const long long v = shrt ? u : u - ushort;
+      const long long upr = shrt ? upr_s : upr_w;
+      const int unit = shrt ? PRUNE_UNIT : PRUNE_WIDE;
+      const long long r = v / upr;
+      const int i = p.worklist[shrt ? p.wlast - (int)r : (int)r];
+      const int sb = (int)(v - r * upr) * unit;
       if ((long long)sb * SW >= i) continue;  // the row ends before this unit's first column
       rs.set_row(i, NJ ? a.R[i] : 0.0);
       prune_unit<T, NJ>(rs, pw, D + (int64_t)i * a.ld, p.E + (int64_t)i * p.stride, i, i, sb, cnow, p, sList[warp],
-                        lane);
+                        lane, unit);
     }
   }
 
@@ -225,8 +237,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
     // every other CTA has finished (counter): clear the per-iteration state, commit the drift
     *p.gbest = enc_f64(INFINITY);
-    atomicAdd(a.stats + 2, (unsigned long long)*p.wcount);  // diagnostics: rows listed over the whole loop
-    *p.wcount = 0u;
+    atomicAdd(a.stats + 2, (unsigned long long)p.wcount[0] + p.wcount[1]);  // diagnostics: rows listed, whole loop
+    p.wcount[0] = 0u;
+    p.wcount[1] = 0u;
     prune_commit(p);
     p.beta[lo] = enc_f32(-INFINITY);
     p.beta[hi] = enc_f32(-INFINITY);
@@ -508,7 +521,8 @@ __global__ void prune_init_kernel(unsigned *E, int64_t count, unsigned *beta, in
     hdr[0] = 0.f;
     *dmax = enc_f32(0.f);
     *gbest = enc_f64(INFINITY);
-    *wcount = 0u;
+    wcount[0] = 0u;
+    wcount[1] = 0u;
     *scanned = 0ull;
   }
 }
@@ -668,6 +682,8 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
   // the opt-in persistent experiment (CAS_PERSISTENT=1) keeps its dense scan
   const bool prune = !strict_nj && prune_enabled(NJ) && n > 2 && !persistent_enabled();
   const int min_k = prune_min_k();
+  // CAS_PRUNE_WIDE=0: every listed row in short units (the behaviour before the split work list)
+  const int prune_wide = getenv("CAS_PRUNE_WIDE") ? (atoi(getenv("CAS_PRUNE_WIDE")) != 0) : 1;
   if (prune) {
     prune_init_kernel<<<sms * 4, 256, 0, stream>>>(w.E, w.lb_stride * n, w.beta, n, w.hdr, w.dmax, w.gbest, w.wcount,
                                                    w.scanned, w.pool);
@@ -721,10 +737,11 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     // beat the pruned scan's three; the switch is one-way, so the bounds need no further maintenance
     const bool prune_it = prune && k > min_k;
     if (prune_it) {
-      PruneArgs pa;
+      PruneArgs pa{};
       pa.E = w.E; pa.stride = w.lb_stride; pa.beta = w.beta; pa.uf = w.uf; pa.hdr = w.hdr; pa.dmax = w.dmax;
       pa.gbest = w.gbest; pa.worklist = w.worklist; pa.wcount = w.wcount; pa.sugg = w.sugg;
       pa.scanned = w.scanned; pa.cta_read = w.cta_read;
+      pa.split = 1; pa.wide = prune_wide; pa.wlast = (int)n + 31;
       CAS_CUDA_TRY(launch_pdl(prune_rowtest_kernel<T, NJ>, (unsigned)((k + 255) / 256), 256u, stream, pa,
                               (const T *)D, ld, k, (const double *)w.R, sa.tinv, (const Sel *)w.sel, t > 0 ? 1 : 0));
       CAS_LAUNCH_CHECK();

@@ -27,6 +27,8 @@ constexpr int SW = 128;        // columns per bound (sub-segment)
 constexpr int PRUNE_UNIT = 8;  // sub-segments per work unit (1024 columns): one warp, one bound test (lanes
                                // 0..7), at most one group of eight 128-bit loads per lane -- the critical
                                // path of an iteration is one unit, so units are kept short
+constexpr int PRUNE_WIDE = 32; // sub-segments per work unit of a row that is known to be almost all skipped:
+                               // one 128-byte load of bounds per step instead of four 32-byte ones
 constexpr int POOL = 512;      // pairs kept to warm-start gbest (>= CTAs of the pruned scan)
 
 struct PruneArgs {
@@ -38,7 +40,14 @@ struct PruneArgs {
   unsigned *dmax;             // encoded float: largest uf increase measured by the last merge
   unsigned long long *gbest;  // encoded double
   int32_t *worklist;          // rows that failed this iteration's row test (row indices)
-  unsigned *wcount;
+  unsigned *wcount;           // [0] rows queued from the front of the list, [1] rows queued from its back (split)
+  int split;                  // 0: one list (front).  1: two lists -- rows scanned in short units (PRUNE_UNIT
+                              // sub-segments: good for rows that are read in full, the critical path) are queued
+                              // from the back (slot wlast downwards), rows scanned in PRUNE_WIDE-sub-segment
+                              // units (one coalesced bound load per step: good for rows of which almost nothing
+                              // is read) from the front
+  int wide;                   // split only: 1 = only rows whose bound is unknown go to the back, 0 = all rows do
+  int wlast;                  // split only: index of the last slot of the work list
   int32_t *sugg;              // [gridDim][2] per-CTA suggestion (slots) for the pool
   unsigned long long *scanned;   // statistics: map elements actually read
   unsigned long long *cta_read;  // [gridDim] per-CTA counts of this launch (summed by the last CTA)
@@ -150,9 +159,10 @@ template <typename T, bool NJ>
 __device__ __forceinline__ void prune_rowtest(const PruneArgs &p, bool valid, int64_t ridx, int i, const T *row,
                                               double Ri, double tinv, int prev_lo, int prev_hi, bool prev_moved) {
   const float cnow = prune_cnow(p);
-  bool unsafe = false;
+  bool unsafe = false, unknown = false;
   if (valid) {
     unsigned b = p.beta[ridx];
+    unknown = b == enc_f32(-INFINITY);  // the whole row will be read
     if (prev_lo >= 0 && i != prev_lo && i != prev_hi) {
       unsigned *erow = p.E + ridx * p.stride;
       if (i > prev_lo) {
@@ -175,13 +185,22 @@ __device__ __forceinline__ void prune_rowtest(const PruneArgs &p, bool valid, in
     // an unsafe row's beta is rebuilt by its work units (atomicMin)
     p.beta[ridx] = unsafe ? enc_f32(INFINITY) : b;
   }
-  const unsigned m = __ballot_sync(0xffffffffu, unsafe);
+  const int lane = threadIdx.x & 31;
+  const bool back = unsafe && p.split && (!p.wide || unknown);
+  const bool front = unsafe && !back;
+  const unsigned m = __ballot_sync(0xffffffffu, front);
   if (m) {
-    const int lane = threadIdx.x & 31;
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(p.wcount, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (unsafe) p.worklist[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)ridx;
+    if (front) p.worklist[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)ridx;
+  }
+  const unsigned mb = __ballot_sync(0xffffffffu, back);
+  if (mb) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(p.wcount + 1, (unsigned)__popc(mb));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (back) p.worklist[p.wlast - (int)(base + __popc(mb & ((1u << lane) - 1u)))] = (int32_t)ridx;
   }
 }
 
@@ -191,15 +210,16 @@ struct PruneWarp {
   unsigned long long nread;   // map elements read
 };
 
-// One work unit = sub-segments [sb, sb + PRUNE_UNIT) of one row, handled by one warp: decide from the bounds
+// One work unit = sub-segments [sb, sb + unit) of one row (unit <= 32), handled by one warp: decide from the bounds
 // which sub-segments can hold a competitive pair, read exactly those (eight 128-bit loads in flight per
 // lane), refresh their bounds, lower the row bound, publish improvements of gbest.  `row` / `erow` point at
 // the row's map elements / bounds, `i` is its slot (columns [0, i) are the lower triangle), `list` is the
-// warp's shared-memory scratch (PRUNE_UNIT entries).
+// warp's shared-memory scratch (`unit` entries).
 template <typename T, bool NJ>
 __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, const T *__restrict__ row,
                                            unsigned *erow, int64_t ridx, int i, int sb, float cnow,
-                                           const PruneArgs &p, unsigned short *list, int lane) {
+                                           const PruneArgs &p, unsigned short *list, int lane,
+                                           int unit = PRUNE_UNIT) {
   constexpr int V = VecOf<T>::N;
   constexpr int LOADS = SW / (32 * V);  // 128-bit loads per lane and sub-segment (1 float, 2 double)
   constexpr int G = 8 / LOADS;          // sub-segments in flight
@@ -212,7 +232,7 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
   bool need = false;
   {
     const int sgm = sb + lane;
-    const bool exists = lane < PRUNE_UNIT && sgm < nsub;
+    const bool exists = lane < unit && sgm < nsub;
     const unsigned e = exists ? erow[sgm] : enc_f32(INFINITY);
     const bool skip = prune_impossible<T, NJ>(dec_f32(e), cnow, rs.uif, gb);
     need = exists && !skip;
@@ -223,7 +243,7 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
   bool diag_needed = false;
   {
     const int dsub = nsub - 1 - sb;
-    if (dsub >= 0 && dsub < PRUNE_UNIT) {
+    if (dsub >= 0 && dsub < unit) {
       diag_needed = (flags >> dsub) & 1u;
       flags &= ~(1u << dsub);
     }

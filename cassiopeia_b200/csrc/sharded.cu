@@ -808,7 +808,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
       if (grid < 1) grid = 1;
       if (prune_it) {
-        PruneArgs pa;
+        PruneArgs pa{};  // split = 0: one work list, short units
         pa.E = rk.w.E; pa.stride = rk.w.lb_stride; pa.beta = rk.w.beta; pa.uf = rk.w.uf; pa.hdr = rk.w.hdr;
         pa.dmax = rk.w.dmax; pa.gbest = rk.w.gbest; pa.worklist = rk.w.worklist; pa.wcount = rk.w.wcount;
         pa.sugg = rk.w.sugg; pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;

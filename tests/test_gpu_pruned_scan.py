@@ -89,3 +89,17 @@ def test_work_list_stays_short_as_the_drift_grows(monkeypatch):
     late = (listed[0.9] - listed[0.5]) / (0.4 * nn)    # rows listed per iteration between 50 % and 90 %
     live = 0.3 * nn                                    # mean live rows in that window
     assert late < 0.1 * live, (listed, late)
+
+
+@pytest.mark.parametrize("algo", ["nj", "upgma"])
+def test_short_units_for_every_row_equal_wide_units(algo, monkeypatch):
+    """CAS_PRUNE_WIDE=0 (every listed row in 8-sub-segment units) and the default split work list (rows with a
+    known bound in 32-sub-segment units) select the same pairs."""
+    D, nn = _map(5000, 40, 50, "f32", 0.3, 0.2, True, seed=9)
+    monkeypatch.setenv("CAS_PRUNE_WIDE", "0")
+    j0, l0, s0 = _run(D, nn, algo, "fast", True, monkeypatch)
+    monkeypatch.setenv("CAS_PRUNE_WIDE", "1")
+    j1, l1, s1 = _run(D, nn, algo, "fast", True, monkeypatch)
+    assert np.array_equal(j0, j1) and np.array_equal(l0, l1)
+    assert (s0["near_ties"], s0["exact_ties"]) == (s1["near_ties"], s1["exact_ties"])
+    assert s0["rows_listed"] > 0 and s1["rows_listed"] > 0
