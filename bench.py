@@ -214,6 +214,33 @@ def workload_config(args, n_gpus, mode):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def solver_api_solve(args, joins):
+    """One solve of the same workload through the drop-in class (the call a Cassiopeia user makes):
+    pandas character matrix + priors in, populated CassiopeiaTree out -- host preparation, H2D, map, loop, D2H
+    and the tree-building tail (rooting, populate_tree, collapse_unifurcations).  Reported next to the C-ABI
+    `e2e`; never fails the bench."""
+    try:
+        import pandas as pd
+        import cassiopeia_b200 as cb
+        from cassiopeia_b200.synthetic import simulate_character_matrix
+
+        cm, priors, _ = simulate_character_matrix(args.cells, args.chars, args.states, seed=args.seed,
+                                                  mutation_rate=args.mutation_rate, missing_fraction=args.missing)
+        frame = pd.DataFrame(cm, index=[f"c{i}" for i in range(cm.shape[0])])
+        tree = cb.CassiopeiaTree(character_matrix=frame, priors=priors)
+        fast = args.mode == "fast"
+        solver = cb.NeighborJoiningSolver(add_root=True, fast=fast, implementation="b200_fast" if fast else "b200_strict")
+        t0 = time.perf_counter()
+        solver.solve(tree)
+        seconds = time.perf_counter() - t0
+        same = bool(np.array_equal(solver.last_join_list[0], joins))
+        return {"value": seconds, "unit": "s", "joins_identical_to_device_path": same,
+                "leaves": len(tree.leaves), "call": "NeighborJoiningSolver(add_root=True, fast=%s).solve(CassiopeiaTree)"
+                % fast}
+    except Exception as e:  # noqa: BLE001 - a reporting extra must not take the bench line down
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_b200(args):
     import torch
 
@@ -350,6 +377,8 @@ def run_b200(args):
                       "d2h_bytes_per_step": int(j_e2e.nbytes + l_e2e.nbytes),
                       "device_ms": {"h2d": tm[0], "map": tm[1], "loop": tm[2], "d2h": tm[3]},
                       "api": "cas_solve_host (C ABI, pinned host buffers)"}
+    if not args.no_e2e and "e2e" in out:
+        out["e2e"]["solver_api"] = solver_api_solve(args, joins)
     if not args.no_cpu_baseline:
         cells = min(args.cpu_sample_cells, args.cells)
         t_map, t_loop, threads = cpu_sample(args, cells)
