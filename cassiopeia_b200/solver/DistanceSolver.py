@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import abc
 import gc
+import itertools
 from typing import Callable, List, Optional, Tuple
 
 import networkx as nx
@@ -196,7 +197,7 @@ class DistanceSolver(abc.ABC):
         from .. import tree_tail
 
         node_name_generator = solver_utilities.node_name_generator()
-        internal_names = [next(node_name_generator) for _ in range(len(joins))]
+        internal_names = list(itertools.islice(node_name_generator, len(joins)))
         # remove root from character matrix before populating tree (:214-222)
         if cassiopeia_tree.root_sample_name in cassiopeia_tree.character_matrix.index:
             cassiopeia_tree.character_matrix = cassiopeia_tree.character_matrix.drop(
