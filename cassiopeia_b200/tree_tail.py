@@ -34,6 +34,11 @@ import numpy as np
 
 from . import _lib
 
+try:  # CPython extension built next to libcas_b200.so (csrc/graphfill.c); the interpreter loop is the fallback
+    from . import _graphfill
+except ImportError:  # pragma: no cover
+    _graphfill = None
+
 
 #: graph attribute set on trees whose node attributes (`character_states`, `time`) and edge `length`s are
 #: already what `populate_tree` would compute
@@ -289,14 +294,21 @@ def build_final_tree(names: Sequence[str], internal_names: Sequence[str], joins:
 
     # successor lists of kept nodes as linked lists: own kept children first, then the lists of removed
     # children, in child order (reference: add_edge appends, post-order splicing)
-    head, tail, nxt = successor_lists(order, c0, c1, removed)
-    head, nxt = head.tolist(), nxt.tolist()
-
-    kept_order = order[~removed[order]].tolist()
-    dl = depth.tolist()
+    head_a, tail, nxt_a = successor_lists(order, c0, c1, removed)
+    kept_a = np.ascontiguousarray(order[~removed[order]])
     g = nx.DiGraph()
     node, succ, pred = getattr(g, "_node", None), getattr(g, "_succ", None), getattr(g, "_pred", None)
-    if node is not None and succ is not None and pred is not None and not node:
+    direct = node is not None and succ is not None and pred is not None and not node
+    if direct and _graphfill is not None:
+        # the same dictionaries as the interpreter loop below, filled by the C extension (csrc/graphfill.c)
+        _graphfill.fill(node, succ, pred, label, kept_a, head_a, nxt_a, np.ascontiguousarray(depth))
+        if all(isinstance(x, str) for x in names):
+            g.graph[PREPARED] = True
+        return g, _internal_states(states, internal, removed, label)
+    head, nxt = head_a.tolist(), nxt_a.tolist()
+    kept_order = kept_a.tolist()
+    dl = depth.tolist()
+    if direct:
         # networkx keeps {node: attrs}, {u: {v: attrs}}, {v: {u: attrs}} with the edge attribute dict shared
         # between the successor and the predecessor map; filling them directly skips the per-call checks of
         # add_nodes_from / add_edges_from (half of this function's time at 10^5 nodes)
@@ -334,9 +346,12 @@ def build_final_tree(names: Sequence[str], internal_names: Sequence[str], joins:
                 c = nxt[c]
         g.add_edges_from(edges)
 
-    internal_states: Dict[str, List[int]] = {}
-    if states is not None:
-        keep_int = np.flatnonzero(internal & ~removed)
-        rows = states[keep_int].tolist()
-        internal_states = {label[v]: row for v, row in zip(keep_int.tolist(), rows)}
-    return g, internal_states
+    return g, _internal_states(states, internal, removed, label)
+
+
+def _internal_states(states, internal, removed, label) -> Dict[str, List[int]]:
+    if states is None:
+        return {}
+    keep_int = np.flatnonzero(internal & ~removed)
+    rows = states[keep_int].tolist()
+    return {label[v]: row for v, row in zip(keep_int.tolist(), rows)}

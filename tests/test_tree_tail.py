@@ -168,3 +168,43 @@ def test_native_passes_equal_interpreter_passes(n, algo, seed):
             # head / tail of removed leaves-of-lists and next of list tails are -1 in both
             assert np.array_equal(a, b)
         assert (got[0][kept[rt.child0[kept] >= 0]] >= -1).all()
+
+
+@pytest.mark.parametrize("algo", ["nj", "upgma"])
+@pytest.mark.parametrize("collapse", [False, True])
+def test_c_dictionary_filler_equals_interpreter_loop(algo, collapse, monkeypatch):
+    """`_graphfill.fill` (csrc/graphfill.c) and the interpreter loop of build_final_tree leave identical
+    networkx dictionaries: key order of all three, attribute values, and one shared attribute dict per edge."""
+    from cassiopeia_b200 import tree_tail
+
+    if tree_tail._graphfill is None:
+        pytest.skip("cassiopeia_b200/_graphfill.so was not built (make -C cassiopeia_b200/csrc needs Python.h)")
+    filler = tree_tail._graphfill
+    rng = np.random.default_rng(3)
+    n, m = 300, 6
+    cm = character_matrix(n, m, rng, low_information=True)
+    names = [f"c{i}" for i in range(n)]
+    joins, last2 = random_joins(n, rng)
+    internal = [f"i{t}" for t in range(n - 2)]
+    graphs = []
+    for use_c in (True, False):
+        if not use_c:
+            monkeypatch.setattr(tree_tail, "_graphfill", None)
+        g, states = tree_tail.build_final_tree(names, internal, joins, last2, algo, "c7" if algo == "nj" else None,
+                                               cm, -1, collapse)
+        graphs.append((g, states))
+    (gc_, sc), (gp, sp) = graphs
+    assert sc == sp and gc_.graph == gp.graph
+    assert list(gc_._node) == list(gp._node) and gc_._node == gp._node
+    assert list(gc_._succ) == list(gp._succ) and list(gc_._pred) == list(gp._pred)
+    for u in gp._node:
+        assert list(gc_._succ[u].items()) == list(gp._succ[u].items())
+        assert list(gc_._pred[u].items()) == list(gp._pred[u].items())
+        for v, attrs in gc_._succ[u].items():
+            assert gc_._pred[v][u] is attrs
+    with pytest.raises(ValueError):
+        filler.fill({}, {}, {}, ["a", "a"], np.array([0, 1]), np.array([-1, -1]), np.array([-1, -1]),
+                                  np.array([0, 1]))
+    with pytest.raises(TypeError):
+        filler.fill({}, {}, {}, ["a"], np.array([0], dtype=np.int32), np.array([-1]), np.array([-1]),
+                                  np.array([0]))
