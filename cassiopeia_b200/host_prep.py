@@ -101,14 +101,15 @@ def compact_states(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dic
     weighted = bool(weights)
     # smallest / largest PRESENT state without gathering the present entries: the indicator only matters
     # when it is itself the extreme value of the matrix
-    smin = smax = 0
+    nonneg, smax = True, 0
     if cm.size and present.any():
-        smin, smax = int(cm.min()), int(cm.max())
-        if smin == missing:
-            smin = int(np.where(present, cm, smax).min())
+        lo, smax = int(cm.min()), int(cm.max())
+        if lo < 0:
+            # negative present states force the remapping; the indicator alone (the usual -1) does not
+            nonneg = lo == missing and not ((cm < 0) & present).any()
         if smax == missing:
-            smax = int(np.where(present, cm, smin).max())
-    direct = smin >= 0 and smax <= DIRECT_STATE_LIMIT
+            smax = int(np.where(present, cm, lo).max())
+    direct = nonneg and smax <= DIRECT_STATE_LIMIT
     if direct:
         codes = cm.astype(np.int32)
         n_states = max(smax, 1)
@@ -143,8 +144,12 @@ def compact_states(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dic
         # distinct present codes per character and how many samples carry each: codes are small
         # non-negative integers, so a counting pass per column replaces a sort
         width = n_states + 2  # bin 0 collects the missing entries
-        shifted = np.where(codes != missing_code, codes, -1).astype(np.int64)
-        shifted += 1 + np.arange(m, dtype=np.int64) * width
+        itype = np.int32 if m * width < 2**31 - 1 else np.int64
+        offsets = (1 + np.arange(m, dtype=np.int64) * width).astype(itype)
+        if missing_code == -1:
+            shifted = codes.astype(itype, copy=False) + offsets  # missing (-1) lands in bin 0 of its character
+        else:
+            shifted = np.where(codes != missing_code, codes, -1).astype(itype) + offsets
         hist2d = np.bincount(shifted.ravel(), minlength=m * width).reshape(m, width)[:, 1:]
         for c in range(m):
             hist = hist2d[c]
