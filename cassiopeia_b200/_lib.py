@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("CAS_B200_LIBRARY", os.path.join(_HERE, "libcas_b200.s
 CAS_ABI_VERSION = 1
 CAS_F32, CAS_F64 = 0, 1
 CAS_ALGO_NJ, CAS_ALGO_UPGMA = 0, 1
-CAS_MODE_STRICT, CAS_MODE_FAST = 0, 1
+CAS_MODE_STRICT, CAS_MODE_FAST, CAS_MODE_EXACT = 0, 1, 2
 CAS_MAP_EXACT, CAS_MAP_TENSOR = 0, 1
 
 EXPORTS = (
@@ -38,6 +38,7 @@ EXPORTS = (
     "cas_agglom_stats",
     "cas_agglom_scanned_elements",
     "cas_agglom_prune_diag",
+    "cas_agglom_exact_stats",
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
     "cas_sharded_workspace_bytes",
@@ -101,6 +102,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_agglom_scanned_elements.argtypes = [vp, i64, vp, ctypes.POINTER(i64)]
     L.cas_agglom_prune_diag.restype = ctypes.c_int
     L.cas_agglom_prune_diag.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]
+    L.cas_agglom_exact_stats.restype = ctypes.c_int
+    L.cas_agglom_exact_stats.argtypes = [vp, i64, vp, vp]
     L.cas_tail_preorder.restype = i64
     L.cas_tail_preorder.argtypes = [vp, vp, i64, i64, vp, vp]
     L.cas_tail_heights.restype = ctypes.c_int

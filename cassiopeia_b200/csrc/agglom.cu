@@ -27,7 +27,7 @@
 // (E = 4 fast, 8 strict); merge touches O(k) elements.
 #include <stdlib.h>
 
-#include "agglom_pruned.cuh"
+#include "agglom_exact.cuh"
 
 namespace cas {
 
@@ -50,7 +50,71 @@ struct ScanArgs {
   int32_t *joins;
   int t;  // iteration index
   unsigned long long *stats;  // [0] near-tie iterations, [1] exact-tie iterations
+  int exact;     // exact (adaptive strict) NJ mode, agglom_exact.cuh
+  ExactArgs ex;
+  int *error;    // set when a scan finds no candidate at all (e.g. an all-NaN map): nothing may be indexed with -1
 };
+
+// A scan that found no candidate at all (a map without a single finite entry, e.g. all NaN through the C ABI):
+// nothing may be indexed with slot -1.  The selection is marked invalid, the merge kernels return at once, the
+// error flag makes last2 = (-2, -2) and the host raises.
+__device__ __forceinline__ void publish_no_candidate(const ScanArgs &a) {
+  Sel s;
+  s.lo = -1; s.hi = -1; s.dij = 0.0; s.size_lo = 0; s.size_hi = 0; s.id_lo = -1; s.id_hi = -1;
+  *a.sel = s;
+  a.joins[2 * a.t] = -1;
+  a.joins[2 * a.t + 1] = -1;
+  if (a.error) *a.error = 1;
+}
+
+// Exact mode, dense scan, step A of the resolver: every pair with q~ <= capq lies in a tile of a CTA whose own best
+// is <= capq, so only those CTAs' tiles are visited again (same tile -> (column block, row block) map as the scan).
+__device__ __noinline__ void exact_collect_dense(ScanArgs a, int ncand, double capq, int epoch) {
+  const double *__restrict__ D = static_cast<const double *>(a.D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int x = 0; x < ncand; ++x) {
+    if (!(__ldcg(&a.cand[x].q) <= capq)) continue;
+    for (int tile = x; tile < a.ntiles; tile += ncand) {
+      int cb = 0, rem = tile;
+      for (;;) {
+        int first = (cb * TC + 1) / a.tr;
+        int cnt = max(a.nrb - first, 0);
+        if (rem < cnt) { rem += first; break; }
+        rem -= cnt;
+        ++cb;
+      }
+      const int c0 = cb * TC, c1 = min(c0 + TC, a.k);
+      const int r0 = rem * a.tr, r1 = min(r0 + a.tr, a.k);
+      for (int i = r0 + warp; i < r1; i += SCAN_WARPS) {
+        const int jend = min(c1, i);
+        if (jend <= c0) continue;
+        exact_collect_span(D + (int64_t)i * a.ld, i, c0, jend, lane, a.R, a.R[i], a.tinv, capq, a.ex, epoch);
+      }
+    }
+  }
+}
+
+// Exact mode: called by every thread of a scan's last CTA with the reduced candidate.  When a second pair lies
+// inside the error window of the minimum the reference's sequential sums decide (agglom_exact.cuh).
+template <bool PRUNED>
+__device__ __forceinline__ void exact_resolve(const ScanArgs &a, const PruneArgs *p, int ncand, Cand &c) {
+  __shared__ int sWin[2];
+  const double W = exact_window(a.ex.xw, a.k, a.tinv);
+  if (c.si < 0 || !(c.q2 - c.q <= W)) return;  // uniform: every thread holds the same candidate
+  const double capq = c.q + W;
+  const int epoch = a.t + 1;
+  if (PRUNED) {
+    exact_collect_pruned(static_cast<const double *>(a.D), a.ld, a.k, a.R, a.tinv, *p, a.ex, capq, epoch,
+                         __ldcg(p->wcount), __ldcg(p->wcount + 1));
+  } else {
+    exact_collect_dense(a, ncand, capq, epoch);
+  }
+  if (threadIdx.x == 0) { sWin[0] = c.si; sWin[1] = c.sj; }
+  exact_finish(static_cast<const double *>(a.D), a.ld, a.k, a.R, a.ids, a.tinv, capq, a.ex, &sWin[0], &sWin[1]);
+  __syncthreads();
+  c.si = sWin[0];
+  c.sj = sWin[1];
+}
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
@@ -62,6 +126,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
   const double umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
+  const double wfloor = (NJ && a.exact) ? 2.0 * exact_window(a.ex.xw, k, a.tinv) : 0.0;
   double bq = INFINITY, b2 = INFINITY;
   int bi = -1, bj = -1;
   int staged_cb = -1;
@@ -93,7 +158,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
       if (jend <= c0) continue;
       const T *__restrict__ row = D + (int64_t)i * a.ld;
       const double Ri = NJ ? a.R[i] : 0.0;
-      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj, b2);
+      scan_row_segment<T, NJ>(row, i, c0, jend, lane, sU, a.R, Ri, a.tinv, umax, a.ids, bq, bi, bj, b2, wfloor);
     }
   }
 
@@ -109,7 +174,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   __threadfence();
   // the last CTA reduces all per-CTA candidates
   c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
+  if constexpr (NJ && sizeof(T) == 8) {
+    if (a.exact) exact_resolve<false>(a, nullptr, (int)gridDim.x, c);
+  }
   if (threadIdx.x == 0) {
+    if (c.si < 0) {
+      publish_no_candidate(a);
+      return;
+    }
     Sel s;
     s.lo = min(c.si, c.sj);
     s.hi = max(c.si, c.sj);
@@ -153,7 +225,7 @@ __global__ void __launch_bounds__(256) prune_rowtest_kernel(PruneArgs p, const T
     moved = phi != k;  // the previous iteration's last slot was k: a node moved into slot hi unless hi was last
   }
   prune_rowtest<T, NJ>(p, valid, i, i, D + (int64_t)(valid ? i : 0) * ld, (valid && NJ) ? R[i] : 0.0, tinv, plo, phi,
-                       moved);
+                       moved, prune_wfloor(p, k, tinv));
 }
 
 template <typename T, bool NJ>
@@ -173,6 +245,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
   rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
   rs.sbest = INFINITY; rs.ssi = -1; rs.ssj = -1; rs.uif = 0.f;
+  rs.wfloor = prune_wfloor(p, k, a.tinv);
   PruneWarp pw;
   pw.gb_seen = INFINITY; pw.nread = 0;
   const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
@@ -219,7 +292,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   if (!sLast) return;
   __threadfence();
   c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
+  if constexpr (NJ && sizeof(T) == 8) {
+    if (a.exact) exact_resolve<true>(a, &p, (int)gridDim.x, c);  // reads the work list: before it is reset below
+  }
   const int lo = min(c.si, c.sj), hi = max(c.si, c.sj);
+  if (lo < 0) {  // uniform
+    if (threadIdx.x == 0) {
+      publish_no_candidate(a);
+      p.wcount[0] = 0u;
+      p.wcount[1] = 0u;
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     Sel s;
     s.lo = lo;
@@ -279,6 +363,9 @@ struct MergeArgs {
   // per-CTA winners / suggestions and the persistent pool (warm start of gbest)
   int prune; float *uf; double tinv_next; unsigned *dmax;
   const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool; int rot;
+  // exact NJ mode (agglom_exact.cuh): error bound / absolute-sum bound of every maintained row sum, their running
+  // maxima, per-CTA partial sums of |new row|
+  int exact; double *Eb; double *Ab; unsigned long long *xw; double *apartial;
 };
 
 template <typename T, bool NJ>
@@ -294,14 +381,17 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
   pdl_wait();  // no-op unless launched with programmatic stream serialization (the pruned loop)
   pdl_launch_dependents();
   __shared__ double sPart[MERGE_THREADS / 32];
+  __shared__ double sPartA[MERGE_THREADS / 32];
   __shared__ bool sLast;
   T *__restrict__ D = static_cast<T *>(a.D);
   const Sel s = *a.sel;
+  if (s.lo < 0) return;  // the scan found no candidate (publish_no_candidate)
   const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1;
   const int64_t ld = a.ld;
   const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
   double contrib = 0.0;
   float uf_up = 0.f;            // pruned scan: increase of this slot's fl32(u) (columns that keep their node)
+  double ebv = 0.0, abv = 0.0;  // exact mode: this row's bounds after the update
 
   if (v < k) {
     if (v == lo) {
@@ -326,7 +416,18 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       const T nvs = round_to<T>(nv);
       contrib = (double)nvs;
       double Rv = 0.0;
-      if (a.maintain_R) Rv = __dadd_rn(__dsub_rn(__dsub_rn(a.R[v], da), db), contrib);
+      if (a.maintain_R) {
+        const double x1 = __dsub_rn(a.R[v], da), x2 = __dsub_rn(x1, db);
+        Rv = __dadd_rn(x2, contrib);
+        if (a.exact) {
+          // three rounded results: the error of R_v grows by at most u (|x1| + |x2| + |Rv|); everything rounded up
+          ebv = __dadd_ru(a.Eb[v], __dmul_ru(__dadd_ru(__dadd_ru(fabs(x1), fabs(x2)), fabs(Rv)), EXACT_U1));
+          abv = fmax(__dsub_ru(__dsub_ru(__dadd_ru(a.Ab[v], fabs(contrib)), fabs(da)), fabs(db)), 0.0);
+          const int dst = (v == last && hi != last) ? hi : v;
+          a.Eb[dst] = ebv;
+          a.Ab[dst] = abv;
+        }
+      }
       if (hi != last && v != last) {
         // the node in the last live slot moves into slot hi
         const T l = D[(int64_t)last * ld + v];
@@ -397,15 +498,31 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     if (v < k && v != lo && v != hi) mine = (v == last && hi != last) ? a.R[hi] : a.R[v];
     warp_atomic_absmax(a.rmax_bits, mine);
   }
+  double acontrib = fabs(contrib);
+  if (a.exact) {
+    warp_atomic_max_nonneg(a.xw + XW_EBMAX, ebv);
+    warp_atomic_max_nonneg(a.xw + XW_ABMAX, abv);
+    warp_atomic_max_nonneg(a.xw + XW_DABS, acontrib);
+  }
   // deterministic sum of the new row: fixed 256-wide chunks, shuffle tree, then sequential
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
   if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = contrib;
+  if (a.exact) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acontrib = __dadd_rn(acontrib, __shfl_down_sync(0xffffffffu, acontrib, off));
+    if ((threadIdx.x & 31) == 0) sPartA[threadIdx.x >> 5] = acontrib;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double sum = 0.0;
     for (int w = 0; w < MERGE_THREADS / 32; ++w) sum = __dadd_rn(sum, sPart[w]);
     a.partial[blockIdx.x] = sum;
+    if (a.exact) {
+      double asum = 0.0;
+      for (int w = 0; w < MERGE_THREADS / 32; ++w) asum = __dadd_rn(asum, sPartA[w]);
+      a.apartial[blockIdx.x] = asum;
+    }
     __threadfence();
     unsigned prev = atomicInc(a.counter, gridDim.x - 1);
     sLast = (prev == gridDim.x - 1);
@@ -418,6 +535,17 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     a.R[lo] = sum;
     atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
     if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
+    if (a.exact) {
+      // every element of the new row passed through at most 5 + 8 + gridDim rounded additions
+      double asum = 0.0;
+      for (int b = 0; b < (int)gridDim.x; ++b) asum = __dadd_rn(asum, ((volatile double *)a.apartial)[b]);
+      const double ab = up30(asum);
+      const double eb = up30((double)(16 + (int)gridDim.x) * EXACT_U1 * ab);
+      a.Ab[lo] = ab;
+      a.Eb[lo] = eb;
+      atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(eb));
+      atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(ab));
+    }
   }
   if (sLast && a.prune) warm_start_gbest<T, NJ>(a, lo, hi, last);
 }
@@ -488,23 +616,43 @@ __global__ void __launch_bounds__(RS_THREADS) rowsum_seq_kernel(const double *__
 }
 
 // fast NJ: initial row sums, one warp per row, fixed lane-strided order + shuffle tree
+// Eb / Ab non-null (exact mode): also the bounds of agglom_exact.cuh -- Ab = sum |d| (biased upwards), Eb = the
+// rounding error of a sum whose elements pass through at most ceil(k/32) + 5 rounded additions -- and their maxima.
 template <typename T>
 __global__ void __launch_bounds__(256) rowsum_init_kernel(const T *__restrict__ D, int64_t ld, int k,
                                                           double *__restrict__ R,
                                                           unsigned long long *rmax_bits, float *uf,
-                                                          double tinv) {
+                                                          double tinv, double *Eb, double *Ab) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= k) return;
   const T *__restrict__ r = D + (int64_t)row * ld;
-  double s = 0.0;
-  for (int j = lane; j < k; j += 32) s = __dadd_rn(s, (double)r[j]);
+  double s = 0.0, as = 0.0, dm = 0.0;
+  for (int j = lane; j < k; j += 32) {
+    const double x = (double)r[j];
+    s = __dadd_rn(s, x);
+    as = __dadd_rn(as, fabs(x));
+    dm = fmax(dm, fabs(x));
+  }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+  for (int off = 16; off > 0; off >>= 1) {
+    s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+    as = __dadd_rn(as, __shfl_down_sync(0xffffffffu, as, off));
+    dm = fmax(dm, __shfl_down_sync(0xffffffffu, dm, off));
+  }
   if (lane == 0) {
     R[row] = s;
     atomicMax(rmax_bits, (unsigned long long)__double_as_longlong(fabs(s)));
     if (uf) uf[row] = __double2float_rn(__dmul_rn(tinv, s));
+    if (Eb) {
+      const double ab = up30(as);
+      const double eb = up30((double)((k + 31) / 32 + 6) * EXACT_U1 * ab);
+      Ab[row] = ab;
+      Eb[row] = eb;
+      atomicMax(rmax_bits + XW_EBMAX, (unsigned long long)__double_as_longlong(eb));
+      atomicMax(rmax_bits + XW_ABMAX, (unsigned long long)__double_as_longlong(ab));
+      atomicMax(rmax_bits + XW_DABS, (unsigned long long)__double_as_longlong(dm));
+    }
   }
 }
 
@@ -528,20 +676,23 @@ __global__ void prune_init_kernel(unsigned *E, int64_t count, unsigned *beta, in
 }
 
 __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *order, int32_t *pos,
-                                  unsigned *counters, unsigned long long *rmax_bits) {
+                                  unsigned *counters, unsigned long long *rmax_bits, int32_t *mark,
+                                  unsigned long long *xstats) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < n) {
     ids[v] = v;
     if (sizes) sizes[v] = 1;
     if (order) { order[v] = v; pos[v] = v; }
+    if (mark) mark[v] = 0;
   }
   if (v < 16) counters[v] = 0;
-  if (v == 0) { rmax_bits[0] = 0ull; rmax_bits[2] = 0ull; rmax_bits[3] = 0ull; rmax_bits[4] = 0ull; }
+  if (v < 8 && v != 1) rmax_bits[v] = 0ull;
+  if (v < 4 && xstats) xstats[v] = 0ull;
 }
 
 __global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2, const int *error) {
   if (threadIdx.x == 0) {
-    if (error && *error) {  // a grid barrier of the persistent loop timed out
+    if (error && *error) {  // a scan found no candidate (a map without a finite entry): the join list is invalid
       last2[0] = -2;
       last2[1] = -2;
     } else if (n >= 2) {
@@ -556,15 +707,7 @@ __global__ void last2_kernel(const int32_t *ids, int n, int32_t *last2, const in
 
 // -------------------------------------------------------------------------------------
 
-// agglom_persistent.cu
-int persistent_loop(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int64_t iters, double *R,
-                    int32_t *ids, int32_t *sizes, void *cand_scratch, double *partial,
-                    unsigned long long *rmax_bits, unsigned *bar_words, int *error, int32_t *joins,
-                    cudaStream_t stream);
-size_t persistent_cand_bytes();
-
 struct AgglomWorkspace {
-  void *candx;
   double *R;
   int32_t *ids, *sizes;
   int32_t *order[2], *pos[2];
@@ -578,6 +721,8 @@ struct AgglomWorkspace {
   unsigned long long *scanned; unsigned long long *cta_read;
   int32_t *pool; int32_t *worklist; unsigned *wcount; int32_t *sugg;
   int64_t lb_stride;
+  // exact NJ mode
+  double *Eb, *Ab, *Rex, *apartial; int32_t *mark, *mlist; unsigned *mcount; unsigned long long *xstats;
   size_t bytes;
 };
 
@@ -597,7 +742,6 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.counters = c.take<unsigned>(64);
   w.rmax_bits = c.take<unsigned long long>(8);
   w.stats = w.rmax_bits + 2;
-  w.candx = c.take<char>(persistent_cand_bytes());
   w.lb_stride = ((n + SW - 1) / SW + 31) / 32 * 32;
   w.E = c.take<unsigned>((size_t)w.lb_stride * (size_t)n);
   w.beta = c.take<unsigned>((size_t)n + 32);
@@ -611,16 +755,16 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.pool = c.take<int32_t>(2 * POOL);
   w.worklist = c.take<int32_t>((size_t)n + 32);
   w.sugg = c.take<int32_t>(2 * MAX_SCAN_CTAS);
+  w.Eb = c.take<double>(n);
+  w.Ab = c.take<double>(n);
+  w.Rex = c.take<double>(n);
+  w.apartial = c.take<double>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
+  w.mark = c.take<int32_t>(n);
+  w.mlist = c.take<int32_t>(n);
+  w.mcount = c.take<unsigned>(4);
+  w.xstats = c.take<unsigned long long>(4);
   w.bytes = c.used();
   return w;
-}
-
-// CAS_PERSISTENT=1 selects the one-launch cooperative loop (agglom_persistent.cu).  It is bit-identical
-// to the multi-kernel loop but measured slightly slower on B200 (two software grid barriers cost about
-// as much as two kernel launches), so it is opt-in; tests run both and compare.
-static bool persistent_enabled() {
-  const char *e = getenv("CAS_PERSISTENT");
-  return e && e[0] == '1';
 }
 
 // Scan selection.  Default: the pruned scan for fast NJ, the dense scan for UPGMA (on tie-heavy,
@@ -666,7 +810,10 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
                       int32_t *last2, void *workspace, cudaStream_t stream) {
   AgglomWorkspace w = carve_workspace(workspace, n);
   const bool strict_nj = NJ && (mode == CAS_MODE_STRICT);
+  const bool exact_nj = NJ && (mode == CAS_MODE_EXACT) && sizeof(T) == 8;
   const bool fast_nj = NJ && (mode == CAS_MODE_FAST);
+  const bool sums_nj = fast_nj || exact_nj;    // row sums maintained incrementally
+  const bool lists_nj = strict_nj || exact_nj; // id-ordered slot list maintained (sequential sums)
   const int sms = sm_count();
   const int target_ctas = sms * 4;
 
@@ -674,13 +821,13 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (blocks == 0) blocks = 1;
     init_state_kernel<<<blocks, 256, 0, stream>>>((int)n, w.ids, NJ ? nullptr : w.sizes,
-                                                  strict_nj ? w.order[0] : nullptr,
-                                                  strict_nj ? w.pos[0] : nullptr, w.counters,
-                                                  w.rmax_bits);
+                                                  lists_nj ? w.order[0] : nullptr,
+                                                  lists_nj ? w.pos[0] : nullptr, w.counters,
+                                                  w.rmax_bits, exact_nj ? w.mark : nullptr, w.xstats);
     CAS_LAUNCH_CHECK();
+    CAS_CUDA_TRY(cudaMemsetAsync(w.mcount, 0, 4 * sizeof(unsigned), stream));
   }
-  // the opt-in persistent experiment (CAS_PERSISTENT=1) keeps its dense scan
-  const bool prune = !strict_nj && prune_enabled(NJ) && n > 2 && !persistent_enabled();
+  const bool prune = !strict_nj && prune_enabled(NJ) && n > 2;
   const int min_k = prune_min_k();
   // CAS_PRUNE_WIDE=0: every listed row in short units (the behaviour before the split work list)
   const int prune_wide = getenv("CAS_PRUNE_WIDE") ? (atoi(getenv("CAS_PRUNE_WIDE")) != 0) : 1;
@@ -691,28 +838,18 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
   } else {
     CAS_CUDA_TRY(cudaMemsetAsync(w.scanned, 0, sizeof(unsigned long long), stream));
   }
-  if (fast_nj && n > 2) {
-    rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>((const T *)D, ld, (int)n, w.R, w.rmax_bits,
-                                                                        prune ? w.uf : nullptr,
-                                                                        1.0 / (double)(n - 2));
+  if (sums_nj && n > 2) {
+    rowsum_init_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(
+        (const T *)D, ld, (int)n, w.R, w.rmax_bits, prune ? w.uf : nullptr, 1.0 / (double)(n - 2),
+        exact_nj ? w.Eb : nullptr, exact_nj ? w.Ab : nullptr);
     CAS_LAUNCH_CHECK();
   }
+  ExactArgs ex{};
+  ex.Eb = w.Eb; ex.Ab = w.Ab; ex.xw = w.rmax_bits; ex.mark = w.mark; ex.mlist = w.mlist; ex.Rex = w.Rex;
+  ex.mcount = w.mcount; ex.xstats = w.xstats;
   int64_t k_final = n;
-  const int64_t total_iters = n > 2 ? ((max_iters >= 0 && max_iters < n - 2) ? max_iters : n - 2) : 0;
-  bool done_persistent = false;
-  if (!strict_nj && total_iters > 0 && persistent_enabled()) {
-    // whole loop in one cooperative launch (agglom_persistent.cu)
-    int rc = persistent_loop(D, n, ld, sizeof(T) == 8 ? CAS_F64 : CAS_F32, NJ ? CAS_ALGO_NJ : CAS_ALGO_UPGMA,
-                             total_iters, w.R, w.ids, w.sizes, w.candx, w.partial, w.rmax_bits, w.counters + 4,
-                             (int *)(w.counters + 6), joins, stream);
-    if (rc == CAS_OK) {
-      done_persistent = true;
-      k_final = n - total_iters;
-    } else if (rc != CAS_ERR_UNSUPPORTED) {
-      return rc;
-    }
-  }
-  for (int64_t t = 0; !done_persistent && t + 2 < n; ++t) {
+  bool was_pruned = false;
+  for (int64_t t = 0; t + 2 < n; ++t) {
     if (max_iters >= 0 && t >= max_iters) break;
     const int k = (int)(n - t);
     k_final = k - 1;
@@ -730,18 +867,35 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     sa.rmax_bits = w.rmax_bits;
     sa.stats = w.stats;
     sa.cand = w.cand; sa.counter = w.counters + 0; sa.sel = w.sel; sa.joins = joins; sa.t = (int)t;
+    sa.error = (int *)(w.counters + 6);
+    sa.exact = exact_nj ? 1 : 0;
+    sa.ex = ex;
+    sa.ex.order = w.order[cur];
     int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
     if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
     if (grid < 1) grid = 1;
     // below ~3k live nodes the map is L2-resident and the dense scan's two launches per iteration
     // beat the pruned scan's three; the switch is one-way, so the bounds need no further maintenance
     const bool prune_it = prune && k > min_k;
+    if (exact_nj && was_pruned && !prune_it) {
+      // exact mode, at the one-way switch to the dense scan: re-accumulate the maintained sums of the k live rows.
+      // Their error bounds restart from a fresh summation and the running maxima from the live rows, so the error
+      // window stays far below the near-tie window while 1/(k-2) grows towards 1.
+      CAS_CUDA_TRY(cudaMemsetAsync(w.rmax_bits, 0, sizeof(unsigned long long), stream));
+      CAS_CUDA_TRY(cudaMemsetAsync(w.rmax_bits + XW_EBMAX, 0, 3 * sizeof(unsigned long long), stream));
+      rowsum_init_kernel<T><<<(unsigned)((k + 7) / 8), 256, 0, stream>>>((const T *)D, ld, k, w.R, w.rmax_bits, nullptr,
+                                                                          sa.tinv, w.Eb, w.Ab);
+      CAS_LAUNCH_CHECK();
+    }
+    was_pruned = prune_it;
     if (prune_it) {
       PruneArgs pa{};
       pa.E = w.E; pa.stride = w.lb_stride; pa.beta = w.beta; pa.uf = w.uf; pa.hdr = w.hdr; pa.dmax = w.dmax;
       pa.gbest = w.gbest; pa.worklist = w.worklist; pa.wcount = w.wcount; pa.sugg = w.sugg;
       pa.scanned = w.scanned; pa.cta_read = w.cta_read;
       pa.split = 1; pa.wide = prune_wide; pa.wlast = (int)n + 31;
+      pa.xw = exact_nj ? w.rmax_bits : nullptr;
+      pa.rmaxb = NJ ? w.rmax_bits : nullptr;
       CAS_CUDA_TRY(launch_pdl(prune_rowtest_kernel<T, NJ>, (unsigned)((k + 255) / 256), 256u, stream, pa,
                               (const T *)D, ld, k, (const double *)w.R, sa.tinv, (const Sel *)w.sel, t > 0 ? 1 : 0));
       CAS_LAUNCH_CHECK();
@@ -755,15 +909,16 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     MergeArgs ma;
     ma.D = D; ma.ld = ld; ma.k = k; ma.sel = w.sel; ma.R = w.R; ma.ids = w.ids;
     ma.sizes = NJ ? nullptr : w.sizes; ma.partial = w.partial; ma.counter = w.counters + 1;
-    ma.new_id = (int)(n + t); ma.maintain_R = fast_nj ? 1 : 0; ma.rmax_bits = w.rmax_bits;
-    ma.order_old = strict_nj ? w.order[cur] : nullptr;
-    ma.pos_old = strict_nj ? w.pos[cur] : nullptr;
-    ma.order_new = strict_nj ? w.order[cur ^ 1] : nullptr;
-    ma.pos_new = strict_nj ? w.pos[cur ^ 1] : nullptr;
+    ma.new_id = (int)(n + t); ma.maintain_R = sums_nj ? 1 : 0; ma.rmax_bits = w.rmax_bits;
+    ma.order_old = lists_nj ? w.order[cur] : nullptr;
+    ma.pos_old = lists_nj ? w.pos[cur] : nullptr;
+    ma.order_new = lists_nj ? w.order[cur ^ 1] : nullptr;
+    ma.pos_new = lists_nj ? w.pos[cur ^ 1] : nullptr;
     ma.prune = prune_it ? 1 : 0; ma.uf = w.uf; ma.dmax = w.dmax;
     ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
     ma.cand = w.cand; ma.ncand = grid; ma.sugg = w.sugg; ma.gbest = w.gbest; ma.pool = w.pool;
     ma.rot = (int)((t * 61) % POOL);
+    ma.exact = exact_nj ? 1 : 0; ma.Eb = w.Eb; ma.Ab = w.Ab; ma.xw = w.rmax_bits; ma.apartial = w.apartial;
     if (prune_it) {
       CAS_CUDA_TRY(launch_pdl(merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
                               (unsigned)MERGE_THREADS, stream, ma));
@@ -822,6 +977,7 @@ __global__ void smj_negate_kernel(double *D, int64_t count) {
 // LCA row of the joined pair: all missing -> missing; one missing -> the other; equal -> that; else 0
 __global__ void smj_lca_kernel(SmjArgs a) {
   const Sel s = *a.sel;
+  if (s.lo < 0) return;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.m; c += gridDim.x * blockDim.x) {
     const int32_t x = a.chars[(int64_t)c * a.cap + s.lo], y = a.chars[(int64_t)c * a.cap + s.hi];
     a.lca[c] = (x == a.missing) ? y : (y == a.missing) ? x : (x == y ? x : 0);
@@ -864,6 +1020,7 @@ __device__ __forceinline__ double smj_pair(const SmjArgs &a, int v) {
 
 __global__ void __launch_bounds__(MERGE_THREADS) smj_update_kernel(SmjArgs a) {
   const Sel s = *a.sel;
+  if (s.lo < 0) return;
   const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1;
   const int64_t ld = a.ld;
   double *__restrict__ D = a.D;
@@ -920,7 +1077,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
   {
     unsigned blocks = (unsigned)((n + 255) / 256);
     init_state_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>((int)n, wk.ids, nullptr, nullptr, nullptr, wk.counters,
-                                                               wk.rmax_bits);
+                                                               wk.rmax_bits, nullptr, wk.xstats);
     CAS_LAUNCH_CHECK();
     const int64_t nm = n * (int64_t)m;
     smj_transpose_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, stream>>>(cm, n, m, chars, n);
@@ -939,7 +1096,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
     plan_scan(k, target_ctas, sa.tr, sa.nrb, sa.ncb, sa.ntiles);
     sa.R = wk.R; sa.ids = wk.ids; sa.sizes = nullptr; sa.tinv = 0.0; sa.rmax_bits = wk.rmax_bits;
     sa.stats = wk.stats; sa.cand = wk.cand; sa.counter = wk.counters + 0; sa.sel = wk.sel; sa.joins = joins;
-    sa.t = (int)t;
+    sa.t = (int)t; sa.exact = 0; sa.ex = ExactArgs{}; sa.error = (int *)(wk.counters + 6);
     int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
     if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
     if (grid < 1) grid = 1;
@@ -953,7 +1110,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
     smj_update_kernel<<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ua);
     CAS_LAUNCH_CHECK();
   }
-  last2_kernel<<<1, 32, 0, stream>>>(wk.ids, (int)(k_final < 2 ? k_final : 2), last2, nullptr);
+  last2_kernel<<<1, 32, 0, stream>>>(wk.ids, (int)(k_final < 2 ? k_final : 2), last2, (const int *)(wk.counters + 6));
   CAS_LAUNCH_CHECK();
   return CAS_OK;
 }
@@ -964,8 +1121,8 @@ int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, in
   CAS_REQUIRE(n >= 1 && n < (int64_t)1 << 30, "n=%lld out of range", (long long)n);
   CAS_REQUIRE(ld >= n && ld % 32 == 0, "ld=%lld must be >= n and a multiple of 32", (long long)ld);
   CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
-  CAS_REQUIRE(mode == CAS_MODE_STRICT || mode == CAS_MODE_FAST, "bad mode %d", mode);
-  CAS_REQUIRE(!(mode == CAS_MODE_STRICT && dtype != CAS_F64), "strict mode requires a float64 map");
+  CAS_REQUIRE(mode == CAS_MODE_STRICT || mode == CAS_MODE_FAST || mode == CAS_MODE_EXACT, "bad mode %d", mode);
+  CAS_REQUIRE(!(mode != CAS_MODE_FAST && dtype != CAS_F64), "strict and exact modes require a float64 map");
   CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(n), "workspace too small for agglomeration");
   CAS_REQUIRE(((uintptr_t)D & 15) == 0, "D must be 16-byte aligned");
   if (algo == CAS_ALGO_NJ) {
@@ -1001,6 +1158,17 @@ int agglom_read_prune_diag(const void *workspace, int64_t n, cudaStream_t stream
   CAS_CUDA_TRY(cudaStreamSynchronize(stream));
   if (rows_listed) *rows_listed = (int64_t)h;
   if (drift) *drift = (double)c;
+  return CAS_OK;
+}
+
+// exact-mode diagnostics: ambiguous iterations, rows whose sequential sum was evaluated, largest row set,
+// iterations whose pair differs from the arg-min of the maintained criterion
+int agglom_read_exact_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *out4) {
+  AgglomWorkspace w = carve_workspace(const_cast<void *>(workspace), n > 0 ? n : 1);
+  unsigned long long h[4] = {0, 0, 0, 0};
+  CAS_CUDA_TRY(cudaMemcpyAsync(h, w.xstats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize(stream));
+  for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
   return CAS_OK;
 }
 

@@ -127,6 +127,48 @@ __device__ __forceinline__ double dec_f64(unsigned long long e) {
   return __longlong_as_double((long long)((e >> 63) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e));
 }
 
+// ---- "exact" (adaptive strict) NJ mode -----------------------------------------------------------------
+// The reference re-accumulates every row sum sequentially each iteration (NeighborJoiningSolver.py:160).  The
+// exact mode MAINTAINS the sums (R_v += new - d_vi - d_vj) together with rigorous bounds
+//     |R_v - S_v| <= Eb_v      (S_v the real-number row sum; Eb_v accumulates u'|x| for every rounded result x)
+//     sum_j |d_vj| <= Ab_v     (kept with upward-biased arithmetic)
+// so that the reference's sequential sum rs_v (k - 1 rounded additions) obeys |rs_v - R_v| <= Ebmax + k u' Abmax
+// =: delta, and the reference criterion q and the maintained one q~ differ by at most
+//     Delta = 2 t delta + 8 u' (dmax + 2 t (Rmax + delta)),      t = 1 / (k - 2).
+// A pair whose q~ exceeds the smallest q~ by more than W = 2 Delta can neither win nor tie under the reference's
+// arithmetic; if exactly one pair lies inside the window it is the reference's pair, otherwise the sequential sums
+// of just the rows involved are evaluated (exact_resolve) and the reference's rule decides.  The running maxima
+// live next to the |row sum| maximum: xw[0] = Rmax, xw[5] = Ebmax, xw[6] = Abmax, xw[7] = max |d| (bit patterns of
+// non-negative doubles, maintained with atomicMax).  oracle/oracle.c: oracle_nj_adaptive is the CPU model.
+constexpr double EXACT_U1 = 1.1102230246251565e-16 * (1.0 + 9.5367431640625e-07);  // 2^-53 (1 + 2^-20)
+constexpr int XW_EBMAX = 5, XW_ABMAX = 6, XW_DABS = 7;
+
+__device__ __forceinline__ double exact_window(const unsigned long long *xw, int k, double tinv) {
+  const double rmax = __longlong_as_double((long long)__ldcg(xw + 0));
+  const double eb = __longlong_as_double((long long)__ldcg(xw + XW_EBMAX));
+  const double ab = __longlong_as_double((long long)__ldcg(xw + XW_ABMAX));
+  const double dm = __longlong_as_double((long long)__ldcg(xw + XW_DABS));
+  const double delta = eb + (double)k * EXACT_U1 * ab;
+  const double Delta = 2.0 * tinv * delta + 8.0 * EXACT_U1 * (dm + 2.0 * tinv * (rmax + delta));
+  return 2.0 * Delta * 1.0001;
+}
+// near-tie window of the diagnostics (1e-6 relative, absolute below 1) around x, never narrower than `wfloor`
+// (exact mode: twice the error window, so that every pair the resolver may need has been evaluated)
+__device__ __forceinline__ double near_window(double x, double wfloor) {
+  return fmax(1.0000001e-6 * fmax(1.0, fabs(x)), wfloor);
+}
+__device__ __forceinline__ double up30(double x) { return x * (1.0 + 9.313225746154785e-10); }  // x (1 + 2^-30), x >= 0
+// all lanes: raise the running maximum *dst to the largest non-negative x of the warp
+__device__ __forceinline__ void warp_atomic_max_nonneg(unsigned long long *dst, double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, b, off);
+    b = o > b ? o : b;
+  }
+  if ((threadIdx.x & 31) == 0 && b > __ldcg(dst)) atomicMax(dst, b);
+}
+
 template <typename T> __device__ __forceinline__ T round_to(double v);
 template <> __device__ __forceinline__ float round_to<float>(double v) { return __double2float_rn(v); }
 template <> __device__ __forceinline__ double round_to<double>(double v) { return v; }
@@ -140,7 +182,7 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
                                                  int lane, const float *sU, const double *R,
                                                  double Ri, double tinv, double umax,
                                                  const int32_t *ids, double &bq, int &bi,
-                                                 int &bj, double &b2) {
+                                                 int &bj, double &b2, double wfloor = 0.0) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;          // independent 128-bit loads in flight per lane
   constexpr int STEP = 32 * V;  // elements per warp-wide load
@@ -150,7 +192,7 @@ __device__ __forceinline__ void scan_row_segment(const T *row, int i, int c0, in
     if (bi < 0) return INFINITY;
     if (!NJ) return __double2float_ru(bq);
     const double B = bq + ui;
-    return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + 1e-300);
+    return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + wfloor + 1e-300);
   };
   float thr = threshold();
   for (int jb = c0; jb < jend; jb += STEP * U) {

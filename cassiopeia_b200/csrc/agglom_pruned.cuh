@@ -51,7 +51,19 @@ struct PruneArgs {
   int32_t *sugg;              // [gridDim][2] per-CTA suggestion (slots) for the pool
   unsigned long long *scanned;   // statistics: map elements actually read
   unsigned long long *cta_read;  // [gridDim] per-CTA counts of this launch (summed by the last CTA)
+  const unsigned long long *xw;  // exact NJ mode: running maxima behind exact_window() (agglom_common.cuh); else null
+  const unsigned long long *rmaxb;  // NJ: bits of the running max |row sum| (umax = tinv * that bounds every |u_j|)
 };
+
+// largest |u_j| of any column (NJ), as a float rounded up; 0 for UPGMA
+__device__ __forceinline__ float prune_umaxf(const PruneArgs &p, double tinv) {
+  return p.rmaxb ? __double2float_ru(tinv * __longlong_as_double((long long)__ldcg(p.rmaxb))) : 0.f;
+}
+
+// floor of the near-tie window: twice the exact mode's error window (0 in the other modes)
+__device__ __forceinline__ double prune_wfloor(const PruneArgs &p, int k, double tinv) {
+  return p.xw ? 2.0 * exact_window(p.xw, k, tinv) : 0.0;
+}
 
 // C as of THIS scan: identical in every thread of every kernel of the iteration (two scalar loads)
 __device__ __forceinline__ float prune_cnow(const PruneArgs &p) {
@@ -82,20 +94,19 @@ struct RowScan {
   double cap;  // gbest + near-tie window: pairs above it cannot win, tie or be a near-tie runner-up, so the
                // (slow, serial) exact evaluation stops there
   float thr, uif;
+  double wfloor;  // floor of the near-tie window (exact mode; else 0)
   // cheap "suggestion" for the pool: the lane's smallest float32-screened criterion over everything it read
   float sbest;
   int ssi, ssj;
-  // near-tie window of the diagnostics (1e-6 relative, absolute below 1) around the value x
-  static __device__ __forceinline__ double window(double x) { return 1.0000001e-6 * fmax(1.0, fabs(x)); }
   __device__ __forceinline__ float threshold() const {
     const double best = bi >= 0 ? fmin(bq, cap) : cap;
     if (best == INFINITY) return INFINITY;
     if (!NJ) return __double2float_ru(best);
     const double B = best + ui;
-    return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + 1e-300);
+    return __double2float_ru(B + 9.5367431640625e-07 * (umax + fabs(B)) + wfloor + 1e-300);
   }
   __device__ __forceinline__ void set_cap(double gb) {
-    const double c = gb + window(gb) + 1e-9 * fabs(gb);
+    const double c = gb + near_window(gb, wfloor) + 1e-9 * fabs(gb);
     if (c < cap) { cap = c; thr = threshold(); }
   }
   __device__ __forceinline__ void set_row(int row, double ri) {
@@ -145,10 +156,13 @@ struct RowScan {
 
 // "a row / sub-segment with bound b (already minus C) and own u cannot hold a competitive pair":
 // false while gbest = +inf or the bound is -inf (unknown)
+// The slack covers every float32 rounding on either side of the comparison, including that of the column term
+// itself (the bounds are on d - fl32(u_j), the criterion uses u_j: up to 2^-24 umax apart).
 template <typename T, bool NJ>
-__device__ __forceinline__ bool prune_impossible(float e, float cnow, float uif, double gb) {
-  const float gbw = __double2float_ru(gb + RowScan<T, NJ>::window(gb));
-  const float mag = fabsf(gbw) + fabsf(uif) + fabsf(e) + cnow;
+__device__ __forceinline__ bool prune_impossible(float e, float cnow, float uif, double gb, double wfloor,
+                                                 float umaxf) {
+  const float gbw = __double2float_ru(gb + near_window(gb, wfloor));
+  const float mag = fabsf(gbw) + fabsf(uif) + fabsf(e) + cnow + umaxf;
   return (e - cnow) > (gbw + uif) + 2e-6f * mag;
 }
 
@@ -157,7 +171,8 @@ __device__ __forceinline__ bool prune_impossible(float e, float cnow, float uif,
 // prev_* = slots of the previous join (prev_lo < 0: none yet; prev_moved: a node moved into slot prev_hi).
 template <typename T, bool NJ>
 __device__ __forceinline__ void prune_rowtest(const PruneArgs &p, bool valid, int64_t ridx, int i, const T *row,
-                                              double Ri, double tinv, int prev_lo, int prev_hi, bool prev_moved) {
+                                              double Ri, double tinv, int prev_lo, int prev_hi, bool prev_moved,
+                                              double wfloor = 0.0) {
   const float cnow = prune_cnow(p);
   bool unsafe = false, unknown = false;
   if (valid) {
@@ -181,7 +196,8 @@ __device__ __forceinline__ void prune_rowtest(const PruneArgs &p, bool valid, in
       }
     }
     const double gb = dec_f64(__ldcg(p.gbest));
-    unsafe = !prune_impossible<T, NJ>(dec_f32(b), cnow, NJ ? (float)(tinv * Ri) : 0.f, gb);
+    unsafe = !prune_impossible<T, NJ>(dec_f32(b), cnow, NJ ? (float)(tinv * Ri) : 0.f, gb, wfloor,
+                                      prune_umaxf(p, tinv));
     // an unsafe row's beta is rebuilt by its work units (atomicMin)
     p.beta[ridx] = unsafe ? enc_f32(INFINITY) : b;
   }
@@ -234,7 +250,7 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
     const int sgm = sb + lane;
     const bool exists = lane < unit && sgm < nsub;
     const unsigned e = exists ? erow[sgm] : enc_f32(INFINITY);
-    const bool skip = prune_impossible<T, NJ>(dec_f32(e), cnow, rs.uif, gb);
+    const bool skip = prune_impossible<T, NJ>(dec_f32(e), cnow, rs.uif, gb, rs.wfloor, (float)rs.umax * 1.0000002f);
     need = exists && !skip;
     if (exists && skip) kept = e;
   }

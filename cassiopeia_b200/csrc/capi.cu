@@ -60,6 +60,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
               int32_t fn, double *D, int64_t ld, int64_t max_iters, int32_t *joins, int32_t *last2,
               void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements);
+int agglom_read_exact_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *out4);
 int agglom_read_prune_diag(const void *workspace, int64_t n, cudaStream_t stream, int64_t *rows_listed, double *drift);
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
@@ -169,6 +170,11 @@ int cas_smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
                    workspace_bytes, (cudaStream_t)stream);
 }
 
+int cas_agglom_exact_stats(const void *workspace, int64_t n, void *stream, int64_t *out4) {
+  CAS_REQUIRE(workspace && out4, "null pointer argument");
+  return agglom_read_exact_stats(workspace, n, (cudaStream_t)stream, out4);
+}
+
 int cas_agglom_scanned_elements(const void *workspace, int64_t n, void *stream, int64_t *elements) {
   CAS_REQUIRE(workspace, "null pointer argument");
   return agglom_read_scanned(workspace, n, (cudaStream_t)stream, elements);
@@ -212,7 +218,7 @@ int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t missing
   CAS_REQUIRE(cm_host && joins_host && last2_host, "null pointer argument");
   CAS_REQUIRE(n >= 2 && m >= 1, "need at least two samples (n=%lld, m=%d)", (long long)n, m);
   CAS_REQUIRE(algo == CAS_ALGO_NJ || algo == CAS_ALGO_UPGMA, "bad algo %d", algo);
-  const int dtype = (mode == CAS_MODE_STRICT) ? CAS_F64 : CAS_F32;
+  const int dtype = (mode == CAS_MODE_FAST) ? CAS_F32 : CAS_F64;
   const size_t esz = dtype == CAS_F64 ? 8 : 4;
   const int64_t ld = (int64_t)align_up((size_t)n, 32);
   const bool weighted = w_host != nullptr;

@@ -812,6 +812,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
         pa.E = rk.w.E; pa.stride = rk.w.lb_stride; pa.beta = rk.w.beta; pa.uf = rk.w.uf; pa.hdr = rk.w.hdr;
         pa.dmax = rk.w.dmax; pa.gbest = rk.w.gbest; pa.worklist = rk.w.worklist; pa.wcount = rk.w.wcount;
         pa.sugg = rk.w.sugg; pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;
+        pa.rmaxb = NJ ? rk.w.rmax_bits : nullptr;
         CAS_CUDA_TRY(launch_pdl(sh_rowtest_kernel<T, NJ>, (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1),
                                 256u, stream, pa, (const T *)rk.D, ld, k, G, rk.r, (const double *)rk.w.R, sa.tinv,
                                 (const Sel *)rk.w.sel, t > 0 ? 1 : 0));

@@ -13,10 +13,12 @@ import numpy as np
 
 from . import _lib
 from ._lib import (CAS_ALGO_NJ, CAS_ALGO_UPGMA, CAS_F32, CAS_F64, CAS_MAP_EXACT, CAS_MAP_TENSOR,
-                   CAS_MODE_FAST, CAS_MODE_STRICT, B200LibraryError)
+                   CAS_MODE_EXACT, CAS_MODE_FAST, CAS_MODE_STRICT, B200LibraryError)
 
 _ALGO = {"nj": CAS_ALGO_NJ, "upgma": CAS_ALGO_UPGMA}
-_MODE = {"strict": CAS_MODE_STRICT, "fast": CAS_MODE_FAST}
+#: loop arithmetic (include/cas_b200.h).  "exact" and "strict" both reproduce the reference's join list; "exact"
+#: evaluates the reference's sequential row sums only where the maintained sums cannot decide.
+_MODE = {"strict": CAS_MODE_STRICT, "fast": CAS_MODE_FAST, "exact": CAS_MODE_EXACT}
 _METHOD = {"exact": CAS_MAP_EXACT, "tensor": CAS_MAP_TENSOR}
 
 
@@ -50,7 +52,8 @@ def device_info() -> dict:
 
 #: diagnostics of the most recent `agglomerate` call: near / exact ties and the number of map elements the
 #: pruned scan actually read (0 for the dense scan, which reads k(k-1)/2 per iteration)
-last_stats = {"near_ties": 0, "exact_ties": 0, "scanned_elements": 0, "rows_listed": 0, "drift": 0.0}
+last_stats = {"near_ties": 0, "exact_ties": 0, "scanned_elements": 0, "rows_listed": 0, "drift": 0.0,
+              "ambiguous_iterations": 0, "rows_resolved": 0, "max_rows_resolved": 0, "pairs_changed": 0}
 
 
 def last_launch_count() -> int:
@@ -160,11 +163,15 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     _lib.check(L.cas_agglom_prune_diag(ws.data_ptr(), int(n), _stream_ptr(torch), ctypes.byref(listed),
                                        ctypes.byref(drift)), "cas_agglom_prune_diag")
     last_stats["rows_listed"], last_stats["drift"] = int(listed.value), float(drift.value)
+    x4 = (ctypes.c_int64 * 4)()
+    _lib.check(L.cas_agglom_exact_stats(ws.data_ptr(), int(n), _stream_ptr(torch), x4), "cas_agglom_exact_stats")
+    (last_stats["ambiguous_iterations"], last_stats["rows_resolved"], last_stats["max_rows_resolved"],
+     last_stats["pairs_changed"]) = (int(v) for v in x4)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     joins_h = joins[:done].cpu().numpy()
     last2_h = last2.cpu().numpy()
     if last2_h[0] == -2:
-        raise B200LibraryError("a grid barrier of the persistent loop kernel timed out")
+        raise B200LibraryError("the loop found no finite entry to join (is the dissimilarity map all NaN / inf?)")
     return joins_h, last2_h
 
 

@@ -32,7 +32,10 @@ from ..data import utilities as data_utilities
 from ..mixins import DistanceSolverError
 from . import dissimilarity_functions, solver_utilities
 
-B200_IMPLEMENTATIONS = ("b200_strict", "b200_fast")
+#: "b200_exact" (default): the reference's join list from maintained row sums + sequential sums only where needed;
+#: "b200_strict": the reference's arithmetic literally (every row sum re-accumulated every iteration; verification);
+#: "b200_fast": float32 map, maintained sums -- the reference's tree only when no near-tie occurs.
+B200_IMPLEMENTATIONS = ("b200_exact", "b200_strict", "b200_fast")
 
 
 class DistanceSolver(abc.ABC):
@@ -43,7 +46,7 @@ class DistanceSolver(abc.ABC):
     def __init__(self, dissimilarity_function: Optional[Callable] = dissimilarity_functions.weighted_hamming_distance,
                  add_root: bool = False, prior_transformation: str = "negative_log", threads: int = 1):
         if not hasattr(self, "_implementation"):
-            self._implementation = "b200_strict"
+            self._implementation = "b200_exact"
         self.prior_transformation = prior_transformation
         self.dissimilarity_function = dissimilarity_function
         self.add_root = add_root
@@ -54,7 +57,7 @@ class DistanceSolver(abc.ABC):
     # ----------------------------------------------------------- configuration
     @property
     def precision(self) -> str:
-        return "fast" if self._implementation == "b200_fast" else "strict"
+        return {"b200_fast": "fast", "b200_strict": "strict"}.get(self._implementation, "exact")
 
     @property
     def _map_dtype(self) -> str:

@@ -18,11 +18,14 @@ from .DistanceSolver import B200_IMPLEMENTATIONS, DistanceSolver
 class NeighborJoiningSolver(DistanceSolver):
     """Saitou-Nei Neighbor-Joining.
 
-    Constructor keywords are the reference's (:68-98).  ``fast=False`` (default) selects the
-    reference-exact arithmetic (float64 map, per-iteration sequential row sums, no FMA:
-    identical join sequence); ``fast=True`` with ``implementation="b200_fast"`` selects the
-    float32 map with incrementally maintained row sums.  The reference's CCPhylo
-    implementations are an external binary and are not available here.
+    Constructor keywords are the reference's (:68-98).  ``fast=False`` (default) produces the reference's
+    join sequence (``"b200_exact"``: float64 map, no FMA, row sums maintained incrementally under rigorous
+    error bounds, the reference's sequential ``d.sum(axis=1)`` evaluated only for the rows of pairs the
+    maintained sums cannot separate -- DESIGN 4.3).  ``fast=True`` selects ``implementation``:
+    ``"b200_fast"`` (float32 map, maintained sums: the reference's tree whenever no near-tie occurs),
+    ``"b200_exact"`` or ``"b200_strict"`` (every row sum re-accumulated sequentially every iteration, the
+    reference's arithmetic literally; same joins as ``"b200_exact"``, kept for verification).  The reference's
+    CCPhylo implementations are an external binary and are not available here.
     """
 
     _algo = "nj"
@@ -36,12 +39,12 @@ class NeighborJoiningSolver(DistanceSolver):
             elif implementation in ("ccphylo_dnj", "ccphylo_hnj", "ccphylo_nj"):
                 raise DistanceSolverError(
                     f"'{implementation}' needs the external CCPhylo binary, which this build does not "
-                    "wrap. Options are: 'b200_fast', 'b200_strict'")
+                    "wrap. Options are: 'b200_fast', 'b200_exact', 'b200_strict'")
             else:
                 raise DistanceSolverError(
-                    "Invalid fast implementation of Neighbor-Joining. Options are: 'b200_fast', 'b200_strict'")
+                    "Invalid fast implementation of Neighbor-Joining. Options are: 'b200_fast', 'b200_exact', 'b200_strict'")
         else:
-            self._implementation = "b200_strict"
+            self._implementation = "b200_exact"
         super().__init__(dissimilarity_function=dissimilarity_function, add_root=add_root,
                          prior_transformation=prior_transformation, threads=threads)
 

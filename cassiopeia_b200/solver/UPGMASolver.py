@@ -16,7 +16,7 @@ class UPGMASolver(DistanceSolver):
 
     Constructor keywords are the reference's (:56-87); see ``NeighborJoiningSolver`` for the
     meaning of ``fast`` / ``implementation``.  UPGMA values involve no reductions, so the
-    float64 ("b200_strict") path reproduces the reference bit for bit at any size.
+    float64 paths ("b200_exact" = "b200_strict" here) reproduce the reference bit for bit at any size.
     """
 
     _algo = "upgma"
@@ -30,12 +30,12 @@ class UPGMASolver(DistanceSolver):
             elif implementation == "ccphylo_upgma":
                 raise DistanceSolverError(
                     "'ccphylo_upgma' needs the external CCPhylo binary, which this build does not wrap. "
-                    "Options are: 'b200_fast', 'b200_strict'")
+                    "Options are: 'b200_fast', 'b200_exact', 'b200_strict'")
             else:
                 raise DistanceSolverError(
-                    "Invalid fast implementation of UPGMA. Options are: 'b200_fast', 'b200_strict'")
+                    "Invalid fast implementation of UPGMA. Options are: 'b200_fast', 'b200_exact', 'b200_strict'")
         else:
-            self._implementation = "b200_strict"
+            self._implementation = "b200_exact"
         super().__init__(dissimilarity_function=dissimilarity_function, add_root=True,
                          prior_transformation=prior_transformation, threads=threads)
         self._cluster_to_cluster_size = defaultdict(int)

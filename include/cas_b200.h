@@ -56,6 +56,11 @@ extern "C" {
  *   FAST  : float32 (or float64) map, NJ row sums maintained incrementally in float64. */
 #define CAS_MODE_STRICT 0
 #define CAS_MODE_FAST 1
+/*   EXACT : float64 map; NJ row sums maintained incrementally together with rigorous error bounds;
+ *           the reference's sequential sums are evaluated only for the rows of pairs that fall
+ *           inside the error window of the minimum.  Same join list as STRICT (= the reference's)
+ *           at the cost of the FAST loop.  For UPGMA (no sums) identical to STRICT. */
+#define CAS_MODE_EXACT 2
 /* dissimilarity-map kernel:
  *   EXACT : CUDA-core kernel, float64 accumulation in character order (bit-exact vs reference)
  *   TENSOR: one-hot contraction on tcgen05 tensor cores (int8 unweighted / split-bf16 weighted) */
@@ -222,6 +227,12 @@ CAS_API int cas_update_map(const double *D_dev, int64_t n, int64_t ld, int32_t a
  * Counted by the multi-kernel single-GPU loop. */
 CAS_API int cas_agglom_stats(const void *workspace_dev, int64_t n, void *stream, int64_t *near_ties,
                      int64_t *exact_ties);
+
+/* CAS_MODE_EXACT diagnostics of the last NJ loop run with this workspace (synchronises the stream):
+ * out4[0] iterations in which a second pair lay inside the error window (resolved with sequential sums),
+ * out4[1] rows whose sequential sum was evaluated, out4[2] largest such row set in one iteration,
+ * out4[3] iterations whose pair differs from the arg-min of the maintained criterion. */
+CAS_API int cas_agglom_exact_stats(const void *workspace_dev, int64_t n, void *stream, int64_t *out4);
 
 /* Map elements the scan kernels of the last loop run with this workspace actually read (synchronises
  * the stream).  The pruned scan (default for every mode but strict NJ; CAS_PRUNE=0 selects the dense

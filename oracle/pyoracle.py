@@ -47,6 +47,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_nj.argtypes = [vp, i64, vp, vp, i64, ctypes.c_int]
         L.oracle_upgma.restype = ctypes.c_int
         L.oracle_upgma.argtypes = [vp, i64, vp, vp, i64, ctypes.c_int]
+        L.oracle_nj_adaptive.restype = ctypes.c_int
+        L.oracle_nj_adaptive.argtypes = [vp, i64, vp, vp, vp, ctypes.c_int]
         L.oracle_max_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -210,6 +212,23 @@ def nj(D: np.ndarray, max_iters: int = -1, threads: int = 0):
 
 def upgma(D: np.ndarray, max_iters: int = -1, threads: int = 0):
     return _loop(lib().oracle_upgma, D, max_iters, threads)
+
+
+def nj_adaptive(D: np.ndarray, threads: int = 0):
+    """CPU model of the product's adaptive-strict NJ loop (maintained row sums + rigorous error window +
+    sequential sums only for the rows of ambiguous pairs).  Returns (joins, last2, stats) with stats =
+    {ambiguous_iterations, rows_resolved, max_rows, max_window, winner_changed}."""
+    D = np.array(D, dtype=np.float64, order="C", copy=True)
+    n = D.shape[0]
+    joins = np.full((max(n - 2, 0), 2), -1, dtype=np.int32)
+    last2 = np.full(2, -1, dtype=np.int32)
+    st = np.zeros(5, dtype=np.int64)
+    rc = lib().oracle_nj_adaptive(D.ctypes.data, n, joins.ctypes.data, last2.ctypes.data, st.ctypes.data, int(threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle_nj_adaptive failed rc={rc}")
+    stats = {"ambiguous_iterations": int(st[0]), "rows_resolved": int(st[1]), "max_rows": int(st[2]),
+             "max_window": float(st[3:4].view(np.float64)[0]), "winner_changed": int(st[4])}
+    return joins, last2, stats
 
 
 def smj(fn: str, cm: np.ndarray, missing: int = -1, table: Optional[np.ndarray] = None):

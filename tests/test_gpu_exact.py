@@ -1,0 +1,139 @@
+"""The "exact" (adaptive strict) NJ mode == the reference's join list.
+
+The reference re-accumulates every row sum sequentially each iteration (NeighborJoiningSolver.py:158-171); the
+exact mode maintains the sums under rigorous error bounds and evaluates sequential sums only for the rows of
+pairs inside the error window of the minimum (cassiopeia_b200/csrc/agglom_exact.cuh).  Checked
+against the CPU oracle (oracle/oracle.c: oracle_nj, pinned to the reference) bit for bit, with the pruned scan,
+the dense scan and the default policy, on simulated data, tie-heavy data, duplicates, non-metric maps with
+negative entries, and at 4096 cells x 3 seeds (SURVEY section 7's matrix)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _upload(D):
+    import torch
+    from cassiopeia_b200 import engine
+
+    n = D.shape[0]
+    host = np.zeros((n, engine.padded_ld(n)), dtype=np.float64)
+    host[:, :n] = D
+    return torch.from_numpy(host).cuda()
+
+
+def _sim_map(n, m, S, rate, miss, weighted, seed):
+    from cassiopeia_b200 import engine
+    from cassiopeia_b200.synthetic import simulate_character_matrix
+
+    cm, priors, table = simulate_character_matrix(n, m, S, seed=seed, mutation_rate=rate, missing_fraction=miss)
+    cm = np.vstack([cm, np.zeros((1, m), dtype=cm.dtype)])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        w = np.nan_to_num(-np.log(table), nan=0.0, posinf=0.0)
+    return engine.whd_map(cm, -1, w if weighted else None, S, dtype="f64", method="exact"), n + 1
+
+
+POLICIES = [("default", {}), ("pruned", {"CAS_PRUNE": "1", "CAS_PRUNE_MIN_K": "0"}), ("dense", {"CAS_PRUNE": "0"})]
+
+
+def _exact(D, n, env, monkeypatch):
+    from cassiopeia_b200 import engine
+
+    for key in ("CAS_PRUNE", "CAS_PRUNE_MIN_K"):
+        monkeypatch.delenv(key, raising=False)
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    joins, last2 = engine.agglomerate(D.clone(), n, "nj", "exact")
+    return joins, last2, dict(engine.last_stats)
+
+
+def _first_diff(a, b):
+    bad = np.nonzero((a != b).any(axis=1))[0]
+    return None if bad.size == 0 else (int(bad[0]), a[bad[0]].tolist(), b[bad[0]].tolist())
+
+
+@pytest.mark.parametrize("policy,env", POLICIES)
+@pytest.mark.parametrize("n,m,S,rate,miss,weighted", [(3, 5, 3, 0.5, 0.0, True), (4, 5, 3, 0.5, 0.0, False),
+                                                      (130, 20, 5, 0.7, 0.1, True), (700, 40, 50, 0.1, 0.2, True),
+                                                      (700, 40, 50, 0.1, 0.1, False), (1500, 10, 3, 0.3, 0.0, False),
+                                                      (2500, 30, 10, 0.4, 0.3, True)])
+def test_exact_mode_equals_oracle_on_simulated_maps(n, m, S, rate, miss, weighted, policy, env, monkeypatch):
+    D, nn = _sim_map(n, m, S, rate, miss, weighted, seed=n + 1)
+    want, want_last = po.nj(D[:, :nn].cpu().numpy())
+    got, got_last, st = _exact(D, nn, env, monkeypatch)
+    assert _first_diff(got, want) is None, (policy, _first_diff(got, want))
+    assert np.array_equal(got_last, want_last)
+    if nn >= 4:
+        # with three nodes left all three criteria coincide mathematically: always resolved exactly
+        assert st["ambiguous_iterations"] >= 1 and st["rows_resolved"] >= 3
+
+
+@pytest.mark.parametrize("policy,env", POLICIES)
+@pytest.mark.parametrize("kind", ["uniform", "small_ints", "gaussian", "duplicates", "all_equal"])
+@pytest.mark.parametrize("n", [9, 257, 1100])
+def test_exact_mode_equals_oracle_on_arbitrary_symmetric_maps(n, kind, policy, env, monkeypatch):
+    """Non-metric inputs: negative entries (absolute-sum bound), massive exact ties (every tie resolved by the
+    reference's sequential sums and its first-row-major rule), duplicated rows."""
+    rng = np.random.default_rng(n * 7 + len(kind))
+    if kind == "uniform":
+        A = rng.random((n, n))
+    elif kind == "small_ints":
+        A = rng.integers(0, 4, (n, n)).astype(np.float64)
+    elif kind == "gaussian":
+        A = rng.normal(size=(n, n)) * 3.0
+    elif kind == "all_equal":
+        A = np.ones((n, n))
+    else:
+        base = rng.random((n // 3 + 1, 12))
+        pts = base[rng.integers(0, base.shape[0], n)]
+        A = np.abs(pts[:, None, :] - pts[None, :, :]).sum(axis=2)
+    D = np.triu(A, 1)
+    D = D + D.T
+    if kind == "all_equal" and n > 300:
+        pytest.skip("k^2 tied pairs per iteration: covered at the smaller sizes")
+    want, want_last = po.nj(D)
+    got, got_last, st = _exact(_upload(D), n, env, monkeypatch)
+    assert _first_diff(got, want) is None, (policy, kind, _first_diff(got, want))
+    assert np.array_equal(got_last, want_last)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_exact_and_strict_modes_equal_oracle_at_4096_cells(seed, monkeypatch):
+    """SURVEY section 7 / VERDICT r1: GPU-vs-oracle join lists at n = 4096 x seeds 0-2 (all host threads)."""
+    from cassiopeia_b200 import engine
+
+    D, nn = _sim_map(4096, 40, 50, 0.1, 0.1, True, seed)
+    want, want_last = po.nj(D[:, :nn].cpu().numpy())
+    got, got_last, st = _exact(D, nn, {}, monkeypatch)
+    assert _first_diff(got, want) is None, _first_diff(got, want)
+    assert np.array_equal(got_last, want_last)
+    strict, strict_last = engine.agglomerate(D.clone(), nn, "nj", "strict")
+    assert np.array_equal(strict, want) and np.array_equal(strict_last, want_last)
+    assert st["scanned_elements"] > 0 and st["ambiguous_iterations"] < 200
+
+
+def test_exact_mode_equals_gpu_strict_at_20k_cells(monkeypatch):
+    """Above the oracle's reach in a test: the literal re-accumulation ("strict", itself pinned to the oracle up to
+    4096 cells) and the adaptive mode must give the identical 20 000-join list."""
+    from cassiopeia_b200 import engine
+
+    D, nn = _sim_map(20000, 60, 100, 0.1, 0.2, True, 3)
+    got, got_last, st = _exact(D, nn, {}, monkeypatch)
+    strict, strict_last = engine.agglomerate(D, nn, "nj", "strict")
+    assert _first_diff(got, strict) is None, _first_diff(got, strict)
+    assert np.array_equal(got_last, strict_last)
+    print("exact-mode stats at 20k:", st)
+
+
+def test_all_nan_map_raises_instead_of_indexing_with_minus_one():
+    from cassiopeia_b200 import engine
+    from cassiopeia_b200._lib import B200LibraryError
+
+    n = 40
+    D = np.full((n, n), np.nan)
+    np.fill_diagonal(D, 0.0)
+    for algo, mode in (("nj", "fast"), ("nj", "exact"), ("upgma", "strict")):
+        with pytest.raises(B200LibraryError):
+            engine.agglomerate(_upload(D), n, algo, mode)

@@ -37,8 +37,11 @@ def test_exact_map_bit_exact_vs_reference(name):
     assert np.array_equal(D32[:, :n].cpu().numpy(), Dh.astype(np.float32))
 
 
+@pytest.mark.parametrize("mode", ["strict", "exact"])
 @pytest.mark.parametrize("name", golden_names())
-def test_strict_loop_reproduces_reference_joins(name):
+def test_strict_loop_reproduces_reference_joins(name, mode):
+    """Both reference-exact modes: "strict" re-accumulates every row sum sequentially each iteration, "exact"
+    maintains them and evaluates sequential sums only for ambiguous pairs."""
     from cassiopeia_b200 import engine
 
     g = Golden(name)
@@ -46,7 +49,7 @@ def test_strict_loop_reproduces_reference_joins(name):
     cm = g.ordered_cm.astype(np.int32)
     n = cm.shape[0]
     D = engine.whd_map(cm, g.missing, w, S, dtype="f64", method="exact")
-    joins, last2 = engine.agglomerate(D, n, g.algo, "strict")
+    joins, last2 = engine.agglomerate(D, n, g.algo, mode)
     assert joins.shape == g.joins.shape
     bad = np.nonzero((joins != g.joins).any(axis=1))[0]
     assert bad.size == 0, f"first differing join at t={bad[0]}: {joins[bad[0]]} vs {g.joins[bad[0]]}"
@@ -78,28 +81,7 @@ def test_solve_host_matches_device_path():
     g = Golden("sim64_s0_nj_priors")
     w, S = _table(g)
     cm = g.ordered_cm.astype(np.int32)
-    joins, last2, tm = engine.solve_host(cm, g.missing, w, S, "nj", "strict", "exact")
-    assert np.array_equal(joins, g.joins)
-    assert (tm >= 0).all()
-
-
-@pytest.mark.parametrize("name,mode,dt", [("sim1024_s0_nj_priors", "fast", "f32"), ("sim256_s1_nj_plain", "fast", "f64"),
-                                          ("sim1024_s0_upgma_plain", "strict", "f64"), ("ties120_upgma_priors", "fast", "f32")])
-def test_persistent_loop_equals_multi_kernel_loop(name, mode, dt, monkeypatch):
-    """The one-launch cooperative loop and the launch-per-phase loop run the same arithmetic."""
-    from cassiopeia_b200 import engine
-
-    g = Golden(name)
-    w, S = _table(g)
-    cm = g.ordered_cm.astype(np.int32)
-    n = cm.shape[0]
-    out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("CAS_PERSISTENT", flag)
-        D = engine.whd_map(cm, g.missing, w, S, dtype=dt, method="exact")
-        out[flag] = engine.agglomerate(D, n, g.algo, mode)
-        launches = engine.last_launch_count()
-        assert (launches < 10) == (flag == "1"), launches
-    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
-    if mode == "strict":
-        assert np.array_equal(out["1"][0], g.joins)
+    for mode in ("strict", "exact"):
+        joins, last2, tm = engine.solve_host(cm, g.missing, w, S, "nj", mode, "exact")
+        assert np.array_equal(joins, g.joins)
+        assert (tm >= 0).all()

@@ -181,8 +181,9 @@ def test_newick_is_iterative_and_wellformed():
 # ---- constructors and errors ---------------------------------------------------------------------
 def test_constructor_keywords_and_invalid_implementations():
     s = cb.NeighborJoiningSolver(add_root=True, prior_transformation="inverse", threads=2)
-    assert s.add_root and s.prior_transformation == "inverse" and s.threads == 2 and s.precision == "strict"
+    assert s.add_root and s.prior_transformation == "inverse" and s.threads == 2 and s.precision == "exact"
     assert cb.NeighborJoiningSolver(fast=True).precision == "fast"
+    assert cb.NeighborJoiningSolver(fast=True, implementation="b200_exact").precision == "exact"
     assert cb.UPGMASolver(fast=True, implementation="b200_strict").precision == "strict"
     assert cb.UPGMASolver().add_root is True
     for bad in ("ccphylo_dnj", "nonsense"):
