@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CAS_B200_LIBRARY", os.path.join(_HERE, "libcas_b200.so"))
 
 # constants of include/cas_b200.h
-CAS_ABI_VERSION = 1
+CAS_ABI_VERSION = 2
 CAS_F32, CAS_F64 = 0, 1
 CAS_ALGO_NJ, CAS_ALGO_UPGMA = 0, 1
 CAS_MODE_STRICT, CAS_MODE_FAST, CAS_MODE_EXACT = 0, 1, 2
@@ -39,6 +39,7 @@ EXPORTS = (
     "cas_agglom_scanned_elements",
     "cas_agglom_prune_diag",
     "cas_agglom_exact_stats",
+    "cas_loop_launch_floor",
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
     "cas_sharded_workspace_bytes",
@@ -57,6 +58,7 @@ EXPORTS = (
     "cas_exchange_error",
     "cas_sharded_solve_p2p",
     "cas_sharded_solve_emulated_p2p",
+    "cas_sharded_exact_stats",
     "cas_tail_preorder",
     "cas_tail_heights",
     "cas_tail_successor_lists",
@@ -104,6 +106,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_agglom_prune_diag.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]
     L.cas_agglom_exact_stats.restype = ctypes.c_int
     L.cas_agglom_exact_stats.argtypes = [vp, i64, vp, vp]
+    L.cas_loop_launch_floor.restype = ctypes.c_int
+    L.cas_loop_launch_floor.argtypes = [i64, i64, i32, vp, sz, vp]
     L.cas_tail_preorder.restype = i64
     L.cas_tail_preorder.argtypes = [vp, vp, i64, i64, vp, vp]
     L.cas_tail_heights.restype = ctypes.c_int
@@ -147,9 +151,11 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_exchange_error.restype = ctypes.c_int
     L.cas_exchange_error.argtypes = [vp, vp, ctypes.POINTER(i32)]
     L.cas_sharded_solve_p2p.restype = ctypes.c_int
-    L.cas_sharded_solve_p2p.argtypes = [vp, i64, i64, i32, i32, i64, i32, i32, vp, u64, vp, vp, vp, sz, vp]
+    L.cas_sharded_solve_p2p.argtypes = [vp, i64, i64, i32, i32, i32, i64, i32, i32, vp, u64, vp, vp, vp, sz, vp]
     L.cas_sharded_solve_emulated_p2p.restype = ctypes.c_int
-    L.cas_sharded_solve_emulated_p2p.argtypes = [vp, i64, i64, i32, i32, i64, i32, vp, u64, vp, vp, vp, sz, vp]
+    L.cas_sharded_solve_emulated_p2p.argtypes = [vp, i64, i64, i32, i32, i32, i64, i32, vp, u64, vp, vp, vp, sz, vp]
+    L.cas_sharded_exact_stats.restype = ctypes.c_int
+    L.cas_sharded_exact_stats.argtypes = [vp, i64, i32, i32, vp, vp]
     L.cas_solve_host.restype = ctypes.c_int
     L.cas_solve_host.argtypes = [vp, i64, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]
 

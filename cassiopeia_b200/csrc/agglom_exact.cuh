@@ -59,21 +59,23 @@ __device__ __forceinline__ void exact_collect_span(const double *__restrict__ ro
   }
 }
 
-// B: Rex[slot] = ((0 + d[slot][o_0]) + d[slot][o_1]) + ... for the marked slots.  All threads of a 256-thread CTA.
-__device__ __forceinline__ void exact_rowsums(const double *__restrict__ D, int64_t ld, int k, const ExactArgs &x,
-                                              int M, double (*tile)[XR_POS + 1]) {
+// B: sum = ((0 + d[s][o_0]) + d[s][o_1]) + ... for M rows.  rowptr(m) = address of the m-th row's elements (indexed
+// by slot), out(m, sum) stores the result.  All threads of a 256-thread CTA; `order` = live slots in id order.
+template <typename RowPtr, typename Out>
+__device__ __forceinline__ void exact_rowsums_generic(int k, const int32_t *order, int M, double (*tile)[XR_POS + 1],
+                                                      RowPtr rowptr, Out out) {
   const int tid = threadIdx.x;
   for (int p0 = 0; p0 < M; p0 += XR_ROWS) {
     const int nr = min(XR_ROWS, M - p0);
-    int64_t rowoff[XR_ROWS];
+    const double *rows[XR_ROWS];
 #pragma unroll
-    for (int r = 0; r < XR_ROWS; ++r) rowoff[r] = (int64_t)x.mlist[p0 + min(r, nr - 1)] * ld;
+    for (int r = 0; r < XR_ROWS; ++r) rows[r] = rowptr(p0 + min(r, nr - 1));
     double pre[XR_ROWS];
     auto fetch = [&](int pos0) {
       const int p = pos0 + tid;
-      const int slot = p < k ? x.order[p] : -1;
+      const int slot = p < k ? order[p] : -1;
 #pragma unroll
-      for (int r = 0; r < XR_ROWS; ++r) pre[r] = (r < nr && slot >= 0) ? D[rowoff[r] + slot] : 0.0;
+      for (int r = 0; r < XR_ROWS; ++r) pre[r] = (r < nr && slot >= 0) ? rows[r][slot] : 0.0;
     };
     fetch(0);
     double acc = 0.0;
@@ -97,9 +99,16 @@ __device__ __forceinline__ void exact_rowsums(const double *__restrict__ D, int6
       }
       __syncthreads();
     }
-    if (tid < nr) x.Rex[x.mlist[p0 + tid]] = acc;
+    if (tid < nr) out(p0 + tid, acc);
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void exact_rowsums(const double *__restrict__ D, int64_t ld, int k, const ExactArgs &x,
+                                              int M, double (*tile)[XR_POS + 1]) {
+  exact_rowsums_generic(
+      k, x.order, M, tile, [&](int m) { return D + (int64_t)x.mlist[m] * ld; },
+      [&](int m, double sum) { x.Rex[x.mlist[m]] = sum; });
 }
 
 // C: the reference's pair among the marked rows.  Returns it in (si, sj) (unchanged when nothing qualifies, which
@@ -143,7 +152,7 @@ __device__ __forceinline__ void exact_decide(const double *__restrict__ D, int64
 }
 
 // B + C + statistics, after the rows have been marked.  All threads of the last CTA.
-__device__ __noinline__ void exact_finish(const double *D, int64_t ld, int k, const double *R, const int32_t *ids,
+static __device__ __noinline__ void exact_finish(const double *D, int64_t ld, int k, const double *R, const int32_t *ids,
                                           double tinv, double capq, ExactArgs x, int *psi, int *psj) {
   __shared__ double tile[XR_ROWS][XR_POS + 1];
   __syncthreads();  // every mark of this CTA has been issued
@@ -165,11 +174,13 @@ __device__ __noinline__ void exact_finish(const double *D, int64_t ld, int k, co
 
 // A for the pruned scan.  Rows that are not on this iteration's work list were proven unable to hold a pair below
 // gbest + window (>= capq) by the row test; listed rows carry bounds the scan has just refreshed.  E and beta were
-// written by other CTAs of this launch: read through L2.
-__device__ __noinline__ void exact_collect_pruned(const double *D, int64_t ld, int k, const double *R, double tinv,
-                                                  PruneArgs p, ExactArgs x, double capq, int epoch, unsigned nfront,
-                                                  unsigned nback) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+// written by other CTAs: read through L2.  Warps gw, gw + nw, ... of the caller share the listed rows;
+// rowof(ridx, i, row) maps a work-list entry (the row's index into E / beta) to its slot and its elements.
+template <typename RowOf>
+__device__ __forceinline__ void exact_collect_listed(const double *R, double tinv, int k, const PruneArgs &p,
+                                                     const ExactArgs &x, double capq, int epoch, unsigned nfront,
+                                                     unsigned nback, int gw, int nw, RowOf rowof) {
+  const int lane = threadIdx.x & 31;
   const float cnow = prune_cnow(p);
   const float umaxf = prune_umaxf(p, tinv);
   const float capf = __double2float_ru(capq);
@@ -178,14 +189,16 @@ __device__ __noinline__ void exact_collect_pruned(const double *D, int64_t ld, i
     return (e - cnow) > (capf + uif) + 2e-6f * mag;
   };
   const unsigned nrows = nfront + nback;
-  for (unsigned r = warp; r < nrows; r += nwarps) {
-    const int i = r < nfront ? p.worklist[r] : p.worklist[p.wlast - (int)(r - nfront)];
+  for (unsigned r = gw; r < nrows; r += nw) {
+    const int ridx = r < nfront ? p.worklist[r] : p.worklist[p.wlast - (int)(r - nfront)];
+    int i = -1;
+    const double *row = nullptr;
+    rowof(ridx, i, row);
     if (i < 1 || i >= k) continue;
     const double Ri = R[i];
     const float uif = (float)__dmul_rn(tinv, Ri);
-    if (impossible(dec_f32(__ldcg(p.beta + i)), uif)) continue;
-    const double *__restrict__ row = D + (int64_t)i * ld;
-    const unsigned *erow = p.E + (int64_t)i * p.stride;
+    if (impossible(dec_f32(__ldcg(p.beta + ridx)), uif)) continue;
+    const unsigned *erow = p.E + (int64_t)ridx * p.stride;
     const int nsub = (i + SW - 1) / SW;
     for (int sb = 0; sb < nsub; sb += 32) {
       const int sgm = sb + lane;
@@ -198,6 +211,16 @@ __device__ __noinline__ void exact_collect_pruned(const double *D, int64_t ld, i
       }
     }
   }
+}
+
+static __device__ __noinline__ void exact_collect_pruned(const double *D, int64_t ld, int k, const double *R, double tinv,
+                                                  PruneArgs p, ExactArgs x, double capq, int epoch, unsigned nfront,
+                                                  unsigned nback) {
+  exact_collect_listed(R, tinv, k, p, x, capq, epoch, nfront, nback, (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5),
+                       [&](int ridx, int &i, const double *&row) {
+                         i = ridx;
+                         row = D + (int64_t)ridx * ld;
+                       });
 }
 
 }  // namespace cas

@@ -61,6 +61,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
               void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements);
 int agglom_read_exact_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *out4);
+int loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, void *workspace, cudaStream_t stream);
 int agglom_read_prune_diag(const void *workspace, int64_t n, cudaStream_t stream, int64_t *rows_listed, double *drift);
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
@@ -170,6 +171,14 @@ int cas_smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
                    workspace_bytes, (cudaStream_t)stream);
 }
 
+int cas_loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, void *workspace, size_t workspace_bytes,
+                          void *stream) {
+  reset_launch_count();
+  CAS_REQUIRE(workspace && k >= 1 && iters >= 0 && kernels_per_iter >= 1 && kernels_per_iter <= 3, "bad argument");
+  CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(k), "workspace too small");
+  return loop_launch_floor(k, iters, kernels_per_iter, workspace, (cudaStream_t)stream);
+}
+
 int cas_agglom_exact_stats(const void *workspace, int64_t n, void *stream, int64_t *out4) {
   CAS_REQUIRE(workspace && out4, "null pointer argument");
   return agglom_read_exact_stats(workspace, n, (cudaStream_t)stream, out4);
@@ -269,11 +278,15 @@ int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t missing
                                stream));
   CAS_CUDA_TRY(cudaEventRecord(ev[4], stream));
   CAS_CUDA_TRY(cudaStreamSynchronize(stream));
+  // both map kernels' encode passes set the first int of their workspace when they meet a state outside
+  // [0, n_states] that is not the missing indicator: the join list would come from a corrupt map
   int flag = 0;
-  if (map_method == CAS_MAP_EXACT) {
-    rc = whd_read_error_flag(ws_map.p, stream, &flag);
-    if (rc != CAS_OK) return rc;
-    CAS_REQUIRE(flag == 0, "character matrix holds a state outside [0, n_states] that is not the missing indicator");
+  rc = whd_read_error_flag(ws_map.p, stream, &flag);
+  if (rc != CAS_OK) return rc;
+  CAS_REQUIRE(flag == 0, "character matrix holds a state outside [0, n_states] that is not the missing indicator");
+  if (njoin && last2_host[0] == -2) {
+    set_error("the loop found no finite entry to join (is the dissimilarity map all NaN / inf?)");
+    return CAS_ERR_INVALID;
   }
   if (timings_ms) {
     for (int i = 0; i < 4; ++i) {

@@ -27,7 +27,7 @@
 
 #include <vector>
 
-#include "agglom_pruned.cuh"
+#include "agglom_exact.cuh"
 
 namespace cas {
 
@@ -59,12 +59,20 @@ __host__ __device__ __forceinline__ int sh_chunk(int k, int G) {
 // ---- direct NVLink exchange (P2P): every rank owns an exchange buffer that its peers map
 // (cudaIpc) and write into with plain stores; iteration-tagged flags replace the collectives.
 constexpr int SH_MAXG = 16;
+constexpr int XT = 128;  // exact mode: most slots whose sequential sums one ambiguous iteration may need
 struct ShExHeader {
   unsigned long long flag1[SH_MAXG];  // flag1[r] = tag: rank r's candidate for that iteration has landed
   unsigned long long flag2[SH_MAXG];  // flag2[r] = tag: rank r's rows (lo, hi, last) chunk has landed
+  unsigned long long flagA[SH_MAXG];  // exact mode: rank r's list of marked slots has landed
+  unsigned long long flagB[SH_MAXG];  // exact mode: rank r's sequential sums (of the marked slots it owns) have landed
   Cand cand[SH_MAXG];
-  int error;                          // a spin-wait timed out
-  int pad[63];
+  int countA[SH_MAXG];                // exact mode: entries of listA[r]
+  int error;                          // 1: a spin-wait timed out, 2: more than XT marked slots
+  int pad[47];
+  // exact mode, one ambiguous iteration at a time:
+  int listA[SH_MAXG][XT];             // marked slots found by rank r among its rows
+  double xsum[XT];                    // sequential row sum of the u-th slot of the sorted union (written by its owner)
+  double xd[XT][XT];                  // xd[u][v] = d(slot_u, slot_v), written by the owner of slot_u
 };
 static_assert(sizeof(ShExHeader) % 256 == 0, "exchange header must keep the gather area aligned");
 struct ShPeers {
@@ -74,13 +82,16 @@ __device__ __forceinline__ ShExHeader *ex_header(char *ex) { return reinterpret_
 __device__ __forceinline__ char *ex_gath(char *ex) { return ex + sizeof(ShExHeader); }
 
 // spin until *flag >= tag (written by a peer GPU); gives up after ~2 s and records the failure
+// Once any wait has failed the flag stays set and every later wait returns at once: the pre-enqueued rest of the
+// loop drains in microseconds instead of spinning two seconds per wait, and the host raises (PeerGroup.check).
 __device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long tag, int *error) {
   const long long t0 = clock64();
   for (;;) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
     if (v >= tag) return;
-    if (clock64() - t0 > 4000000000LL) { atomicExch(error, 1); return; }
+    if (*(volatile int *)error != 0) return;
+    if (clock64() - t0 > 4000000000LL) { atomicCAS(error, 0, 1); return; }
   }
 }
 __device__ __forceinline__ void post_flag(unsigned long long *flag, unsigned long long tag) {
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(256) sh_rowtest_kernel(PruneArgs p, const T *_
     moved = phi != k;
   }
   prune_rowtest<T, NJ>(p, valid, lr, i, Dloc + (int64_t)(valid ? lr : 0) * ld, (valid && NJ) ? R[i] : 0.0, tinv, plo,
-                       phi, moved);
+                       phi, moved, prune_wfloor(p, k, tinv));
 }
 
 template <typename T, bool NJ>
@@ -213,6 +224,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanA
   rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
   rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
   rs.sbest = INFINITY; rs.ssi = -1; rs.ssj = -1; rs.uif = 0.f;
+  rs.wfloor = prune_wfloor(p, k, a.tinv);
   PruneWarp pw;
   pw.gb_seen = INFINITY; pw.nread = 0;
   const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
@@ -256,6 +268,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanA
   if (threadIdx.x == 0) {
     // every other CTA of this rank has finished (counter): clear the per-iteration state, commit the drift
     *p.gbest = enc_f64(INFINITY);
+    p.wcount[2] = p.wcount[0];  // length of this iteration's work list, for the exact mode's resolver
     *p.wcount = 0u;
     prune_commit(p);
   }
@@ -288,58 +301,74 @@ struct ShColsArgs {
   unsigned *counter;
   // pruned scan (or E == null): the bounds of the two rows the merge rewrites become unknown
   unsigned *E; int64_t e_stride; unsigned *beta;
+  // exact NJ mode (P2P exchange only): see "exact mode, sharded" below
+  int exact; const double *R; double tinv; PruneArgs p; ExactArgs ex; unsigned *xstate;
 };
 
+// The part of the cols kernel that needs the selected pair: marks the two rows the merge rewrites unknown,
+// publishes this rank's pieces of columns lo / hi / last, the selection and the join.  All threads of all CTAs.
 template <typename T>
-__global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
-  pdl_wait();  // no-ops unless launched with programmatic stream serialization (the pruned loop)
-  pdl_launch_dependents();
-  __shared__ Cand sCand[8];
+__device__ __forceinline__ void sh_cols_body(const ShColsArgs &a, int si, int sj) {
   __shared__ bool sLast;
   const bool p2p = a.peers.ex[0] != nullptr;
-  const Cand *cand_all = a.cand_all;
-  if (p2p) {
-    ShExHeader *own = ex_header(a.peers.ex[a.r]);
-    if (threadIdx.x < a.G) wait_flag(&own->flag1[threadIdx.x], a.tag, &own->error);
-    __syncthreads();
-    cand_all = own->cand;
-  }
-  const Cand c = reduce_candidates(cand_all, a.G, sCand);
-  const int lo = min(c.si, c.sj), hi = max(c.si, c.sj), last = a.k - 1;
+  const int lo = min(si, sj), hi = max(si, sj), last = a.k - 1;
   const T *__restrict__ D = static_cast<const T *>(a.Dloc);
-  if (a.E && blockIdx.x == 0) {
-    const int nsk = (a.k + SW - 1) / SW;
-    const bool own_lo = sh_owner(lo, a.G) == a.r, own_hi = sh_owner(hi, a.G) == a.r;
-    for (int sgm = threadIdx.x; sgm < nsk; sgm += 256) {
-      if (own_lo) a.E[(int64_t)sh_local(lo, a.G) * a.e_stride + sgm] = enc_f32(-INFINITY);
-      if (own_hi) a.E[(int64_t)sh_local(hi, a.G) * a.e_stride + sgm] = enc_f32(-INFINITY);
+  if (lo < 0) {  // no candidate anywhere (a map without a finite entry): flag it, publish nothing
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      Sel s;
+      s.lo = -1; s.hi = -1; s.dij = 0.0; s.size_lo = 0; s.size_hi = 0; s.id_lo = -1; s.id_hi = -1;
+      *a.sel = s;
+      a.joins[2 * a.t] = -1;
+      a.joins[2 * a.t + 1] = -1;
     }
-    if (threadIdx.x == 0) {
-      if (own_lo) a.beta[sh_local(lo, a.G)] = enc_f32(-INFINITY);
-      if (own_hi) a.beta[sh_local(hi, a.G)] = enc_f32(-INFINITY);
+  } else {
+    if (a.E && blockIdx.x == 0) {
+      const int nsk = (a.k + SW - 1) / SW;
+      const bool own_lo = sh_owner(lo, a.G) == a.r, own_hi = sh_owner(hi, a.G) == a.r;
+      for (int sgm = threadIdx.x; sgm < nsk; sgm += 256) {
+        if (own_lo) a.E[(int64_t)sh_local(lo, a.G) * a.e_stride + sgm] = enc_f32(-INFINITY);
+        if (own_hi) a.E[(int64_t)sh_local(hi, a.G) * a.e_stride + sgm] = enc_f32(-INFINITY);
+      }
+      if (threadIdx.x == 0) {
+        if (own_lo) a.beta[sh_local(lo, a.G)] = enc_f32(-INFINITY);
+        if (own_hi) a.beta[sh_local(hi, a.G)] = enc_f32(-INFINITY);
+      }
     }
-  }
-  const int lr = blockIdx.x * 256 + threadIdx.x;
-  if (lr < sh_count(a.k, a.r, a.G)) {
-    const T *row = D + (int64_t)lr * a.ld;
-    const T va = row[lo], vb = row[hi], vl = row[last];
-    if (p2p) {
-      // write this rank's chunk straight into every rank's gather area over NVLink
-      for (int pr = 0; pr < a.G; ++pr) {
-        T *out = reinterpret_cast<T *>(ex_gath(a.peers.ex[pr])) + (size_t)a.r * 3 * a.chunk;
+    const int lr = blockIdx.x * 256 + threadIdx.x;
+    if (lr < sh_count(a.k, a.r, a.G)) {
+      const T *row = D + (int64_t)lr * a.ld;
+      const T va = row[lo], vb = row[hi], vl = row[last];
+      if (p2p) {
+        // write this rank's chunk straight into every rank's gather area over NVLink
+        for (int pr = 0; pr < a.G; ++pr) {
+          T *out = reinterpret_cast<T *>(ex_gath(a.peers.ex[pr])) + (size_t)a.r * 3 * a.chunk;
+          out[lr] = va;
+          out[a.chunk + lr] = vb;
+          out[2 * a.chunk + lr] = vl;
+        }
+      } else {
+        T *__restrict__ out = static_cast<T *>(a.mine);
         out[lr] = va;
         out[a.chunk + lr] = vb;
         out[2 * a.chunk + lr] = vl;
       }
-    } else {
-      T *__restrict__ out = static_cast<T *>(a.mine);
-      out[lr] = va;
-      out[a.chunk + lr] = vb;
-      out[2 * a.chunk + lr] = vl;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      Sel s;
+      s.lo = lo; s.hi = hi;
+      s.dij = 0.0;  // filled from the gathered row in the merge kernel
+      s.size_lo = a.sizes ? a.sizes[lo] : 1;
+      s.size_hi = a.sizes ? a.sizes[hi] : 1;
+      s.id_lo = a.ids[lo];
+      s.id_hi = a.ids[hi];
+      *a.sel = s;
+      a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
+      a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
     }
   }
   if (p2p) {
-    // last block of this kernel signals "chunk landed" to every rank
+    // last block of this kernel signals "chunk landed" to every rank (also when nothing could be selected:
+    // the peers' merge kernels must not wait for ever)
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -352,18 +381,225 @@ __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
       post_flag(&ex_header(a.peers.ex[threadIdx.x])->flag2[a.r], a.tag);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    Sel s;
-    s.lo = lo; s.hi = hi;
-    s.dij = 0.0;  // filled from the gathered row in the merge kernel
-    s.size_lo = a.sizes ? a.sizes[lo] : 1;
-    s.size_hi = a.sizes ? a.sizes[hi] : 1;
-    s.id_lo = a.ids[lo];
-    s.id_hi = a.ids[hi];
-    *a.sel = s;
-    a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
-    a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
+}
+
+// ---- exact mode, sharded ----------------------------------------------------------------------------------
+// Every rank reduces the same G candidates and holds the same replicated bounds, so all ranks agree whether an
+// iteration is ambiguous (a second pair inside the error window, agglom_exact.cuh).  Then, instead of the cols body:
+//   cols kernel (X1)   : all CTAs collect the pairs with q~ <= capq among this rank's listed rows and mark their
+//                        slots; the last CTA publishes the rank's list of marked slots to every rank (flagA);
+//   exact sums kernel  : one CTA per rank: sorted union of the G lists (identical on every rank); for the slots this
+//                        rank owns, the reference's sequential row sum and the distances to all other marked slots,
+//                        published to every rank (flagB);
+//   second cols kernel : every CTA re-evaluates the marked pairs with the sequential sums (redundantly, identically
+//                        on every rank), applies the (value, id_lo, id_hi) rule and runs the cols body.
+// The two extra kernels are launched every iteration and return at once unless the iteration is ambiguous.
+template <typename T>
+__device__ __forceinline__ Cand sh_cols_reduce(const ShColsArgs &a, Cand *sCand) {
+  const bool p2p = a.peers.ex[0] != nullptr;
+  const Cand *cand_all = a.cand_all;
+  if (p2p) {
+    ShExHeader *own = ex_header(a.peers.ex[a.r]);
+    if (threadIdx.x < a.G) wait_flag(&own->flag1[threadIdx.x], a.tag, &own->error);
+    __syncthreads();
+    cand_all = own->cand;
   }
+  return reduce_candidates(cand_all, a.G, sCand);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
+  pdl_wait();  // no-ops unless launched with programmatic stream serialization (the pruned loop)
+  pdl_launch_dependents();
+  __shared__ Cand sCand[8];
+  __shared__ bool sLastX;
+  const Cand c = sh_cols_reduce<T>(a, sCand);
+  if constexpr (sizeof(T) == 8) {
+    if (a.exact) {
+      const double W = exact_window(a.p.xw, a.k, a.tinv);
+      if (c.si >= 0 && c.q2 - c.q <= W) {
+        // X1: collect among this rank's listed rows (work-list entries, E and beta are indexed by LOCAL row)
+        const double *Dl = static_cast<const double *>(a.Dloc);
+        const int G = a.G, r = a.r;
+        const int64_t ld = a.ld;
+        exact_collect_listed(a.R, a.tinv, a.k, a.p, a.ex, c.q + W, a.t + 1, __ldcg(a.p.wcount + 2), 0u,
+                             (int)(blockIdx.x * 8 + (threadIdx.x >> 5)), (int)(gridDim.x * 8),
+                             [&](int lr, int &i, const double *&row) {
+                               i = sh_slot(lr, r, G);
+                               row = Dl + (int64_t)lr * ld;
+                             });
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          unsigned prev = atomicInc(a.xstate + 1, gridDim.x - 1);
+          sLastX = (prev == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!sLastX) return;
+        __threadfence();
+        ShExHeader *own = ex_header(a.peers.ex[a.r]);
+        int M = (int)__ldcg(a.ex.mcount);
+        if (M > XT) {
+          if (threadIdx.x == 0) atomicExch(&own->error, 2);
+          M = XT;
+        }
+        for (int pr = 0; pr < a.G; ++pr) {
+          ShExHeader *h = ex_header(a.peers.ex[pr]);
+          for (int e = threadIdx.x; e < M; e += 256) h->listA[a.r][e] = __ldcg(a.ex.mlist + e);
+          if (threadIdx.x == 0) h->countA[a.r] = M;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < a.G) post_flag(&ex_header(a.peers.ex[threadIdx.x])->flagA[a.r], a.tag);
+        if (threadIdx.x == 0) {
+          *a.ex.mcount = 0u;
+          a.xstate[0] = 1u;  // deferred: the exact sums kernel and the second cols kernel finish this iteration
+        }
+        return;
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) a.xstate[0] = 0u;
+    }
+  }
+  sh_cols_body<T>(a, c.si, c.sj);
+}
+
+struct ShSumsArgs {
+  const double *Dloc;
+  int64_t ld;
+  int k, G, r;
+  ShPeers peers;
+  unsigned long long tag;
+  const int32_t *order;   // live slots in id order (replicated)
+  int32_t *ulist;         // out: sorted union of the marked slots
+  unsigned *xstate;       // [0] deferred, [2] size of the union
+};
+
+__global__ void __launch_bounds__(256) sh_exact_sums_kernel(ShSumsArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (!a.xstate[0]) return;
+  __shared__ double tile[XR_ROWS][XR_POS + 1];
+  __shared__ int sU[XT];
+  __shared__ int sMine[XT];
+  __shared__ int sT, sNm;
+  ShExHeader *own = ex_header(a.peers.ex[a.r]);
+  if (threadIdx.x < a.G) wait_flag(&own->flagA[threadIdx.x], a.tag, &own->error);
+  if (threadIdx.x == 0) { sT = 0; sNm = 0; }
+  __syncthreads();
+  // sorted union of the G lists: an entry is kept if no earlier entry (rank, position order) holds the same slot;
+  // its rank is the number of kept entries with a smaller slot
+  int cnt[SH_MAXG];
+  int total = 0;
+  for (int g = 0; g < a.G; ++g) { cnt[g] = min(max(own->countA[g], 0), XT); total += cnt[g]; }
+  auto entry = [&](int e) {
+    int g = 0;
+    while (e >= cnt[g]) { e -= cnt[g]; ++g; }
+    return own->listA[g][e];
+  };
+  for (int e = threadIdx.x; e < total; e += 256) {
+    const int s = entry(e);
+    bool first = true;
+    for (int f = 0; f < e && first; ++f) first = entry(f) != s;
+    if (!first) continue;
+    int rank = 0;
+    for (int f = 0; f < total; ++f) {
+      const int sf = entry(f);
+      if (sf < s) {
+        bool ff = true;
+        for (int g2 = 0; g2 < f && ff; ++g2) ff = entry(g2) != sf;
+        rank += ff ? 1 : 0;
+      }
+    }
+    if (rank < XT) sU[rank] = s;
+    atomicAdd(&sT, 1);
+  }
+  __syncthreads();
+  int T = sT;
+  if (T > XT) {
+    if (threadIdx.x == 0) atomicExch(&own->error, 2);
+    T = XT;
+  }
+  for (int u = threadIdx.x; u < T; u += 256) {
+    a.ulist[u] = sU[u];
+    if (sh_owner(sU[u], a.G) == a.r) sMine[atomicAdd(&sNm, 1)] = u;
+  }
+  if (threadIdx.x == 0) a.xstate[2] = (unsigned)T;
+  __syncthreads();
+  // the slots this rank owns: sequential sums (reference order) and distances to every marked slot
+  const int nm = sNm;
+  const double *Dl = a.Dloc;
+  const int G = a.G;
+  const int64_t ld = a.ld;
+  ShPeers peers = a.peers;
+  exact_rowsums_generic(
+      a.k, a.order, nm, tile, [&](int m) { return Dl + (int64_t)sh_local(sU[sMine[m]], G) * ld; },
+      [&](int m, double sum) {
+        for (int pr = 0; pr < G; ++pr) ex_header(peers.ex[pr])->xsum[sMine[m]] = sum;
+      });
+  for (int m = 0; m < nm; ++m) {
+    const int u = sMine[m];
+    const double *row = Dl + (int64_t)sh_local(sU[u], G) * ld;
+    for (int v = threadIdx.x; v < T; v += 256) {
+      const double d = row[sU[v]];
+      for (int pr = 0; pr < G; ++pr) ex_header(peers.ex[pr])->xd[u][v] = d;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < a.G) post_flag(&ex_header(a.peers.ex[threadIdx.x])->flagB[a.r], a.tag);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sh_cols2_kernel(ShColsArgs a, const int32_t *ulist) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (!a.xstate[0]) return;
+  __shared__ Cand sCand[8];
+  __shared__ double sQ[8];
+  __shared__ unsigned long long sK[8];
+  __shared__ int sI[8], sJ[8];
+  const Cand c = sh_cols_reduce<T>(a, sCand);  // the same G candidates as in the first cols kernel
+  ShExHeader *own = ex_header(a.peers.ex[a.r]);
+  if (threadIdx.x < a.G) wait_flag(&own->flagB[threadIdx.x], a.tag, &own->error);
+  __syncthreads();
+  const double W = exact_window(a.p.xw, a.k, a.tinv);
+  const double capq = c.q + W;
+  const int Tn = (int)a.xstate[2];
+  double bq = INFINITY;
+  unsigned long long bk = ~0ull;
+  int bi = -1, bj = -1;
+  for (int e = threadIdx.x; e < Tn * Tn; e += 256) {
+    const int u = e / Tn, v = e - u * Tn;
+    if (v >= u) continue;  // ulist is sorted by slot: slot_u > slot_v
+    const int i = ulist[u], j = ulist[v];
+    const double d = own->xd[u][v];
+    if (exact_q(d, a.tinv, a.R[i], a.R[j]) > capq) continue;
+    const double q = exact_q(d, a.tinv, own->xsum[u], own->xsum[v]);
+    const unsigned long long key = make_key(a.ids[i], a.ids[j]);
+    if (cand_better(q, key, bq, bk)) { bq = q; bk = key; bi = i; bj = j; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double oq = __shfl_xor_sync(0xffffffffu, bq, off);
+    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off), oj = __shfl_xor_sync(0xffffffffu, bj, off);
+    if (cand_better(oq, ok, bq, bk)) { bq = oq; bk = ok; bi = oi; bj = oj; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sQ[warp] = bq; sK[warp] = bk; sI[warp] = bi; sJ[warp] = bj; }
+  __syncthreads();
+  bq = sQ[0]; bk = sK[0]; bi = sI[0]; bj = sJ[0];
+  for (int w = 1; w < 8; ++w)
+    if (cand_better(sQ[w], sK[w], bq, bk)) { bq = sQ[w]; bk = sK[w]; bi = sI[w]; bj = sJ[w]; }
+  if (bi < 0) { bi = c.si; bj = c.sj; }  // cannot happen: the arg-min of q~ is always among the marked pairs
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(a.ex.xstats + 0, 1ull);
+    atomicAdd(a.ex.xstats + 1, (unsigned long long)Tn);
+    atomicMax(a.ex.xstats + 2, (unsigned long long)Tn);
+    if (max(bi, bj) != max(c.si, c.sj) || min(bi, bj) != min(c.si, c.sj)) atomicAdd(a.ex.xstats + 3, 1ull);
+  }
+  __syncthreads();
+  sh_cols_body<T>(a, bi, bj);
 }
 
 struct ShMergeArgs {
@@ -385,6 +621,9 @@ struct ShMergeArgs {
   // pruned scan (prune != 0), see MergeArgs in agglom.cu
   int prune; float *uf; double tinv_next; unsigned *dmax;
   const Cand *cand; int ncand; const int32_t *sugg; unsigned long long *gbest; int32_t *pool; int rot;
+  // exact NJ mode (replicated like R): bounds of the maintained sums, their maxima, id-ordered slot lists
+  int exact; double *Eb; double *Ab; unsigned long long *xw; double *apartial;
+  const int32_t *order_old; const int32_t *pos_old; int32_t *order_new; int32_t *pos_new;
 };
 
 // Per-rank warm start of the pruned scan's bound (prune_warm_start, agglom_pruned.cuh): only pairs whose row
@@ -406,6 +645,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
   pdl_wait();
   pdl_launch_dependents();
   __shared__ double sPart[MERGE_THREADS / 32];
+  __shared__ double sPartA[MERGE_THREADS / 32];
   __shared__ bool sLast;
   T *__restrict__ D = static_cast<T *>(a.Dloc);
   const T *g = static_cast<const T *>(a.gath);
@@ -416,6 +656,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
     g = reinterpret_cast<const T *>(ex_gath(a.peers.ex[a.r]));
   }
   const Sel s = *a.sel;
+  if (s.lo < 0) return;  // no candidate (sh_cols_body)
   const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1, G = a.G;
   const int64_t ld = a.ld;
   const int64_t cstride = 3 * (int64_t)a.chunk;
@@ -438,6 +679,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
   const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
   double contrib = 0.0, mine = 0.0;
   float uf_up = 0.f;
+  double ebv = 0.0, abv = 0.0;
   if (v < k) {
     const bool own_v = sh_owner(v, G) == a.r;
     T *row_v = own_v ? D + (int64_t)sh_local(v, G) * ld : nullptr;
@@ -454,7 +696,17 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
       const T nvs = round_to<T>(merged(da, db));
       contrib = (double)nvs;
       double Rv = 0.0;
-      if (a.maintain_R) Rv = __dadd_rn(__dsub_rn(__dsub_rn(a.R[v], da), db), contrib);
+      if (a.maintain_R) {
+        const double x1 = __dsub_rn(a.R[v], da), x2 = __dsub_rn(x1, db);
+        Rv = __dadd_rn(x2, contrib);
+        if (a.exact) {  // as in merge_kernel (agglom.cu)
+          ebv = __dadd_ru(a.Eb[v], __dmul_ru(__dadd_ru(__dadd_ru(fabs(x1), fabs(x2)), fabs(Rv)), EXACT_U1));
+          abv = fmax(__dsub_ru(__dsub_ru(__dadd_ru(a.Ab[v], fabs(contrib)), fabs(da)), fabs(db)), 0.0);
+          const int dst = (v == last && hi != last) ? hi : v;
+          a.Eb[dst] = ebv;
+          a.Ab[dst] = abv;
+        }
+      }
       if (hi != last && v != last) {
         const T l = gathered(2, v);
         if (own_hi) row_hi[v] = l;
@@ -477,6 +729,22 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
         mine = Rv;
       }
     }
+    // id-ordered list of live slots (exact mode), as in merge_kernel
+    if (a.order_old) {
+      const int p = v;
+      const int p_lo = a.pos_old[lo], p_hi = a.pos_old[hi];
+      if (p != p_lo && p != p_hi) {
+        int sl = a.order_old[p];
+        if (sl == last) sl = hi;
+        const int np = p - (p > p_lo ? 1 : 0) - (p > p_hi ? 1 : 0);
+        a.order_new[np] = sl;
+        a.pos_new[sl] = np;
+      }
+      if (p == 0) {
+        a.order_new[k - 2] = lo;
+        a.pos_new[lo] = k - 2;
+      }
+    }
   }
   if (a.prune && a.maintain_R) {
     const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(uf_up));
@@ -495,14 +763,30 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
   }
   if (!a.maintain_R) return;
   warp_atomic_absmax(a.rmax_bits, mine);
+  double acontrib = fabs(contrib);
+  if (a.exact) {
+    warp_atomic_max_nonneg(a.xw + XW_EBMAX, ebv);
+    warp_atomic_max_nonneg(a.xw + XW_ABMAX, abv);
+    warp_atomic_max_nonneg(a.xw + XW_DABS, acontrib);
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
   if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = contrib;
+  if (a.exact) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acontrib = __dadd_rn(acontrib, __shfl_down_sync(0xffffffffu, acontrib, off));
+    if ((threadIdx.x & 31) == 0) sPartA[threadIdx.x >> 5] = acontrib;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double sum = 0.0;
     for (int w = 0; w < MERGE_THREADS / 32; ++w) sum = __dadd_rn(sum, sPart[w]);
     a.partial[blockIdx.x] = sum;
+    if (a.exact) {
+      double asum = 0.0;
+      for (int w = 0; w < MERGE_THREADS / 32; ++w) asum = __dadd_rn(asum, sPartA[w]);
+      a.apartial[blockIdx.x] = asum;
+    }
     __threadfence();
     unsigned prev = atomicInc(a.counter, gridDim.x - 1);
     sLast = (prev == gridDim.x - 1);
@@ -515,32 +799,57 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
     a.R[lo] = sum;
     atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
     if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
+    if (a.exact) {
+      double asum = 0.0;
+      for (int b = 0; b < (int)gridDim.x; ++b) asum = __dadd_rn(asum, ((volatile double *)a.apartial)[b]);
+      const double ab = up30(asum);
+      const double eb = up30((double)(16 + (int)gridDim.x) * EXACT_U1 * ab);
+      a.Ab[lo] = ab;
+      a.Eb[lo] = eb;
+      atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(eb));
+      atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(ab));
+    }
   }
   if (sLast && a.prune) sh_warm_start<T, NJ>(a, lo, hi, last);
 }
 
 // initial row sums of the local rows (same lane-strided order as rowsum_init_kernel)
+// nval = 1: the row sum.  nval = 3 (exact mode): also sum |d| and max |d| of the row, at [chunk + lr], [2 chunk + lr]
+// of the rank's part of the gather area (rank stride nval * chunk).
 template <typename T>
 __global__ void __launch_bounds__(256) sh_rowsum_kernel(const T *__restrict__ D, int64_t ld, int k, int G,
                                                         int r, double *__restrict__ mine, int chunk,
                                                         ShPeers peers, unsigned long long tag,
-                                                        unsigned *counter) {
+                                                        unsigned *counter, int nval) {
   __shared__ bool sLast;
   const int lr = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const bool p2p = peers.ex[0] != nullptr;
   if (lr < sh_count(k, r, G)) {
     const T *__restrict__ row = D + (int64_t)lr * ld;
-    double s = 0.0;
-    for (int j = lane; j < k; j += 32) s = __dadd_rn(s, (double)row[j]);
+    double s = 0.0, as = 0.0, dm = 0.0;
+    for (int j = lane; j < k; j += 32) {
+      const double x = (double)row[j];
+      s = __dadd_rn(s, x);
+      as = __dadd_rn(as, fabs(x));
+      dm = fmax(dm, fabs(x));
+    }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+    for (int off = 16; off > 0; off >>= 1) {
+      s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+      as = __dadd_rn(as, __shfl_down_sync(0xffffffffu, as, off));
+      dm = fmax(dm, __shfl_down_sync(0xffffffffu, dm, off));
+    }
     if (lane == 0) {
       if (p2p) {
-        for (int pr = 0; pr < G; ++pr)
-          (reinterpret_cast<double *>(ex_gath(peers.ex[pr])) + (size_t)r * chunk)[lr] = s;
+        for (int pr = 0; pr < G; ++pr) {
+          double *o = reinterpret_cast<double *>(ex_gath(peers.ex[pr])) + (size_t)r * nval * chunk;
+          o[lr] = s;
+          if (nval == 3) { o[chunk + lr] = as; o[2 * chunk + lr] = dm; }
+        }
       } else {
         mine[lr] = s;
+        if (nval == 3) { mine[chunk + lr] = as; mine[2 * chunk + lr] = dm; }
       }
     }
   }
@@ -561,7 +870,7 @@ __global__ void __launch_bounds__(256) sh_rowsum_kernel(const T *__restrict__ D,
 
 __global__ void sh_rscatter_kernel(const double *gath, int chunk, int k, int G, int r,
                                    double *__restrict__ R, unsigned long long *rmax_bits, ShPeers peers,
-                                   unsigned long long tag, float *uf, double tinv) {
+                                   unsigned long long tag, float *uf, double tinv, int nval, double *Eb, double *Ab) {
   if (peers.ex[0] != nullptr) {
     ShExHeader *own = ex_header(peers.ex[r]);
     if (threadIdx.x < G) wait_flag(&own->flag2[threadIdx.x], tag, &own->error);
@@ -569,21 +878,40 @@ __global__ void sh_rscatter_kernel(const double *gath, int chunk, int k, int G, 
     gath = reinterpret_cast<const double *>(ex_gath(peers.ex[r]));
   }
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  double s = 0.0;
+  double s = 0.0, eb = 0.0, ab = 0.0, dm = 0.0;
   if (v < k) {
-    s = gath[(int64_t)sh_owner(v, G) * chunk + sh_local(v, G)];
+    const double *o = gath + (int64_t)sh_owner(v, G) * nval * chunk;
+    const int lr = sh_local(v, G);
+    s = o[lr];
     R[v] = s;
     if (uf) uf[v] = __double2float_rn(__dmul_rn(tinv, s));
+    if (nval == 3) {  // exact mode: bounds as in rowsum_init_kernel (agglom.cu)
+      ab = up30(o[chunk + lr]);
+      eb = up30((double)((k + 31) / 32 + 6) * EXACT_U1 * ab);
+      dm = o[2 * chunk + lr];
+      Ab[v] = ab;
+      Eb[v] = eb;
+    }
   }
   warp_atomic_absmax(rmax_bits, s);
+  if (nval == 3) {
+    warp_atomic_max_nonneg(rmax_bits + XW_EBMAX, eb);
+    warp_atomic_max_nonneg(rmax_bits + XW_ABMAX, ab);
+    warp_atomic_max_nonneg(rmax_bits + XW_DABS, dm);
+  }
 }
 
 __global__ void sh_init_kernel(int n, int32_t *ids, int32_t *sizes, unsigned *counters,
-                               unsigned long long *rmax_bits) {
+                               unsigned long long *rmax_bits, int32_t *order, int32_t *pos, int32_t *mark,
+                               unsigned long long *xstats, unsigned *xstate) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < n) { ids[v] = v; sizes[v] = 1; }
-  if (v < 8) counters[v] = 0;
-  if (v == 0) *rmax_bits = 0ull;
+  if (v < n) {
+    ids[v] = v;
+    sizes[v] = 1;
+    if (order) { order[v] = v; pos[v] = v; mark[v] = 0; }
+  }
+  if (v < 8) { counters[v] = 0; rmax_bits[v] = 0ull; xstate[v] = 0u; }
+  if (v < 4) xstats[v] = 0ull;
 }
 
 __global__ void sh_prune_init_kernel(unsigned *E, int64_t count, unsigned *beta, int64_t nrows, float *hdr,
@@ -680,6 +1008,9 @@ struct ShWorkspace {
   unsigned *E; unsigned *beta; float *uf; float *hdr; unsigned *dmax; unsigned long long *gbest;
   unsigned long long *scanned; unsigned long long *cta_read; int32_t *pool; int32_t *worklist; unsigned *wcount;
   int32_t *sugg; int64_t lb_stride;
+  // exact NJ mode
+  double *Eb, *Ab, *apartial; int32_t *order[2], *pos[2], *mark, *mlist, *ulist; unsigned *mcount, *xstate;
+  unsigned long long *xstats;
   size_t bytes;
 };
 
@@ -713,6 +1044,16 @@ static ShWorkspace sh_carve(void *base, int64_t n, int G, size_t esz) {
   w.pool = c.take<int32_t>(2 * POOL);
   w.worklist = c.take<int32_t>(chunk + 32);
   w.sugg = c.take<int32_t>(2 * MAX_SCAN_CTAS);
+  w.Eb = c.take<double>(n);
+  w.Ab = c.take<double>(n);
+  w.apartial = c.take<double>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
+  for (int b = 0; b < 2; ++b) { w.order[b] = c.take<int32_t>(n); w.pos[b] = c.take<int32_t>(n); }
+  w.mark = c.take<int32_t>(n);
+  w.mlist = c.take<int32_t>(n);
+  w.ulist = c.take<int32_t>(XT);
+  w.mcount = c.take<unsigned>(4);
+  w.xstate = c.take<unsigned>(8);
+  w.xstats = c.take<unsigned long long>(4);
   w.bytes = c.used();
   return w;
 }
@@ -731,7 +1072,7 @@ struct ShRank {
 template <typename T, bool NJ>
 static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int64_t max_iters, void *comm,
                   const ShPeers *peers_in, unsigned long long epoch, int32_t *joins, int32_t *last2,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int mode) {
   const int sms = sm_count();
   const int target_ctas = sms * 4;
   ShPeers peers;
@@ -742,12 +1083,20 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
   const unsigned long long tag0 = epoch << 32;
   Cand *cand_all = ranks[0].w.cand_all;
   char *gath = ranks[0].w.gath;
-  const bool prune = prune_enabled(NJ) && n > 2;
-  const int min_k = prune_min_k();  // exact pruned scan (agglom_pruned.cuh; policy in agglom.cu)
+  // exact (adaptive strict) NJ: float64, P2P exchange (real or emulated), pruned scan down to the last iteration
+  const bool exact = NJ && sizeof(T) == 8 && mode == CAS_MODE_EXACT;
+  if (exact && !p2p) {
+    set_error("the sharded exact mode needs the P2P exchange (CAS_SHARDED_EXCHANGE=p2p)");
+    return CAS_ERR_UNSUPPORTED;
+  }
+  const bool prune = (exact || prune_enabled(NJ)) && n > 2;
+  const int min_k = exact ? 0 : prune_min_k();  // exact pruned scan (agglom_pruned.cuh; policy in agglom.cu)
   for (auto &rk : ranks) {
-    sh_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((int)n, rk.w.ids, rk.w.sizes,
-                                                                    rk.w.counters, rk.w.rmax_bits);
+    sh_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        (int)n, rk.w.ids, rk.w.sizes, rk.w.counters, rk.w.rmax_bits, exact ? rk.w.order[0] : nullptr,
+        exact ? rk.w.pos[0] : nullptr, rk.w.mark, rk.w.xstats, rk.w.xstate);
     CAS_LAUNCH_CHECK();
+    CAS_CUDA_TRY(cudaMemsetAsync(rk.w.mcount, 0, 4 * sizeof(unsigned), stream));
     if (prune) {
       sh_prune_init_kernel<<<sms * 4, 256, 0, stream>>>(rk.w.E, rk.w.lb_stride * sh_chunk((int)n, G), rk.w.beta,
                                                         sh_chunk((int)n, G), rk.w.hdr, rk.w.dmax, rk.w.gbest,
@@ -757,12 +1106,13 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
   }
   if (NJ && n > 2) {
     const int chunk = sh_chunk((int)n, G);
+    const int nval = exact ? 3 : 1;
     for (auto &rk : ranks) {
       const int nloc = sh_count((int)n, rk.r, G);
-      double *mine = reinterpret_cast<double *>(emu ? gath : rk.w.gath) + (size_t)rk.r * chunk;
+      double *mine = reinterpret_cast<double *>(emu ? gath : rk.w.gath) + (size_t)rk.r * nval * chunk;
       const unsigned blocks = (unsigned)((nloc + 7) / 8 > 0 ? (nloc + 7) / 8 : 1);
       sh_rowsum_kernel<T><<<blocks, 256, 0, stream>>>((const T *)rk.D, ld, (int)n, G, rk.r, mine, chunk, peers,
-                                                      tag0 + 1, rk.w.counters + 2);
+                                                      tag0 + 1, rk.w.counters + 2, nval);
       CAS_LAUNCH_CHECK();
     }
     if (!emu && !p2p) {
@@ -774,7 +1124,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       const double *buf = reinterpret_cast<const double *>(emu ? gath : rk.w.gath);
       sh_rscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
           buf, chunk, (int)n, G, rk.r, rk.w.R, rk.w.rmax_bits, peers, tag0 + 1, prune ? rk.w.uf : nullptr,
-          1.0 / (double)(n - 2));
+          1.0 / (double)(n - 2), nval, rk.w.Eb, rk.w.Ab);
       CAS_LAUNCH_CHECK();
     }
   }
@@ -784,6 +1134,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     const int k = (int)(n - t);
     const int chunk = sh_chunk(k, G);
     const int ncb = (k + TC - 1) / TC;
+    const int cur = (int)(t & 1);
     const unsigned long long tag = tag0 + 2 + (unsigned long long)t;
     // one-way switch to the dense scan once a rank's share of the map is small (cf. PRUNE_MIN_K in agglom.cu)
     const bool prune_it = prune && (double)k * (double)k > (double)min_k * (double)min_k * (double)G;
@@ -813,6 +1164,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
         pa.dmax = rk.w.dmax; pa.gbest = rk.w.gbest; pa.worklist = rk.w.worklist; pa.wcount = rk.w.wcount;
         pa.sugg = rk.w.sugg; pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;
         pa.rmaxb = NJ ? rk.w.rmax_bits : nullptr;
+        pa.xw = exact ? rk.w.rmax_bits : nullptr;
         CAS_CUDA_TRY(launch_pdl(sh_rowtest_kernel<T, NJ>, (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1),
                                 256u, stream, pa, (const T *)rk.D, ld, k, G, rk.r, (const double *)rk.w.R, sa.tinv,
                                 (const Sel *)rk.w.sel, t > 0 ? 1 : 0));
@@ -831,8 +1183,10 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       CAS_NCCL_TRY(g_nccl.AllGather(rk.w.cand_all + rk.r, rk.w.cand_all, sizeof(Cand), NCCL_INT8, comm, stream));
     }
     // --- cols
-    for (auto &rk : ranks) {
-      ShColsArgs ca;
+    std::vector<ShColsArgs> cas_(ranks.size());
+    for (size_t x = 0; x < ranks.size(); ++x) {
+      ShRank &rk = ranks[x];
+      ShColsArgs &ca = cas_[x];
       ca.Dloc = rk.D; ca.ld = ld; ca.k = k; ca.G = G; ca.r = rk.r; ca.chunk = chunk;
       ca.cand_all = emu ? cand_all : rk.w.cand_all;
       ca.mine = (emu ? gath : rk.w.gath) + (size_t)rk.r * 3 * chunk * sizeof(T);
@@ -840,14 +1194,39 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ca.joins = joins; ca.t = (int)t;
       ca.peers = peers; ca.tag = tag; ca.counter = rk.w.counters + 2;
       ca.E = prune_it ? rk.w.E : nullptr; ca.e_stride = rk.w.lb_stride; ca.beta = rk.w.beta;
+      ca.exact = exact ? 1 : 0; ca.R = rk.w.R; ca.tinv = 1.0 / (double)(k - 2);
+      ca.p = PruneArgs{};
+      ca.p.E = rk.w.E; ca.p.stride = rk.w.lb_stride; ca.p.beta = rk.w.beta; ca.p.uf = rk.w.uf; ca.p.hdr = rk.w.hdr;
+      ca.p.dmax = rk.w.dmax; ca.p.gbest = rk.w.gbest; ca.p.worklist = rk.w.worklist; ca.p.wcount = rk.w.wcount;
+      ca.p.rmaxb = NJ ? rk.w.rmax_bits : nullptr; ca.p.xw = exact ? rk.w.rmax_bits : nullptr;
+      ca.ex = ExactArgs{};
+      ca.ex.Eb = rk.w.Eb; ca.ex.Ab = rk.w.Ab; ca.ex.xw = rk.w.rmax_bits; ca.ex.mark = rk.w.mark;
+      ca.ex.mlist = rk.w.mlist; ca.ex.mcount = rk.w.mcount; ca.ex.xstats = rk.w.xstats; ca.ex.order = rk.w.order[cur];
+      ca.xstate = rk.w.xstate;
       const int nloc = sh_count(k, rk.r, G);
+      const unsigned cgrid = (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1);
       if (prune_it) {
-        CAS_CUDA_TRY(launch_pdl(sh_cols_kernel<T>, (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256u,
-                                stream, ca));
+        CAS_CUDA_TRY(launch_pdl(sh_cols_kernel<T>, cgrid, 256u, stream, ca));
       } else {
-        sh_cols_kernel<T><<<(unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1), 256, 0, stream>>>(ca);
+        sh_cols_kernel<T><<<cgrid, 256, 0, stream>>>(ca);
       }
       CAS_LAUNCH_CHECK();
+    }
+    if (exact) {
+      // the two resolver kernels of an ambiguous iteration (return at once otherwise)
+      for (auto &rk : ranks) {
+        ShSumsArgs xa;
+        xa.Dloc = (const double *)rk.D; xa.ld = ld; xa.k = k; xa.G = G; xa.r = rk.r; xa.peers = peers; xa.tag = tag;
+        xa.order = rk.w.order[cur]; xa.ulist = rk.w.ulist; xa.xstate = rk.w.xstate;
+        CAS_CUDA_TRY(launch_pdl(sh_exact_sums_kernel, 1u, 256u, stream, xa));
+        CAS_LAUNCH_CHECK();
+      }
+      for (size_t x = 0; x < ranks.size(); ++x) {
+        const int nloc = sh_count(k, ranks[x].r, G);
+        const unsigned cgrid = (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1);
+        CAS_CUDA_TRY(launch_pdl(sh_cols2_kernel<T>, cgrid, 256u, stream, cas_[x], (const int32_t *)ranks[x].w.ulist));
+        CAS_LAUNCH_CHECK();
+      }
     }
     // --- C2: rows lo, hi, last
     if (!emu && !p2p) {
@@ -868,6 +1247,9 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
       ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.sugg = rk.w.sugg; ma.gbest = rk.w.gbest;
       ma.pool = rk.w.pool; ma.rot = (int)((t * 61) % POOL);
+      ma.exact = exact ? 1 : 0; ma.Eb = rk.w.Eb; ma.Ab = rk.w.Ab; ma.xw = rk.w.rmax_bits; ma.apartial = rk.w.apartial;
+      ma.order_old = exact ? rk.w.order[cur] : nullptr; ma.pos_old = exact ? rk.w.pos[cur] : nullptr;
+      ma.order_new = exact ? rk.w.order[cur ^ 1] : nullptr; ma.pos_new = exact ? rk.w.pos[cur ^ 1] : nullptr;
       if (prune_it) {
         CAS_CUDA_TRY(launch_pdl(sh_merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
                                 (unsigned)MERGE_THREADS, stream, ma));
@@ -886,15 +1268,17 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
 
 static int sh_dispatch(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int dtype, int algo,
                        int64_t max_iters, void *comm, const ShPeers *peers, unsigned long long epoch,
-                       int32_t *joins, int32_t *last2, cudaStream_t stream) {
+                       int32_t *joins, int32_t *last2, cudaStream_t stream, int mode = CAS_MODE_FAST) {
+  CAS_REQUIRE(mode == CAS_MODE_FAST || mode == CAS_MODE_EXACT, "the sharded loop runs in fast or exact mode");
+  CAS_REQUIRE(!(mode == CAS_MODE_EXACT && dtype != CAS_F64), "the exact mode requires a float64 map");
   if (algo == CAS_ALGO_NJ) {
     if (dtype == CAS_F64)
-      return sh_run<double, true>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
-    return sh_run<float, true>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
+      return sh_run<double, true>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream, mode);
+    return sh_run<float, true>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream, mode);
   }
   if (dtype == CAS_F64)
-    return sh_run<double, false>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
-  return sh_run<float, false>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream);
+    return sh_run<double, false>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream, mode);
+  return sh_run<float, false>(ranks, n, ld, G, max_iters, comm, peers, epoch, joins, last2, stream, mode);
 }
 
 }  // namespace cas
@@ -922,6 +1306,18 @@ int cas_sharded_scanned_elements(const void *workspace, int64_t n, int32_t world
   CAS_CUDA_TRY(cudaMemcpyAsync(&h, w.scanned, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CAS_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   *elements = (int64_t)h;
+  return CAS_OK;
+}
+
+int cas_sharded_exact_stats(const void *workspace, int64_t n, int32_t world, int32_t dtype, void *stream,
+                            int64_t *out4) {
+  CAS_REQUIRE(workspace && out4, "null pointer argument");
+  ShWorkspace w = sh_carve(const_cast<void *>(workspace), n > 0 ? n : 1, world > 0 ? world : 1,
+                           dtype == CAS_F64 ? 8 : 4);
+  unsigned long long h[4] = {0, 0, 0, 0};
+  CAS_CUDA_TRY(cudaMemcpyAsync(h, w.xstats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
   return CAS_OK;
 }
 
@@ -1071,8 +1467,8 @@ static int fill_peers(ShPeers &peers, void *const *exchange_ptrs, int world) {
   return CAS_OK;
 }
 
-int cas_sharded_solve_p2p(void *D_local, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int64_t max_iters,
-                          int32_t rank, int32_t world, void *const *exchange_ptrs, uint64_t epoch,
+int cas_sharded_solve_p2p(void *D_local, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
+                          int64_t max_iters, int32_t rank, int32_t world, void *const *exchange_ptrs, uint64_t epoch,
                           int32_t *joins, int32_t *last2, void *workspace, size_t workspace_bytes,
                           void *stream) {
   reset_launch_count();
@@ -1089,11 +1485,11 @@ int cas_sharded_solve_p2p(void *D_local, int64_t n, int64_t ld, int32_t dtype, i
   ranks[0].w = sh_carve(workspace, n, world, dtype == CAS_F64 ? 8 : 4);
   ranks[0].r = rank;
   return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nullptr, &peers, epoch, joins, last2,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, mode);
 }
 
 int cas_sharded_solve_emulated_p2p(void *const *D_locals, int64_t n, int64_t ld, int32_t dtype, int32_t algo,
-                                   int64_t max_iters, int32_t world, void *const *exchange_ptrs,
+                                   int32_t mode, int64_t max_iters, int32_t world, void *const *exchange_ptrs,
                                    uint64_t epoch, int32_t *joins, int32_t *last2, void *const *workspaces,
                                    size_t workspace_bytes, void *stream) {
   reset_launch_count();
@@ -1112,7 +1508,7 @@ int cas_sharded_solve_emulated_p2p(void *const *D_locals, int64_t n, int64_t ld,
     ranks[r].r = r;
   }
   return sh_dispatch(ranks, n, ld, world, dtype, algo, max_iters, nullptr, &peers, epoch, joins, last2,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, mode);
 }
 
 }  // extern "C"

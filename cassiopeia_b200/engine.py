@@ -175,6 +175,26 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     return joins_h, last2_h
 
 
+def loop_launch_floor_us(k: int, iters: int = 2000, kernels_per_iter: int = 3) -> float:
+    """Device microseconds per iteration of the pruned loop's bare launch pattern at live size k
+    (``cas_loop_launch_floor``: same grids and programmatic dependent launches, kernels that do nothing)."""
+    torch = _torch()
+    L = _lib.load()
+    ws_bytes = int(L.cas_agglom_workspace_bytes(int(k), CAS_ALGO_NJ, CAS_MODE_FAST))
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
+    out = None
+    for rep in range(2):  # first pass warms the launch path up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        _lib.check(L.cas_loop_launch_floor(int(k), int(iters), int(kernels_per_iter), ws.data_ptr(), ws_bytes,
+                                           _stream_ptr(torch)), "cas_loop_launch_floor")
+        e1.record()
+        torch.cuda.synchronize()
+        out = 1e3 * e0.elapsed_time(e1) / max(int(iters), 1)
+    return out
+
+
 def smj_solve(cm, missing: int, weights: Optional[np.ndarray], n_states: int,
               function: str = "hamming_similarity_without_missing", max_iters: int = -1):
     """Shared-Mutation-Joining loop (``cas_smj_solve``) on the int32 [n, m] matrix of compact codes `cm`, rows

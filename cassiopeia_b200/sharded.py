@@ -1,10 +1,18 @@
-"""Row-sharded NJ / UPGMA over several B200s (one process per GPU, NCCL over NVLink).
+"""Row-sharded NJ / UPGMA over several B200s (one process per GPU).
 
-The n x n map is dealt to the ranks in 64-row blocks, block-cyclically; every rank builds its
-own rows from the replicated character matrix (no exchange) and the loop exchanges, per
-iteration, the ranks' arg-min candidates and the three rows (lo, hi, last) with two NCCL
-all-gathers issued from the C++ host loop of ``cas_sharded_solve``.  ``torch.distributed`` is
-used only to hand the NCCL unique id to the other ranks.
+The n x n map is dealt to the ranks in 64-row blocks, block-cyclically; every rank builds its own rows from the
+replicated character matrix (no exchange).  Per iteration the loop exchanges the ranks' arg-min candidates and
+the three rows (lo, hi, last).  Default exchange ("p2p"): every rank owns an exchange buffer that its peers map
+through cudaIpc; the scan / cols kernels store straight into the peers' buffers over NVLink and publish
+iteration-tagged flags, the consuming kernels spin on them -- no collective call, no host in the loop
+(csrc/sharded.cu).  ``CAS_SHARDED_EXCHANGE=nccl`` selects two NCCL all-gathers per iteration issued from the C++
+host loop instead (fast mode only).  ``torch.distributed`` only carries the 64-byte IPC handles / the NCCL unique
+id, and a barrier at the start of every solve so that no rank writes a peer's buffer while that peer is still
+reading it for the previous solve.
+
+Modes: "fast" (float32 / float64 map, maintained row sums) and "exact" (float64, NJ: the reference's join list;
+in an ambiguous iteration the ranks exchange the slots whose sequential row sums are needed, the owners evaluate
+them and every rank decides identically).  1-GPU and N-GPU runs give the identical join list in either mode.
 """
 from __future__ import annotations
 
@@ -16,7 +24,20 @@ from typing import Optional
 import numpy as np
 
 from . import _lib, engine
-from ._lib import CAS_ALGO_NJ, CAS_ALGO_UPGMA, CAS_F32, CAS_F64, CAS_MAP_EXACT
+from ._lib import CAS_ALGO_NJ, CAS_ALGO_UPGMA, CAS_F32, CAS_F64, CAS_MAP_EXACT, CAS_MODE_EXACT, CAS_MODE_FAST
+
+_MODE = {"fast": CAS_MODE_FAST, "exact": CAS_MODE_EXACT}
+
+#: exact-mode diagnostics of the most recent sharded solve on this rank (identical on every rank)
+last_exact_stats = {"ambiguous_iterations": 0, "rows_resolved": 0, "max_rows_resolved": 0, "pairs_changed": 0}
+
+
+def _record_exact(L, torch, ws, n, world, code):
+    x4 = (ctypes.c_int64 * 4)()
+    _lib.check(L.cas_sharded_exact_stats(ws.data_ptr(), int(n), int(world), code, engine._stream_ptr(torch), x4),
+               "cas_sharded_exact_stats")
+    for key, v in zip(("ambiguous_iterations", "rows_resolved", "max_rows_resolved", "pairs_changed"), x4):
+        last_exact_stats[key] = int(v)
 
 BLOCK = 64  # rows per ownership block (SHB in csrc/sharded.cu)
 
@@ -74,7 +95,7 @@ def build_shard(cm_dev, missing: int, table, n_states: int, rank: int, world: in
 
 
 def emulated_solve(codes: np.ndarray, missing: int, table, n_states: int, algo: str, world: int,
-                   dtype: str = "f32", max_iters: int = -1, p2p: bool = False):
+                   dtype: str = "f32", max_iters: int = -1, p2p: bool = False, mode: str = "fast"):
     """All `world` virtual ranks in this process on the current GPU (no collective): the same
     kernels as the multi-process path, used to check that sharding does not change the joins."""
     torch = engine._torch()
@@ -97,23 +118,35 @@ def emulated_solve(codes: np.ndarray, missing: int, table, n_states: int, algo: 
         ex_bytes = int(L.cas_exchange_bytes(n, world, code))
         exs = [torch.zeros(ex_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
         eptr = (ctypes.c_void_p * world)(*[e.data_ptr() for e in exs])
-        rc = L.cas_sharded_solve_emulated_p2p(dptr, n, ld, code, algo_code, int(max_iters), int(world), eptr, 1,
-                                              joins.data_ptr(), last2.data_ptr(), wptr, ws_bytes,
+        rc = L.cas_sharded_solve_emulated_p2p(dptr, n, ld, code, algo_code, _MODE[mode], int(max_iters), int(world),
+                                              eptr, 1, joins.data_ptr(), last2.data_ptr(), wptr, ws_bytes,
                                               engine._stream_ptr(torch))
         _lib.check(rc, "cas_sharded_solve_emulated_p2p")
         for e in exs:
             err = ctypes.c_int32(0)
             _lib.check(L.cas_exchange_error(e.data_ptr(), engine._stream_ptr(torch), ctypes.byref(err)),
                        "cas_exchange_error")
-            if err.value:
-                raise _lib.B200LibraryError("a P2P flag wait timed out")
+            _raise_exchange_error(err.value)
+        _record_exact(L, torch, wss[0], n, world, code)
     else:
+        if mode != "fast":
+            raise ValueError("the exact mode needs the P2P exchange (p2p=True)")
         rc = L.cas_sharded_solve_emulated(dptr, n, ld, code, algo_code, int(max_iters), int(world),
                                           joins.data_ptr(), last2.data_ptr(), wptr, ws_bytes,
                                           engine._stream_ptr(torch))
         _lib.check(rc, "cas_sharded_solve_emulated")
     done = njoin if max_iters < 0 else min(njoin, max_iters)
     return joins[:done].cpu().numpy(), last2.cpu().numpy()
+
+
+def _raise_exchange_error(code: int) -> None:
+    if code == 1:
+        raise _lib.B200LibraryError("a P2P flag wait timed out (peer rank stalled or died)")
+    if code == 2:
+        raise _lib.B200LibraryError("exact mode: more than 128 slots tie inside the error window in one iteration "
+                                    "(de-duplicate the cells or solve on one GPU)")
+    if code:
+        raise _lib.B200LibraryError(f"P2P exchange error {code}")
 
 
 class NcclGroup:
@@ -187,8 +220,18 @@ class PeerGroup:
         err = ctypes.c_int32(0)
         _lib.check(_lib.load().cas_exchange_error(self.own, engine._stream_ptr(torch), ctypes.byref(err)),
                    "cas_exchange_error")
-        if err.value:
-            raise _lib.B200LibraryError("a P2P flag wait timed out (peer rank stalled or died)")
+        _raise_exchange_error(err.value)
+
+    def begin_solve(self):
+        """Handshake before a solve: every rank has finished the previous one (its kernels no longer read their
+        exchange buffer) and has its modules loaded, so the first flag wait cannot time out on start-up skew and
+        no rank's first stores land in a buffer that is still being read."""
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.epoch += 1
 
     def close(self):
         import torch.distributed as dist
@@ -219,7 +262,7 @@ def _record_scanned(L, torch, ws, n, world, code):
     last_scanned_elements = int(out.value)
 
 
-def sharded_solve_p2p(shard, n: int, algo: str, group: PeerGroup, max_iters: int = -1):
+def sharded_solve_p2p(shard, n: int, algo: str, group: PeerGroup, max_iters: int = -1, mode: str = "fast"):
     """P2P variant of ``sharded_solve``: NVLink stores + flags from inside the kernels, no NCCL."""
     torch = engine._torch()
     L = _lib.load()
@@ -231,22 +274,25 @@ def sharded_solve_p2p(shard, n: int, algo: str, group: PeerGroup, max_iters: int
     njoin = max(int(n) - 2, 0)
     joins = torch.full((njoin + 1, 2), -1, dtype=torch.int32, device="cuda")
     last2 = torch.full((2,), -1, dtype=torch.int32, device="cuda")
-    group.epoch += 1
+    group.begin_solve()
     rc = L.cas_sharded_solve_p2p(shard.data_ptr(), int(n), ld, code, CAS_ALGO_NJ if algo == "nj" else CAS_ALGO_UPGMA,
-                                 int(max_iters), group.rank, group.world, group.array(), group.epoch,
+                                 _MODE[mode], int(max_iters), group.rank, group.world, group.array(), group.epoch,
                                  joins.data_ptr(), last2.data_ptr(), ws.data_ptr(), ws_bytes,
                                  engine._stream_ptr(torch))
     _lib.check(rc, "cas_sharded_solve_p2p")
     _record_scanned(L, torch, ws, n, group.world, code)
+    _record_exact(L, torch, ws, n, group.world, code)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     out = joins[:done].cpu().numpy(), last2.cpu().numpy()
     group.check()
     return out
 
 
-def sharded_solve(shard, n: int, algo: str, group: NcclGroup, max_iters: int = -1):
-    """Runs the sharded loop on this rank's shard ([capacity, ld] CUDA tensor, destroyed).
-    Every rank returns the same (joins, last2)."""
+def sharded_solve(shard, n: int, algo: str, group: NcclGroup, max_iters: int = -1, mode: str = "fast"):
+    """Runs the sharded loop on this rank's shard ([capacity, ld] CUDA tensor, destroyed) with two NCCL all-gathers
+    per iteration.  Every rank returns the same (joins, last2).  Fast mode only."""
+    if mode != "fast":
+        raise _lib.B200LibraryError("the NCCL exchange runs the fast mode only; the exact mode needs the P2P exchange")
     torch = engine._torch()
     L = _lib.load()
     ld = int(shard.stride(0))
@@ -266,49 +312,102 @@ def sharded_solve(shard, n: int, algo: str, group: NcclGroup, max_iters: int = -
 
 
 # ---- bench.py entry for --gpus N > 1 ------------------------------------------------------------
-def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
+def fits_one_gpu(rows: int, esz: int) -> bool:
+    """Policy of the multi-GPU entry points: a map that fits one B200 (with the loop's workspace) is solved on ONE
+    GPU.  The pruned loop is bound by its per-iteration latency, not by bandwidth or capacity, and every sharded
+    iteration adds two NVLink flag round trips and two launches: measured 1.5-1.7x SLOWER on 2-8 GPUs than on one at
+    50k cells (profiles/).  Sharding the loop is for maps beyond one GPU's memory."""
+    torch = engine._torch()
+    total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+    return rows * engine.padded_ld(rows) * esz <= 0.7 * total
+
+
+def _gather_map_rank0(torch, dist, cm_dev, missing_code, table, n_states, dt, method, rank, world, D):
+    """Every rank builds a contiguous block of rows of the map; rank 0 receives the blocks straight into its map
+    over NVLink (NCCL send / recv).  Returns rank 0's full map (None elsewhere)."""
+    n = int(cm_dev.shape[0])
+    bounds = [(n * r) // world for r in range(world + 1)]
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    if rank == 0:
+        engine.whd_map(cm_dev, missing_code, table, n_states, dtype=dt, method=method, rows=(r0, r1), out=D[r0:r1])
+        reqs = [dist.irecv(D[bounds[r]:bounds[r + 1]], src=r) for r in range(1, world)]
+        for q in reqs:
+            q.wait()
+        return D
+    blk = engine.whd_map(cm_dev, missing_code, table, n_states, dtype=dt, method=method, rows=(r0, r1))
+    dist.send(blk, dst=0)
+    return None
+
+
+def bench_entry(args, B):
+    """`B` is the bench module (workload, roofline helpers).  Two paths:
+    * the map fits one GPU (BASELINE configs 1-3): every rank builds 1/N of the map rows, rank 0 gathers them over
+      NVLink and runs the loop alone (fits_one_gpu explains why); `--sharded-loop` forces the sharded loop;
+    * otherwise (config 4, 200k cells in float64): block-cyclic shards built in place, row-sharded loop with the
+      P2P exchange, exact or fast mode."""
+    import time as _time
+
     import torch
     import torch.distributed as dist
-
-    import bench
 
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dt = "f32"
-    codes, missing_code, table, n_states = bench.make_workload(args)
+    dt = "f32" if args.mode == "fast" else "f64"
+    esz = 4 if dt == "f32" else 8
+    mode = "fast" if args.mode == "fast" else "exact"
+    codes, missing_code, table, n_states = B.make_workload(args)
     n = codes.shape[0]
-    exchange = os.environ.get("CAS_SHARDED_EXCHANGE", "p2p")
-    if exchange == "p2p":
-        try:
-            group = PeerGroup(n, dt)
-            solve_fn = sharded_solve_p2p
-        except Exception as e:  # cudaIpc unavailable in this container
-            if rank == 0:
-                print(f"# P2P exchange unavailable ({e}); using NCCL all-gathers", flush=True)
-            exchange = "nccl"
-    if exchange != "p2p":
-        group = NcclGroup()
-        solve_fn = sharded_solve
+    sharded_loop = bool(getattr(args, "sharded_loop", False)) or not fits_one_gpu(n, esz)
     cm_dev = torch.from_numpy(codes).cuda()
     launches = [0]
+    stats = {}
+    exchange = None
+    group = None
+    if sharded_loop:
+        exchange = os.environ.get("CAS_SHARDED_EXCHANGE", "p2p")
+        if exchange == "p2p":
+            group = PeerGroup(n, dt)  # raises if cudaIpc peer mapping is unavailable: no silent fallback
+            solve_fn = sharded_solve_p2p
+        elif exchange == "nccl":
+            group = NcclGroup()
+            solve_fn = sharded_solve
+        else:
+            raise ValueError(f"CAS_SHARDED_EXCHANGE={exchange!r}: expected 'p2p' or 'nccl'")
+    else:
+        ld = engine.padded_ld(n)
+        D = (torch.zeros((n, ld), dtype=torch.float32 if dt == "f32" else torch.float64, device="cuda")
+             if rank == 0 else None)
+    method = "exact"
 
-    def step():
-        shard = build_shard(cm_dev, missing_code, table, n_states, rank, world, dt)
-        launches[0] += engine.last_launch_count()
+    def step(cm):
         mid = torch.cuda.Event(enable_timing=True)
-        mid.record()
-        joins, last2 = solve_fn(shard, n, "nj", group)
+        if sharded_loop:
+            shard = build_shard(cm, missing_code, table, n_states, rank, world, dt)
+            launches[0] += engine.last_launch_count()
+            mid.record()
+            joins, last2 = solve_fn(shard, n, args.algo, group, mode=mode)
+            launches[0] += engine.last_launch_count()
+            stats.update(last_exact_stats)
+            stats["scanned_elements"] = last_scanned_elements
+            return joins, last2, mid
+        full = _gather_map_rank0(torch, dist, cm, missing_code, table, n_states, dt, method, rank, world, D)
         launches[0] += engine.last_launch_count()
-        return joins, last2, mid
+        mid.record()
+        if rank == 0:
+            joins, last2 = engine.agglomerate(full, n, args.algo, args.mode)
+            launches[0] += engine.last_launch_count()
+            stats.update(engine.last_stats)
+            return joins, last2, mid
+        return None, None, mid
 
     for _ in range(args.warmup):
-        step()
+        step(cm_dev)
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = B.ClockSampler(local_rank)
     sampler.start()
     launches[0] = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -316,7 +415,7 @@ def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
     ev0.record()
     mids, ends = [], []
     for _ in range(args.steps):
-        joins, last2, mid = step()
+        joins, last2, mid = step(cm_dev)
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         mids.append(mid)
@@ -330,87 +429,82 @@ def bench_entry(args, metric, workload_config, scan_bytes, ClockSampler, peaks):
     t = torch.tensor([total_ms, loop_ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, loop_ms = float(t[0]), float(t[1])
-    # every rank must hold the same join list
-    h = torch.tensor([int(np.int64(joins.astype(np.int64).sum())), int(joins[-1, 0])], dtype=torch.int64, device="cuda")
-    hmax, hmin = h.clone(), h.clone()
-    dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
-    dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
-    assert torch.equal(hmax, hmin), "ranks disagree on the join list"
-    # end to end: pinned host character matrix + weights -> device, shard build, loop, join list -> host
+    jh = B.join_hash(joins, last2) if joins is not None else None
+    if sharded_loop:
+        # every rank must hold the same join list: compare the full hashes
+        hashes = [None] * world
+        dist.all_gather_object(hashes, jh)
+        assert len(set(hashes)) == 1, f"ranks disagree on the join list: {hashes}"
+    # end to end: pinned host character matrix (+ weights) -> device, map, loop, join list -> host
     cm_pin = torch.from_numpy(codes).pin_memory()
     torch.cuda.synchronize()
     dist.barrier()
-    import time as _time
     t_e2e0 = _time.perf_counter()
     cm_e2e = cm_pin.to("cuda", non_blocking=True)
-    shard = build_shard(cm_e2e, missing_code, table, n_states, rank, world, dt)  # uploads the weight table
-    j_e2e, l_e2e = solve_fn(shard, n, "nj", group)
+    j_e2e, l_e2e, _ = step(cm_e2e)  # uploads the weight table, returns host join lists
     torch.cuda.synchronize()
     e2e_s = torch.tensor([_time.perf_counter() - t_e2e0], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    assert np.array_equal(j_e2e, joins)
-    scanned = torch.tensor([last_scanned_elements], dtype=torch.int64, device="cuda")
+    if joins is not None:
+        assert np.array_equal(j_e2e, joins)
+    scanned = torch.tensor([int(stats.get("scanned_elements", 0)) if (sharded_loop or rank == 0) else 0],
+                           dtype=torch.int64, device="cuda")
     dist.all_reduce(scanned, op=dist.ReduceOp.SUM)
     scanned = int(scanned.item())
-    # the HBM-bound kernel of this path is the DENSE sharded scan: measure it live on a bounded sample (first
-    # iterations at full size, CAS_PRUNE=0) -- the timed loop above uses the exact pruned scan
-    dense_iters = min(300, n - 2)
-    os.environ["CAS_PRUNE"] = "0"
-    try:
-        shard = build_shard(cm_dev, missing_code, table, n_states, rank, world, dt)
-        solve_fn(shard, n, "nj", group, max_iters=8)
-        shard = build_shard(cm_dev, missing_code, table, n_states, rank, world, dt)
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        dist.barrier()
-        d0.record()
-        solve_fn(shard, n, "nj", group, max_iters=dense_iters)
-        d1.record()
-        torch.cuda.synchronize()
-    finally:
-        os.environ.pop("CAS_PRUNE", None)
-    dms = torch.tensor([d0.elapsed_time(d1)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(dms, op=dist.ReduceOp.MAX)
-    dense_ms = float(dms[0])
     if rank == 0:
-        peak, peak_src = peaks()
+        peak, peak_src = B.peaks()
         ms_per_step = total_ms / args.steps
-        b_alg = scan_bytes(n, 4)
+        b_alg = B.scan_bytes(n, esz)
+        n_scans = max(n - 2, 1)
         achieved = b_alg / (loop_ms * 1e-3) / 1e9
-        exch = (("P2P NVLink stores + tagged flags from inside the scan/cols kernels" if exchange == "p2p"
-                 else "2 NCCL all-gathers") + " (24 B x G candidates; 3 rows x k x 4 B)")
-        kk = np.arange(n - dense_iters + 1, n + 1, dtype=np.float64)
-        d_bytes = float((4 * kk * (kk - 1) / 2).sum())
-        d_gbs = d_bytes / (dense_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "sh_scan_kernel<float,NJ>", "achieved": d_gbs, "peak": peak * world,
-                    "unit": "GB/s", "frac": d_gbs / (peak * world), "traffic": None,
-                    "peak_source": peak_src + f" x {world} GPUs", "loop_ms": loop_ms,
-                    "sample": f"dense sharded scan (CAS_PRUNE=0), first {dense_iters} iterations at full size, "
-                              f"{dense_ms:.1f} ms incl. the exchange and merge launches",
-                    "exchange_per_iteration": exch}
-        if scanned:
-            roofline["pruned_loop"] = {
-                "kernels": ["sh_rowtest_kernel", "sh_scan_pruned_kernel", "sh_cols_kernel", "sh_merge_kernel"],
-                "loop_ms": loop_ms, "launch_ms_mean": loop_ms / max(n - 2, 1),
-                "traffic": scanned * 4 / max(n - 2, 1), "read_fraction_of_algorithmic": scanned * 4 / b_alg,
-                "algorithmic_equivalent_gbs": achieved, "algorithmic_equivalent_over_peak": achieved / (peak * world),
-                "note": "exact pruned scan (DESIGN 4.1): the timed loop; traffic = bytes all ranks actually read "
-                        "per iteration (kernel counters)"}
+        loop_gpus = world if sharded_loop else 1
+        tname = "float" if esz == 4 else "double"
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak * loop_gpus, "unit": "GB/s",
+                    "frac": achieved / (peak * loop_gpus), "peak_source": peak_src + f" x {loop_gpus} GPU(s) running the loop",
+                    "loop_ms": loop_ms, "map_and_gather_ms": ms_per_step - loop_ms,
+                    "traffic": scanned * esz / n_scans if scanned else 1.0005 * b_alg / n_scans,
+                    "algorithmic_bytes_per_launch_mean": b_alg / n_scans,
+                    "latency_model": {"us_per_iteration": 1e3 * loop_ms / n_scans,
+                                      "launches_per_iteration": (6 if mode == "exact" else 4) if sharded_loop else 3,
+                                      "nvlink_flag_waits_per_iteration": 2 if sharded_loop else 0},
+                    "note": "exact pruned scan: frac = algorithmic bytes / time / peak exceeds 1 by construction "
+                            "(DESIGN 4.1); the loop is latency-bound"}
+        if sharded_loop:
+            roofline["kernel"] = (f"sh_scan_pruned_kernel<{tname}> (+ sh_rowtest, sh_cols, sh_merge"
+                                  + (", sh_exact_sums, sh_cols2" if mode == "exact" else "") + ")")
+            roofline["exchange_per_iteration"] = (
+                ("P2P NVLink stores + tagged flags from inside the scan / cols kernels" if exchange == "p2p"
+                 else "2 NCCL all-gathers") + f" (40 B x G candidates; 3 rows x k x {esz} B)")
         else:
-            roofline.update({"achieved": achieved, "frac": achieved / (peak * world)})
+            roofline["kernel"] = f"scan_pruned_kernel<{tname}> (+ prune_rowtest_kernel, merge_kernel) on rank 0"
+        cfg = B.workload_config(args, world)
+        cfg["parallelism"] = (f"map and loop row-sharded over {world} GPUs (block-cyclic 64-row blocks)" if sharded_loop
+                              else f"map rows built on {world} GPUs and gathered over NVLink; loop on ONE GPU "
+                                   "(the map fits one B200 and the loop is latency-bound: sharding it is slower)")
         out = {
-            "metric": metric, "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": dt, "data": "synthetic",
-            "config": workload_config(args, world, "fast/exact-map"),
+            "metric": B.metric_name(args), "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": dt, "data": "synthetic",
+            "config": cfg, "mode": f"{args.mode}/exact-map",
+            "loop": "sharded" if sharded_loop else "single-gpu", "exchange": exchange,
             "clocks": clocks, "gpu_launches": int(launches[0]),
             "roofline": roofline,
+            "parity": {"join_hash": jh, "joins": int(joins.shape[0]),
+                       "ranks_agree_on_full_join_hash": True if sharded_loop else None,
+                       "near_ties": stats.get("near_ties"), "exact_ties": stats.get("exact_ties"),
+                       "ambiguous_iterations": int(stats.get("ambiguous_iterations", 0)),
+                       "rows_resolved": int(stats.get("rows_resolved", 0)),
+                       "max_rows_resolved": int(stats.get("max_rows_resolved", 0)),
+                       "pairs_changed_by_resolution": int(stats.get("pairs_changed", 0)),
+                       "note": "same seeded workload as the N=1 line: equal join_hash means the identical join list"},
             "e2e": {"value": float(e2e_s[0]), "unit": "s",
-                    "h2d_bytes_per_step": int(codes.nbytes + table.nbytes) * world,
-                    "d2h_bytes_per_step": int(joins.nbytes + last2.nbytes) * world,
-                    "note": "per rank: pinned host character matrix + weight table -> device, shard build, "
-                            "sharded loop, join list -> host (wall clock, max over ranks)"},
+                    "h2d_bytes_per_step": int(codes.nbytes + (table.nbytes if table is not None else 0)) * world,
+                    "d2h_bytes_per_step": int(joins.nbytes + last2.nbytes) * loop_gpus,
+                    "note": "per rank: pinned host character matrix + weight table -> device, map rows, "
+                            + ("sharded loop" if sharded_loop else "NVLink gather, loop on rank 0")
+                            + ", join list -> host (wall clock, max over ranks)"},
         }
         print(json.dumps(out), flush=True)
-    group.close()
+    if group is not None:
+        group.close()
     dist.destroy_process_group()

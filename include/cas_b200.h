@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CAS_ABI_VERSION 1
+#define CAS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CAS_API __attribute__((visibility("default")))
@@ -199,15 +199,21 @@ CAS_API int cas_exchange_open(const void *handle64, void **ptr_out);
 CAS_API int cas_exchange_close(void *ptr);
 CAS_API int cas_exchange_free(void *ptr);
 CAS_API int cas_exchange_error(const void *own_exchange_dev, void *stream, int32_t *error_out);
-CAS_API int cas_sharded_solve_p2p(void *D_local_dev, int64_t n, int64_t ld, int32_t dtype, int32_t algo,
+/* mode: CAS_MODE_FAST (float32 or float64 map, maintained sums) or CAS_MODE_EXACT (float64 map, NJ: the reference's
+ * join list -- in an ambiguous iteration the ranks exchange their marked slots, the owners evaluate the reference's
+ * sequential row sums of those slots and every rank decides identically; at most 128 slots per iteration, else the
+ * exchange error flag is set to 2).  cas_sharded_exact_stats: as cas_agglom_exact_stats, for a sharded workspace. */
+CAS_API int cas_sharded_solve_p2p(void *D_local_dev, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                           int64_t max_iters, int32_t rank, int32_t world, void *const *exchange_ptrs,
                           uint64_t epoch, int32_t *joins_dev, int32_t *last2_dev, void *workspace_dev,
                           size_t workspace_bytes, void *stream);
 CAS_API int cas_sharded_solve_emulated_p2p(void *const *D_locals_dev, int64_t n, int64_t ld, int32_t dtype,
-                                   int32_t algo, int64_t max_iters, int32_t world,
+                                   int32_t algo, int32_t mode, int64_t max_iters, int32_t world,
                                    void *const *exchange_ptrs, uint64_t epoch, int32_t *joins_dev,
                                    int32_t *last2_dev, void *const *workspaces_dev,
                                    size_t workspace_bytes, void *stream);
+CAS_API int cas_sharded_exact_stats(const void *workspace_dev, int64_t n, int32_t world, int32_t dtype, void *stream,
+                            int64_t *out4);
 
 /* ---- single-step hooks (float64, reference operation order) -----------------
  * cas_nj_q       : Q[n,n] (zero diagonal) of NeighborJoiningSolver.compute_q
@@ -244,6 +250,12 @@ CAS_API int cas_agglom_scanned_elements(const void *workspace_dev, int64_t n, vo
  * on the work list summed over all iterations, and the final cumulative drift C of the bounds */
 CAS_API int cas_agglom_prune_diag(const void *workspace_dev, int64_t n, void *stream, int64_t *rows_listed,
                           double *drift);
+
+/* Measurement aid (bench.py's latency model): enqueues `iters` iterations of the pruned loop's launch pattern at
+ * live size k -- `kernels_per_iter` programmatically chained launches with the loop's grid sizes -- with kernels
+ * that only pass one word along.  The device time of this sequence is the launch floor of the loop. */
+CAS_API int cas_loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, void *workspace_dev,
+                          size_t workspace_bytes, void *stream);
 
 /* number of kernels the last cas_*_solve / cas_whd_map / cas_solve_host call on this
  * thread launched (bench.py's gpu_launches) */
