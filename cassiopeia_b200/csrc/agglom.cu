@@ -213,25 +213,26 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(256) prune_rowtest_kernel(PruneArgs p, const T *__restrict__ D, int64_t ld, int k,
                                                             const double *__restrict__ R, double tinv,
-                                                            const Sel *prev, int has_prev) {
+                                                            const Sel *prev, int has_prev, int t) {
+  TL_STAMP(t, 0, 0);
   pdl_wait();
   pdl_launch_dependents();
+  TL_STAMP(t, 0, 1);
+  __shared__ IterRaw sc;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i >= 1 && i < k;
-  int plo = -1, phi = -1;
-  bool moved = false;
-  if (has_prev) {
-    plo = prev->lo; phi = prev->hi;
-    moved = phi != k;  // the previous iteration's last slot was k: a node moved into slot hi unless hi was last
-  }
-  prune_rowtest<T, NJ>(p, valid, i, i, D + (int64_t)(valid ? i : 0) * ld, (valid && NJ) ? R[i] : 0.0, tinv, plo, phi,
-                       moved, prune_wfloor(p, k, tinv));
+  const double Ri = (valid && NJ) ? R[i] : 0.0;  // in flight while the scalars are staged
+  iter_raw_load(&sc, p, prev, has_prev != 0);
+  prune_rowtest<T, NJ>(p, sc, valid, i, i, Ri, tinv, k, iter_wfloor(sc, p.xw != nullptr, k, tinv));
+  TL_STAMP(t, 0, 2);
 }
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a, PruneArgs p) {
+  TL_STAMP(a.t, 1, 0);
   pdl_wait();
   pdl_launch_dependents();
+  TL_STAMP(a.t, 1, 1);
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
   __shared__ unsigned long long sRead[SCAN_WARPS];
@@ -240,16 +241,22 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   const T *__restrict__ D = static_cast<const T *>(a.D);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
+  __shared__ IterRaw sc;
+  iter_raw_load(&sc, p, nullptr, false);
   RowScan<T, NJ> rs;
   rs.R = a.R; rs.ids = a.ids; rs.tinv = a.tinv;
-  rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
+  rs.umax = NJ ? a.tinv * __longlong_as_double((long long)sc.rmax) : 0.0;
   rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
   rs.sbest = INFINITY; rs.ssi = -1; rs.ssj = -1; rs.uif = 0.f;
-  rs.wfloor = prune_wfloor(p, k, a.tinv);
+  rs.wfloor = iter_wfloor(sc, p.xw != nullptr, k, a.tinv);
   PruneWarp pw;
   pw.gb_seen = INFINITY; pw.nread = 0;
-  const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
-  const float cnow = prune_cnow(p);
+  // unit u goes to warp (u / gridDim) of CTA (u % gridDim): consecutive units -- in particular the short units of
+  // the two rewritten rows, the only ones that read a lot -- land on different SMs
+  const int gw = warp * gridDim.x + blockIdx.x, W = gridDim.x * SCAN_WARPS;
+  const float cnow = iter_cnow(sc);
+  // short units: one round of 128-bit loads per lane (8 sub-segments of floats, 4 of doubles)
+  constexpr int UNIT_S = sizeof(T) == 8 ? PRUNE_UNIT / 2 : PRUNE_UNIT;
   {
     // work units, round-robin over all warps.  Rows queued from the back of the list (bound unknown: the whole
     // row is read -- the two rows the last merge rewrote, or every row in the first iteration) are cut into
@@ -257,15 +264,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     // path.  Rows queued from the front passed a bound test that will skip nearly all of their sub-segments:
     // wide units, one coalesced load of 32 bounds per step.
     const long long nsub_max = ((long long)k - 1 + SW - 1) / SW;
-    const long long upr_s = (nsub_max + PRUNE_UNIT - 1) / PRUNE_UNIT;  // units per row, short
+    const long long upr_s = (nsub_max + UNIT_S - 1) / UNIT_S;  // units per row, short
     const long long upr_w = (nsub_max + PRUNE_WIDE - 1) / PRUNE_WIDE;  // units per row, wide
-    const long long ushort = (long long)__ldcg(p.wcount + 1) * upr_s;
-    const long long nunits = ushort + (long long)__ldcg(p.wcount) * upr_w;
+    const long long ushort = (long long)sc.wc1 * upr_s;
+    const long long nunits = ushort + (long long)sc.wc0 * upr_w;
     for (long long u = gw; u < nunits; u += W) {
       const bool shrt = u < ushort;
       const long long v = shrt ? u : u - ushort;
       const long long upr = shrt ? upr_s : upr_w;
-      const int unit = shrt ? PRUNE_UNIT : PRUNE_WIDE;
+      const int unit = shrt ? UNIT_S : PRUNE_WIDE;
       const long long r = v / upr;
       const int i = p.worklist[shrt ? p.wlast - (int)r : (int)r];
       const int sb = (int)(v - r * upr) * unit;
@@ -276,22 +283,29 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     }
   }
 
+  TL_STAMP(a.t, 1, 2);
   if (lane == 0) sRead[warp] = pw.nread;
   prune_publish_suggestion<T, NJ>(rs, p);
   Cand c = block_best(rs.bq, rs.bi, rs.bj, rs.b2, a.ids, sCand);  // contains a __syncthreads
+  TL_STAMP(a.t, 1, 3);
   if (threadIdx.x == 0) {
     a.cand[blockIdx.x] = c;
     unsigned long long tot = 0;
     for (int w2 = 0; w2 < SCAN_WARPS; ++w2) tot += sRead[w2];
     p.cta_read[blockIdx.x] = tot;
     __threadfence();
+    TL_STAMP(a.t, 1, 4);
     unsigned prev = atomicInc(a.counter, gridDim.x - 1);
     sLast = (prev == gridDim.x - 1);
+    TL_STAMP(a.t, 1, 5);
   }
   __syncthreads();
   if (!sLast) return;
-  __threadfence();
+  // no fence on the reading side: every CTA fenced before its atomicInc, and everything the last CTA reads of the
+  // others' results (candidates, bounds, counters) is read through L2 (__ldcg / atomics), never through its L1
+  TL_STAMP(a.t, 1, 6);
   c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
+  TL_STAMP(a.t, 1, 7);
   if constexpr (NJ && sizeof(T) == 8) {
     if (a.exact) exact_resolve<true>(a, &p, (int)gridDim.x, c);  // reads the work list: before it is reset below
   }
@@ -304,29 +318,34 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     }
     return;
   }
+  // the tail's independent pieces run on different warps: selection + join (warp 0), per-iteration state of the
+  // pruned scan (warp 1), diagnostics (warp 2)
   if (threadIdx.x == 0) {
-    Sel s;
-    s.lo = lo;
-    s.hi = hi;
-    s.dij = (double)D[(int64_t)s.lo * a.ld + s.hi];
-    s.size_lo = a.sizes ? a.sizes[s.lo] : 1;
-    s.size_hi = a.sizes ? a.sizes[s.hi] : 1;
-    s.id_lo = a.ids[s.lo];
-    s.id_hi = a.ids[s.hi];
-    *a.sel = s;
-    a.joins[2 * a.t] = min(s.id_lo, s.id_hi);
-    a.joins[2 * a.t + 1] = max(s.id_lo, s.id_hi);
-    const double gap = c.q2 - c.q;
-    if (gap <= 1e-6 * fmax(1.0, fabs(c.q))) atomicAdd(a.stats + 0, 1ull);
-    if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
+    a.sel->lo = lo;
+    a.sel->hi = hi;
+    a.sel->size_lo = a.sizes ? a.sizes[lo] : 1;
+    a.sel->size_hi = a.sizes ? a.sizes[hi] : 1;
+    const int id_lo = a.ids[lo], id_hi = a.ids[hi];
+    a.sel->id_lo = id_lo;
+    a.sel->id_hi = id_hi;
+    a.joins[2 * a.t] = min(id_lo, id_hi);
+    a.joins[2 * a.t + 1] = max(id_lo, id_hi);
+  }
+  if (threadIdx.x == 96) a.sel->dij = (double)D[(int64_t)lo * a.ld + hi];  // the map element is a DRAM round trip
+  if (threadIdx.x == 32) {
     // every other CTA has finished (counter): clear the per-iteration state, commit the drift
     *p.gbest = enc_f64(INFINITY);
-    atomicAdd(a.stats + 2, (unsigned long long)p.wcount[0] + p.wcount[1]);  // diagnostics: rows listed, whole loop
-    p.wcount[0] = 0u;
-    p.wcount[1] = 0u;
     prune_commit(p);
     p.beta[lo] = enc_f32(-INFINITY);
     p.beta[hi] = enc_f32(-INFINITY);
+  }
+  if (threadIdx.x == 64) {
+    const double gap = c.q2 - c.q;
+    if (gap <= 1e-6 * fmax(1.0, fabs(c.q))) atomicAdd(a.stats + 0, 1ull);
+    if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
+    atomicAdd(a.stats + 2, (unsigned long long)p.wcount[0] + p.wcount[1]);  // diagnostics: rows listed, whole loop
+    p.wcount[0] = 0u;
+    p.wcount[1] = 0u;
   }
   {
     unsigned long long tot = 0;
@@ -335,12 +354,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
     if (lane == 0 && tot) atomicAdd(p.scanned, tot);
   }
+  TL_STAMP(a.t, 1, 8);
   // rows lo and hi are rewritten by the merge: bounds unknown
   const int nsk = (k + SW - 1) / SW;
   for (int sgm = threadIdx.x; sgm < nsk; sgm += SCAN_THREADS) {
     p.E[(int64_t)lo * p.stride + sgm] = enc_f32(-INFINITY);
     p.E[(int64_t)hi * p.stride + sgm] = enc_f32(-INFINITY);
   }
+  TL_STAMP(a.t, 1, 9);
 }
 
 struct MergeArgs {
@@ -366,34 +387,67 @@ struct MergeArgs {
   // exact NJ mode (agglom_exact.cuh): error bound / absolute-sum bound of every maintained row sum, their running
   // maxima, per-CTA partial sums of |new row|
   int exact; double *Eb; double *Ab; unsigned long long *xw; double *apartial;
+  int t;  // iteration index
+  void *newcol; int64_t newcol_stride;  // pruned scan: contiguous copies of the two rewritten columns (PruneArgs)
+  double *pmax; unsigned *pufup;        // per-CTA maxima ([grid][4]) and largest uf increase ([grid])
 };
 
-template <typename T, bool NJ>
-__device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int hi, int last) {
-  const T *D = static_cast<const T *>(a.D);
-  const int64_t ld = a.ld;
-  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last, a.rot,
-                                         [=](int si, int sj) { return D + (int64_t)si * ld + sj; });
-}
+constexpr int WARM_THREADS = MERGE_THREADS - 32;  // the merge's last CTA: warp 0 sums, warps 1.. warm-start gbest
 
 template <typename T, bool NJ>
+__device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int hi, int last, int tid) {
+  const T *D = static_cast<const T *>(a.D);
+  const int64_t ld = a.ld;
+  prune_warm_start<T, NJ, WARM_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last, a.rot,
+                                        [=](int si, int sj) { return D + (int64_t)si * ld + sj; }, tid);
+}
+
+// Latency notes (profiles/r2_timeline_*.txt): the kernel is a chain of dependent memory round trips, so (1) the
+// selection is loaded once per CTA and broadcast through shared memory, (2) every load of the main body is issued in
+// one wave before anything is consumed, (3) running maxima go through per-CTA slots that the last CTA reduces
+// (no same-address atomics from every warp), (4) in the last CTA warp 0 sums the partial sums while the other warps
+// re-evaluate the warm-start pool.
+template <typename T, bool NJ>
 __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
+  TL_STAMP(a.t, 2, 0);
   pdl_wait();  // no-op unless launched with programmatic stream serialization (the pruned loop)
   pdl_launch_dependents();
-  __shared__ double sPart[MERGE_THREADS / 32];
-  __shared__ double sPartA[MERGE_THREADS / 32];
+  TL_STAMP(a.t, 2, 1);
+  __shared__ double sPart[MERGE_THREADS / 32], sPartA[MERGE_THREADS / 32];
+  __shared__ double sMax[4][MERGE_THREADS / 32];  // |R|, Eb, Ab, |new d| maxima of the CTA's warps
+  __shared__ unsigned sUfUp[MERGE_THREADS / 32];
+  __shared__ Sel sSel;
   __shared__ bool sLast;
   T *__restrict__ D = static_cast<T *>(a.D);
-  const Sel s = *a.sel;
-  if (s.lo < 0) return;  // the scan found no candidate (publish_no_candidate)
-  const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1;
+  const int k = a.k, last = k - 1;
   const int64_t ld = a.ld;
   const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
-  double contrib = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // loads that do not depend on the selection, issued before it is known
+  const bool live = v < k;
+  const double Rv0 = (live && a.maintain_R) ? a.R[v] : 0.0;
+  const double Eb0 = (live && a.exact) ? a.Eb[v] : 0.0, Ab0 = (live && a.exact) ? a.Ab[v] : 0.0;
+  const float uf0 = (live && a.prune && a.maintain_R) ? a.uf[v] : 0.f;
+  const T dl = (live && v != last) ? D[(int64_t)last * ld + v] : (T)0;  // row of the node that may move
+  const int ord0 = (live && a.order_old) ? a.order_old[v] : 0;
+  if (threadIdx.x == 0) sSel = *a.sel;
+  __syncthreads();
+  const Sel s = sSel;
+  if (s.lo < 0) return;  // the scan found no candidate (publish_no_candidate)
+  const int lo = s.lo, hi = s.hi;
+  double contrib = 0.0, mine = 0.0;
   float uf_up = 0.f;            // pruned scan: increase of this slot's fl32(u) (columns that keep their node)
   double ebv = 0.0, abv = 0.0;  // exact mode: this row's bounds after the update
 
-  if (v < k) {
+  if (live) {
+    // second wave: everything that needs the selection
+    const bool other = v != lo && v != hi;
+    const double da = other ? (double)D[(int64_t)lo * ld + v] : 0.0;
+    const double db = other ? (double)D[(int64_t)hi * ld + v] : 0.0;
+    int p_lo = 0, p_hi = 0;
+    if (a.order_old) { p_lo = a.pos_old[lo]; p_hi = a.pos_old[hi]; }
+    const int id_last = (v == last && hi != last) ? a.ids[last] : 0;
+    const int sz_last = (v == last && hi != last && a.sizes) ? a.sizes[last] : 0;
     if (v == lo) {
       D[(int64_t)lo * ld + lo] = (T)0;
       a.ids[lo] = a.new_id;
@@ -401,11 +455,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     } else if (v == hi) {
       D[(int64_t)hi * ld + hi] = (T)0;
     } else {
-      const double da = (double)D[(int64_t)lo * ld + v];
-      const double db = (double)D[(int64_t)hi * ld + v];
       double nv;
       if (NJ) {
-        // 0.5 * ((d_vi + d_vj) - d_ij)   (NeighborJoiningSolver.py:254-258)
+        // 0.5 * ((d_vi + d_vj) - d_ij)   (NeighborJoiningSolver.py:254-258).  d_ij comes from the scan kernel:
+        // elements (lo, hi) and (hi, lo) are rewritten by this launch (the moved node's distance to the new node)
         nv = __dmul_rn(0.5, __dsub_rn(__dadd_rn(da, db), s.dij));
       } else {
         // (s_i * d_vi + s_j * d_vj) / (s_i + s_j)   (UPGMASolver.py:231-234)
@@ -415,52 +468,51 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       }
       const T nvs = round_to<T>(nv);
       contrib = (double)nvs;
+      const bool moves = (v == last && hi != last);
+      const int vdst = moves ? hi : v;  // this node's slot after the compaction
       double Rv = 0.0;
       if (a.maintain_R) {
-        const double x1 = __dsub_rn(a.R[v], da), x2 = __dsub_rn(x1, db);
+        const double x1 = __dsub_rn(Rv0, da), x2 = __dsub_rn(x1, db);
         Rv = __dadd_rn(x2, contrib);
+        mine = Rv;
+        a.R[vdst] = Rv;
         if (a.exact) {
           // three rounded results: the error of R_v grows by at most u (|x1| + |x2| + |Rv|); everything rounded up
-          ebv = __dadd_ru(a.Eb[v], __dmul_ru(__dadd_ru(__dadd_ru(fabs(x1), fabs(x2)), fabs(Rv)), EXACT_U1));
-          abv = fmax(__dsub_ru(__dsub_ru(__dadd_ru(a.Ab[v], fabs(contrib)), fabs(da)), fabs(db)), 0.0);
-          const int dst = (v == last && hi != last) ? hi : v;
-          a.Eb[dst] = ebv;
-          a.Ab[dst] = abv;
+          ebv = __dadd_ru(Eb0, __dmul_ru(__dadd_ru(__dadd_ru(fabs(x1), fabs(x2)), fabs(Rv)), EXACT_U1));
+          abv = fmax(__dsub_ru(__dsub_ru(__dadd_ru(Ab0, fabs(contrib)), fabs(da)), fabs(db)), 0.0);
+          a.Eb[vdst] = ebv;
+          a.Ab[vdst] = abv;
         }
       }
       if (hi != last && v != last) {
         // the node in the last live slot moves into slot hi
-        const T l = D[(int64_t)last * ld + v];
-        D[(int64_t)hi * ld + v] = l;
-        D[(int64_t)v * ld + hi] = l;
+        D[(int64_t)hi * ld + v] = dl;
+        D[(int64_t)v * ld + hi] = dl;
+        if (a.prune) static_cast<T *>(a.newcol)[a.newcol_stride + v] = dl;
       }
       D[(int64_t)lo * ld + v] = nvs;
       D[(int64_t)v * ld + lo] = nvs;
+      if (a.prune) static_cast<T *>(a.newcol)[vdst] = nvs;
       if (a.prune && a.maintain_R) {
         // u of the next scan, and its increase for the columns that keep their node (the new node's column
         // and the moved node's column are folded into the bounds exactly by the next row test)
-        const bool moves = (v == last && hi != last);
         const float un = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
-        if (!moves) uf_up = un - a.uf[v];
-        a.uf[moves ? hi : v] = un;
+        if (!moves) uf_up = un - uf0;
+        a.uf[vdst] = un;
       }
-      if (v == last && hi != last) {
+      if (moves) {
         D[(int64_t)hi * ld + lo] = nvs;
         D[(int64_t)lo * ld + hi] = nvs;
         D[(int64_t)hi * ld + hi] = (T)0;
-        a.ids[hi] = a.ids[last];
-        if (a.sizes) a.sizes[hi] = a.sizes[last];
-        if (a.maintain_R) a.R[hi] = Rv;
-      } else if (a.maintain_R) {
-        a.R[v] = Rv;
+        a.ids[hi] = id_last;
+        if (a.sizes) a.sizes[hi] = sz_last;
       }
     }
-    // strict NJ: rebuild the id-ordered list of live slots
+    // strict / exact NJ: rebuild the id-ordered list of live slots
     if (a.order_old) {
       const int p = v;  // thread p handles the p-th live node in id order
-      const int p_lo = a.pos_old[lo], p_hi = a.pos_old[hi];
       if (p != p_lo && p != p_hi) {
-        int sl = a.order_old[p];
+        int sl = ord0;
         if (sl == last) sl = hi;
         const int np = p - (p > p_lo ? 1 : 0) - (p > p_hi ? 1 : 0);
         a.order_new[np] = sl;
@@ -472,82 +524,116 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       }
     }
   }
+  TL_STAMP(a.t, 2, 2);
 
-  if (a.prune && a.maintain_R) {
-    // largest upward drift of any column's u: one atomic per warp, skipped unless it raises the maximum
-    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(uf_up));
-    if ((threadIdx.x & 31) == 0 && m > __ldcg(a.dmax)) atomicMax(a.dmax, m);
-  }
   if (a.prune && !a.maintain_R) {
     // UPGMA: no row sums; the last CTA to finish warm-starts gbest
-    __shared__ bool sLastU;
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       unsigned prev = atomicInc(a.counter, gridDim.x - 1);
-      sLastU = (prev == gridDim.x - 1);
+      sLast = (prev == gridDim.x - 1);
     }
     __syncthreads();
-    if (sLastU) warm_start_gbest<T, NJ>(a, lo, hi, last);
+    if (sLast && threadIdx.x >= 32) warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32);
     return;
   }
   if (!a.maintain_R) return;
-  {
-    // keep the screening bound max|row sum| current (all lanes participate)
-    double mine = 0.0;
-    if (v < k && v != lo && v != hi) mine = (v == last && hi != last) ? a.R[hi] : a.R[v];
-    warp_atomic_absmax(a.rmax_bits, mine);
-  }
+
+  // per-warp reductions: the new row's sum (fixed shuffle tree: deterministic), |new row| and the maxima
   double acontrib = fabs(contrib);
-  if (a.exact) {
-    warp_atomic_max_nonneg(a.xw + XW_EBMAX, ebv);
-    warp_atomic_max_nonneg(a.xw + XW_ABMAX, abv);
-    warp_atomic_max_nonneg(a.xw + XW_DABS, acontrib);
+  double m0 = fabs(mine), m1 = ebv, m2 = abv, m3 = acontrib;
+  unsigned up = enc_f32(uf_up);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
+    m0 = fmax(m0, __shfl_down_sync(0xffffffffu, m0, off));
+    if (a.exact) {
+      acontrib = __dadd_rn(acontrib, __shfl_down_sync(0xffffffffu, acontrib, off));
+      m1 = fmax(m1, __shfl_down_sync(0xffffffffu, m1, off));
+      m2 = fmax(m2, __shfl_down_sync(0xffffffffu, m2, off));
+      m3 = fmax(m3, __shfl_down_sync(0xffffffffu, m3, off));
+    }
   }
-  // deterministic sum of the new row: fixed 256-wide chunks, shuffle tree, then sequential
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
-  if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = contrib;
-  if (a.exact) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acontrib = __dadd_rn(acontrib, __shfl_down_sync(0xffffffffu, acontrib, off));
-    if ((threadIdx.x & 31) == 0) sPartA[threadIdx.x >> 5] = acontrib;
+  if (a.prune) up = __reduce_max_sync(0xffffffffu, up);
+  if (lane == 0) {
+    sPart[warp] = contrib; sPartA[warp] = acontrib;
+    sMax[0][warp] = m0; sMax[1][warp] = m1; sMax[2][warp] = m2; sMax[3][warp] = m3;
+    sUfUp[warp] = up;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double sum = 0.0;
-    for (int w = 0; w < MERGE_THREADS / 32; ++w) sum = __dadd_rn(sum, sPart[w]);
-    a.partial[blockIdx.x] = sum;
-    if (a.exact) {
-      double asum = 0.0;
-      for (int w = 0; w < MERGE_THREADS / 32; ++w) asum = __dadd_rn(asum, sPartA[w]);
-      a.apartial[blockIdx.x] = asum;
+    double sum = 0.0, asum = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    unsigned u = enc_f32(0.f);
+    for (int w = 0; w < MERGE_THREADS / 32; ++w) {
+      sum = __dadd_rn(sum, sPart[w]);
+      asum = __dadd_rn(asum, sPartA[w]);
+      x0 = fmax(x0, sMax[0][w]); x1 = fmax(x1, sMax[1][w]); x2 = fmax(x2, sMax[2][w]); x3 = fmax(x3, sMax[3][w]);
+      u = max(u, sUfUp[w]);
     }
+    a.partial[blockIdx.x] = sum;
+    a.apartial[blockIdx.x] = asum;
+    double *pm = a.pmax + 4 * (size_t)blockIdx.x;
+    pm[0] = x0; pm[1] = x1; pm[2] = x2; pm[3] = x3;
+    a.pufup[blockIdx.x] = u;
+    TL_STAMP(a.t, 2, 3);
     __threadfence();
+    TL_STAMP(a.t, 2, 4);
     unsigned prev = atomicInc(a.counter, gridDim.x - 1);
     sLast = (prev == gridDim.x - 1);
+    TL_STAMP(a.t, 2, 5);
   }
   __syncthreads();
-  if (sLast && threadIdx.x == 0) {
-    __threadfence();
-    double sum = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
-    a.R[lo] = sum;
-    atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
-    if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
-    if (a.exact) {
-      // every element of the new row passed through at most 5 + 8 + gridDim rounded additions
-      double asum = 0.0;
-      for (int b = 0; b < (int)gridDim.x; ++b) asum = __dadd_rn(asum, ((volatile double *)a.apartial)[b]);
-      const double ab = up30(asum);
-      const double eb = up30((double)(16 + (int)gridDim.x) * EXACT_U1 * ab);
-      a.Ab[lo] = ab;
-      a.Eb[lo] = eb;
-      atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(eb));
-      atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(ab));
+  if (!sLast) return;
+  // Last CTA.  Everything it reads of the other CTAs' results is read through L2 (no fence needed on this side).
+  TL_STAMP(a.t, 2, 6);
+  if (warp == 0) {
+    const int nb = (int)gridDim.x;
+    double sum, asum;
+    sum_partials_one_warp(a.partial, a.apartial, nb, a.exact != 0, sum, asum);
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    unsigned u = enc_f32(0.f);
+    for (int b = lane; b < nb; b += 32) {
+      const double *pm = a.pmax + 4 * (size_t)b;
+      x0 = fmax(x0, __ldcg(pm + 0));
+      if (a.exact) { x1 = fmax(x1, __ldcg(pm + 1)); x2 = fmax(x2, __ldcg(pm + 2)); x3 = fmax(x3, __ldcg(pm + 3)); }
+      if (a.prune) u = max(u, __ldcg(a.pufup + b));
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      x0 = fmax(x0, __shfl_down_sync(0xffffffffu, x0, off));
+      x1 = fmax(x1, __shfl_down_sync(0xffffffffu, x1, off));
+      x2 = fmax(x2, __shfl_down_sync(0xffffffffu, x2, off));
+      x3 = fmax(x3, __shfl_down_sync(0xffffffffu, x3, off));
+    }
+    u = __reduce_max_sync(0xffffffffu, u);
+    if (lane == 0) {
+      a.R[lo] = sum;
+      x0 = fmax(x0, fabs(sum));
+      // running maxima: this thread is their only writer while the merge runs
+      if ((unsigned long long)__double_as_longlong(x0) > a.rmax_bits[0]) a.rmax_bits[0] = __double_as_longlong(x0);
+      if (a.prune) {
+        a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
+        if (u > *a.dmax) *a.dmax = u;
+      }
+      if (a.exact) {
+        const double ab = up30(asum);
+        const double eb = up30(new_row_sum_depth(nb) * EXACT_U1 * ab);
+        a.Ab[lo] = ab;
+        a.Eb[lo] = eb;
+        x1 = fmax(x1, eb);
+        x2 = fmax(x2, ab);
+        if ((unsigned long long)__double_as_longlong(x1) > a.xw[XW_EBMAX]) a.xw[XW_EBMAX] = __double_as_longlong(x1);
+        if ((unsigned long long)__double_as_longlong(x2) > a.xw[XW_ABMAX]) a.xw[XW_ABMAX] = __double_as_longlong(x2);
+        if ((unsigned long long)__double_as_longlong(x3) > a.xw[XW_DABS]) a.xw[XW_DABS] = __double_as_longlong(x3);
+      }
+    }
+    TL_STAMP(a.t, 2, 7);
+  } else if (a.prune) {
+    // entries touching slot lo are dropped, so the warm start needs neither R[lo] nor anything warp 0 writes
+    warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32);
   }
-  if (sLast && a.prune) warm_start_gbest<T, NJ>(a, lo, hi, last);
+  TL_STAMP(a.t, 2, 8);
 }
 
 // strict NJ: R[c] = ((0 + d[o_0][c]) + d[o_1][c]) + ... over live nodes in id order.
@@ -723,6 +809,8 @@ struct AgglomWorkspace {
   int64_t lb_stride;
   // exact NJ mode
   double *Eb, *Ab, *Rex, *apartial; int32_t *mark, *mlist; unsigned *mcount; unsigned long long *xstats;
+  double *newcol;  // [2][n] elements of the map's type
+  double *pmax; unsigned *pufup;
   size_t bytes;
 };
 
@@ -763,6 +851,9 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.mlist = c.take<int32_t>(n);
   w.mcount = c.take<unsigned>(4);
   w.xstats = c.take<unsigned long long>(4);
+  w.newcol = c.take<double>(2 * (size_t)n);
+  w.pmax = c.take<double>(4 * ((n + MERGE_THREADS - 1) / MERGE_THREADS + 1));
+  w.pufup = c.take<unsigned>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
   w.bytes = c.used();
   return w;
 }
@@ -896,8 +987,10 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
       pa.split = 1; pa.wide = prune_wide; pa.wlast = (int)n + 31;
       pa.xw = exact_nj ? w.rmax_bits : nullptr;
       pa.rmaxb = NJ ? w.rmax_bits : nullptr;
+      pa.newcol = w.newcol; pa.newcol_stride = n;
       CAS_CUDA_TRY(launch_pdl(prune_rowtest_kernel<T, NJ>, (unsigned)((k + 255) / 256), 256u, stream, pa,
-                              (const T *)D, ld, k, (const double *)w.R, sa.tinv, (const Sel *)w.sel, t > 0 ? 1 : 0));
+                              (const T *)D, ld, k, (const double *)w.R, sa.tinv, (const Sel *)w.sel, t > 0 ? 1 : 0,
+                              (int)t));
       CAS_LAUNCH_CHECK();
       grid = sms * 2;  // few units per iteration in steady state: a small grid keeps the launch + tail short
       CAS_CUDA_TRY(launch_pdl(scan_pruned_kernel<T, NJ>, (unsigned)grid, (unsigned)SCAN_THREADS, stream, sa, pa));
@@ -919,6 +1012,9 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.cand = w.cand; ma.ncand = grid; ma.sugg = w.sugg; ma.gbest = w.gbest; ma.pool = w.pool;
     ma.rot = (int)((t * 61) % POOL);
     ma.exact = exact_nj ? 1 : 0; ma.Eb = w.Eb; ma.Ab = w.Ab; ma.xw = w.rmax_bits; ma.apartial = w.apartial;
+    ma.t = (int)t;
+    ma.newcol = w.newcol; ma.newcol_stride = n;
+    ma.pmax = w.pmax; ma.pufup = w.pufup;
     if (prune_it) {
       CAS_CUDA_TRY(launch_pdl(merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
                               (unsigned)MERGE_THREADS, stream, ma));
@@ -1139,6 +1235,15 @@ int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, in
 }  // namespace cas
 
 namespace cas {
+#ifdef CAS_TIMELINE
+int timeline_set(void *buf, int t0, int t1) {
+  Timeline tl;
+  tl.buf = (unsigned long long *)buf; tl.t0 = t0; tl.t1 = t1;
+  CAS_CUDA_TRY(cudaMemcpyToSymbol(g_timeline, &tl, sizeof(tl)));
+  return CAS_OK;
+}
+#endif
+
 // Launch floor of the pruned loop: the same three programmatically chained launches per iteration (grids of the row
 // test, the pruned scan and the merge at live size k) with kernels that do nothing but pass one word along.  What
 // bench.py reports as the latency model's floor: an iteration cannot be faster than its launches.

@@ -273,20 +273,75 @@ __device__ __forceinline__ Cand cand_shfl_down(const Cand &c, int off) {
   return o;
 }
 
-// Reduces the lanes' bests to one candidate per CTA (thread 0 returns it).
+// Sum of the merge kernels' per-CTA partial sums (and, in exact mode, of the partial sums of absolute values) by ONE
+// warp in a FIXED order: lane-strided, then a shuffle tree.  Deterministic and independent of everything but `count`,
+// hence identical in the single-GPU and the sharded merge (whose ranks all compute the merged row redundantly).
+// Lane 0 returns the sums.  Any element passes through at most count / 32 + 1 + 5 rounded additions here.
+__device__ __forceinline__ void sum_partials_one_warp(const double *partial, const double *apartial, int count,
+                                                      bool with_abs, double &sum, double &asum) {
+  const int lane = threadIdx.x & 31;
+  sum = 0.0;
+  asum = 0.0;
+  for (int b = lane; b < count; b += 32) {
+    sum = __dadd_rn(sum, __ldcg(partial + b));
+    if (with_abs) asum = __dadd_rn(asum, __ldcg(apartial + b));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sum = __dadd_rn(sum, __shfl_down_sync(0xffffffffu, sum, off));
+    asum = __dadd_rn(asum, __shfl_down_sync(0xffffffffu, asum, off));
+  }
+}
+// bound on the rounded additions any element of the new row passes through: 5 + 8 inside its CTA, then the above
+__device__ __forceinline__ double new_row_sum_depth(int count) { return (double)(13 + count / 32 + 1 + 5 + 2); }
+
+// Warp-wide candidate reduction, order-free and therefore identical to any sequence of cand_merge calls: the winner
+// is the lexicographic minimum of (q, key), the runner-up the smallest value among everything else (the other lanes'
+// winners and every lane's own runner-up).  Three butterfly minima instead of five rounds of full merges.  Every
+// lane returns the result.
+__device__ __forceinline__ Cand warp_cand_reduce(Cand c) {
+  const int lane = threadIdx.x & 31;
+  const bool has = c.si >= 0;
+  double qm = has ? c.q : INFINITY;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) qm = fmin(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+  unsigned long long km = (has && c.q == qm) ? c.key : ~0ull;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, km, off);
+    km = o < km ? o : km;
+  }
+  const unsigned wb = __ballot_sync(0xffffffffu, has && c.q == qm && c.key == km);
+  const int wl = wb ? __ffs(wb) - 1 : 0;
+  double r = (wb && lane == wl) ? c.q2 : fmin(c.q2, has ? c.q : INFINITY);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) r = fmin(r, __shfl_xor_sync(0xffffffffu, r, off));
+  Cand o;
+  o.q = wb ? qm : INFINITY;
+  o.key = wb ? km : ~0ull;
+  o.si = __shfl_sync(0xffffffffu, c.si, wl);
+  o.sj = __shfl_sync(0xffffffffu, c.sj, wl);
+  if (!wb) { o.si = -1; o.sj = -1; }
+  o.q2 = r;
+  return o;
+}
+
+// Reduces the lanes' bests to one candidate per CTA (every thread of warp 0 returns it; the other warps return
+// their own warp's candidate).  Contains one __syncthreads.
 template <bool COH = false>
 __device__ __forceinline__ Cand block_best(double bq, int bi, int bj, double b2, const int32_t *ids, Cand *sCand) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Cand c;
   c.q = bq; c.si = bi; c.sj = bj; c.q2 = b2;
   c.key = (bi >= 0) ? make_key(ld_state<COH>(ids + bi), ld_state<COH>(ids + bj)) : ~0ull;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) cand_merge(c, cand_shfl_down(c, off));
+  c = warp_cand_reduce(c);
   if (lane == 0) sCand[warp] = c;
   __syncthreads();
-  c = sCand[0];
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < SCAN_WARPS; ++w) cand_merge(c, sCand[w]);
+  if (warp == 0) {
+    Cand e;
+    e.q = INFINITY; e.key = ~0ull; e.si = -1; e.sj = -1; e.q2 = INFINITY;
+    if (lane < (int)(blockDim.x >> 5)) e = sCand[lane];
+    c = warp_cand_reduce(e);
   }
   return c;
 }
@@ -305,14 +360,14 @@ __device__ __forceinline__ Cand reduce_candidates(const Cand *cand, int count, C
     o.q2 = __ldcg(&cand[x].q2);
     cand_merge(c, o);
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) cand_merge(c, cand_shfl_down(c, off));
+  c = warp_cand_reduce(c);
   __syncthreads();
   if (lane == 0) sCand[warp] = c;
   __syncthreads();
-  c = sCand[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) cand_merge(c, sCand[w]);
-  return c;  // identical in every thread
+  Cand e;
+  e.q = INFINITY; e.key = ~0ull; e.si = -1; e.sj = -1; e.q2 = INFINITY;
+  if (lane < (int)(blockDim.x >> 5)) e = sCand[lane];
+  return warp_cand_reduce(e);  // identical in every thread
 }
 
 }  // namespace cas

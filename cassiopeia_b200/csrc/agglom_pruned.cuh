@@ -53,7 +53,58 @@ struct PruneArgs {
   unsigned long long *cta_read;  // [gridDim] per-CTA counts of this launch (summed by the last CTA)
   const unsigned long long *xw;  // exact NJ mode: running maxima behind exact_window() (agglom_common.cuh); else null
   const unsigned long long *rmaxb;  // NJ: bits of the running max |row sum| (umax = tinv * that bounds every |u_j|)
+  const void *newcol;            // [2][newcol_stride] map elements: the two columns the previous merge rewrote, by
+  int64_t newcol_stride;         // slot -- d(v, lo) and d(v, hi) as the merge computed them.  The row test reads these
+                                 // contiguous copies instead of two map elements per row (one per 2 MB page: the
+                                 // scattered reads were most of the row test's time)
 };
+
+// Per-iteration scalars that the previous kernels left in global memory (drift, gbest, running maxima, the previous
+// selection, work-list lengths).  Every warp of every CTA needs them; loading each word once per CTA (a different
+// thread each, then shared memory) instead of once per warp keeps thousands of requests for the same few words from
+// queueing up at their L2 slices, which the timeline (profiles/r2_timeline_*.txt) showed as ~0.5 us per dependent step.
+struct IterRaw {
+  unsigned long long rmax, eb, ab, dm, gbest;
+  unsigned dmaxw, wc0, wc1;
+  float hdr, uf_lo, uf_hi;
+  int plo, phi;
+};
+
+__device__ __forceinline__ void iter_raw_load(IterRaw *s, const PruneArgs &p, const void *prev_sel, bool want_prev) {
+  const int t = threadIdx.x;
+  if (t == 0) s->rmax = p.rmaxb ? __ldcg(p.rmaxb) : 0ull;
+  if (t == 32) s->eb = p.xw ? __ldcg(p.xw + XW_EBMAX) : 0ull;
+  if (t == 64) s->ab = p.xw ? __ldcg(p.xw + XW_ABMAX) : 0ull;
+  if (t == 96) s->dm = p.xw ? __ldcg(p.xw + XW_DABS) : 0ull;
+  if (t == 128) s->gbest = __ldcg(p.gbest);
+  if (t == 160) { s->dmaxw = __ldcg(p.dmax); s->hdr = __ldcg(p.hdr); }
+  if (t == 192) { s->wc0 = __ldcg(p.wcount); s->wc1 = __ldcg(p.wcount + 1); }
+  if (t == 224) {
+    int plo = -1, phi = -1;
+    if (want_prev && prev_sel) {
+      const int *ps = static_cast<const int *>(prev_sel);  // Sel: lo, hi first
+      plo = __ldcg(ps);
+      phi = __ldcg(ps + 1);
+    }
+    s->plo = plo;
+    s->phi = phi;
+    s->uf_lo = (plo >= 0 && p.uf) ? __ldcg(p.uf + plo) : 0.f;
+    s->uf_hi = (phi >= 0 && p.uf) ? __ldcg(p.uf + phi) : 0.f;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float iter_cnow(const IterRaw &s) {
+  const float d = fmaxf(dec_f32(s.dmaxw), 0.f);
+  return __fadd_ru(s.hdr, __fmul_ru(d, 1.000001f));
+}
+__device__ __forceinline__ double iter_wfloor(const IterRaw &s, bool exact, int k, double tinv) {
+  if (!exact) return 0.0;
+  const double rmax = __longlong_as_double((long long)s.rmax), eb = __longlong_as_double((long long)s.eb);
+  const double ab = __longlong_as_double((long long)s.ab), dm = __longlong_as_double((long long)s.dm);
+  const double delta = eb + (double)k * EXACT_U1 * ab;
+  const double Delta = 2.0 * tinv * delta + 8.0 * EXACT_U1 * (dm + 2.0 * tinv * (rmax + delta));
+  return 2.0 * (2.0 * Delta * 1.0001);
+}
 
 // largest |u_j| of any column (NJ), as a float rounded up; 0 for UPGMA
 __device__ __forceinline__ float prune_umaxf(const PruneArgs &p, double tinv) {
@@ -170,34 +221,46 @@ __device__ __forceinline__ bool prune_impossible(float e, float cnow, float uif,
 // bounds, test the row, queue it if it may hold a competitive pair.  `row` = the row's map elements,
 // prev_* = slots of the previous join (prev_lo < 0: none yet; prev_moved: a node moved into slot prev_hi).
 template <typename T, bool NJ>
-__device__ __forceinline__ void prune_rowtest(const PruneArgs &p, bool valid, int64_t ridx, int i, const T *row,
-                                              double Ri, double tinv, int prev_lo, int prev_hi, bool prev_moved,
-                                              double wfloor = 0.0) {
-  const float cnow = prune_cnow(p);
+__device__ __forceinline__ void prune_rowtest(const PruneArgs &p, const IterRaw &sc, bool valid, int64_t ridx, int i,
+                                              double Ri, double tinv, int k_prev_last, double wfloor) {
+  const T *newcol = static_cast<const T *>(p.newcol);
+  const float cnow = iter_cnow(sc);
+  const int prev_lo = sc.plo, prev_hi = sc.phi;
+  const bool prev_moved = prev_hi != k_prev_last;  // a node moved into slot hi unless hi was the last live slot
   bool unsafe = false, unknown = false;
   if (valid) {
     unsigned b = p.beta[ridx];
     unknown = b == enc_f32(-INFINITY);  // the whole row will be read
     if (prev_lo >= 0 && i != prev_lo && i != prev_hi) {
       unsigned *erow = p.E + ridx * p.stride;
-      if (i > prev_lo) {
-        const float x = screen_value(row[prev_lo]);
-        const float q = x - (NJ ? p.uf[prev_lo] : 0.f);
-        const unsigned e = enc_f32((q + cnow) - 1e-6f * (fabsf(x) + fabsf(q) + cnow));
-        erow[prev_lo / SW] = min(erow[prev_lo / SW], e);
+      // both loads first: one round trip for the two read-modify-writes
+      const bool fold_lo = i > prev_lo, fold_hi = prev_moved && i > prev_hi;
+      const unsigned e_lo_old = fold_lo ? erow[prev_lo / SW] : 0u, e_hi_old = fold_hi ? erow[prev_hi / SW] : 0u;
+      const float x_lo = fold_lo ? screen_value(newcol[i]) : 0.f;
+      const float x_hi = fold_hi ? screen_value(newcol[p.newcol_stride + i]) : 0.f;
+      if (fold_lo) {
+        const float q = x_lo - (NJ ? sc.uf_lo : 0.f);
+        const unsigned e = enc_f32((q + cnow) - 1e-6f * (fabsf(x_lo) + fabsf(q) + cnow));
+        unsigned cur = min(e_lo_old, e);
+        erow[prev_lo / SW] = cur;
         b = min(b, e);
+        if (fold_hi && prev_hi / SW == prev_lo / SW) {
+          const float q2 = x_hi - (NJ ? sc.uf_hi : 0.f);
+          const unsigned e2 = enc_f32((q2 + cnow) - 1e-6f * (fabsf(x_hi) + fabsf(q2) + cnow));
+          erow[prev_hi / SW] = min(cur, e2);
+          b = min(b, e2);
+        }
       }
-      if (prev_moved && i > prev_hi) {
-        const float x = screen_value(row[prev_hi]);
-        const float q = x - (NJ ? p.uf[prev_hi] : 0.f);
-        const unsigned e = enc_f32((q + cnow) - 1e-6f * (fabsf(x) + fabsf(q) + cnow));
-        erow[prev_hi / SW] = min(erow[prev_hi / SW], e);
+      if (fold_hi && !(fold_lo && prev_hi / SW == prev_lo / SW)) {
+        const float q = x_hi - (NJ ? sc.uf_hi : 0.f);
+        const unsigned e = enc_f32((q + cnow) - 1e-6f * (fabsf(x_hi) + fabsf(q) + cnow));
+        erow[prev_hi / SW] = min(e_hi_old, e);
         b = min(b, e);
       }
     }
-    const double gb = dec_f64(__ldcg(p.gbest));
-    unsafe = !prune_impossible<T, NJ>(dec_f32(b), cnow, NJ ? (float)(tinv * Ri) : 0.f, gb, wfloor,
-                                      prune_umaxf(p, tinv));
+    const double gb = dec_f64(sc.gbest);
+    const float umaxf = NJ ? __double2float_ru(tinv * __longlong_as_double((long long)sc.rmax)) : 0.f;
+    unsafe = !prune_impossible<T, NJ>(dec_f32(b), cnow, NJ ? (float)(tinv * Ri) : 0.f, gb, wfloor, umaxf);
     // an unsafe row's beta is rebuilt by its work units (atomicMin)
     p.beta[ridx] = unsafe ? enc_f32(INFINITY) : b;
   }
@@ -382,15 +445,16 @@ __device__ __forceinline__ void prune_publish_suggestion(const RowScan<T, NJ> &r
 // `rot` rotates which CTA feeds which entry from iteration to iteration: in steady state only the first few
 // CTAs of the scan have any work unit, and with a fixed mapping only their entries would ever be refreshed
 // while every join kills entries -- the pool would shrink to a handful of pairs and the bound would go loose.
+// Called by whole warps: NTHREADS threads with indices tid = 0 .. NTHREADS - 1 (a multiple of 32).
 template <typename T, bool NJ, int NTHREADS, typename Addr>
 __device__ __forceinline__ void prune_warm_start(int32_t *pool, const Cand *cand, int ncand, const int32_t *sugg,
                                                  unsigned long long *gbest, const double *R, double tinv_next,
-                                                 int lo, int hi, int last, int rot, Addr addr) {
+                                                 int lo, int hi, int last, int rot, Addr addr, int tid) {
   constexpr int EPT = (POOL + NTHREADS - 1) / NTHREADS;
   int px[EPT][3], py[EPT][3];
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
-    const int x = threadIdx.x + e * NTHREADS;
+    const int x = tid + e * NTHREADS;
 #pragma unroll
     for (int c = 0; c < 3; ++c) { px[e][c] = -1; py[e][c] = -1; }
     if (x < POOL) {
@@ -426,7 +490,7 @@ __device__ __forceinline__ void prune_warm_start(int32_t *pool, const Cand *cand
   double best = INFINITY;
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
-    const int x = threadIdx.x + e * NTHREADS;
+    const int x = tid + e * NTHREADS;
     double qb = INFINITY;
     int bi = -1, bj = -1;
 #pragma unroll

@@ -62,6 +62,9 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
 int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements);
 int agglom_read_exact_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *out4);
 int loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, void *workspace, cudaStream_t stream);
+#ifdef CAS_TIMELINE
+int timeline_set(void *buf, int t0, int t1);
+#endif
 int agglom_read_prune_diag(const void *workspace, int64_t n, cudaStream_t stream, int64_t *rows_listed, double *drift);
 int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                  int64_t max_iters, int32_t *joins, int32_t *last2, void *workspace,
@@ -170,6 +173,12 @@ int cas_smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, cons
   return smj_solve(cm, n, m, missing, w, n_states, fn, S_map, ld, max_iters, joins, last2, workspace,
                    workspace_bytes, (cudaStream_t)stream);
 }
+
+#ifdef CAS_TIMELINE
+__attribute__((visibility("default"))) int cas_debug_timeline(void *buf, int t0, int t1) {
+  return cas::timeline_set(buf, t0, t1);
+}
+#endif
 
 int cas_loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, void *workspace, size_t workspace_bytes,
                           void *stream) {

@@ -74,6 +74,33 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 bool pdl_enabled();
 
+// Development aid (build with -DCAS_TIMELINE, see scripts/timeline.py): per-CTA clock64 stamps at the phase
+// boundaries of the loop kernels, for a window of iterations.  Compiled out of the product library.
+#ifdef CAS_TIMELINE
+struct Timeline {
+  unsigned long long *buf;  // [window][3 kernels][TL_CTAS][TL_SLOTS]
+  int t0, t1;
+};
+constexpr int TL_CTAS = 512, TL_SLOTS = 12;
+static __device__ Timeline g_timeline;  // one copy per translation unit; agglom.cu's is set by timeline_set()
+__device__ __forceinline__ void tl_stamp(int t, int kernel, int slot) {
+  const Timeline tl = g_timeline;
+  if (tl.buf && t >= tl.t0 && t < tl.t1 && blockIdx.x < TL_CTAS) {
+    unsigned long long c = clock64();
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    unsigned long long *p = tl.buf + ((((size_t)(t - tl.t0) * 3 + kernel) * TL_CTAS + blockIdx.x) * TL_SLOTS);
+    p[slot] = c;
+    if (slot == 0) { p[TL_SLOTS - 1] = g; p[TL_SLOTS - 2] = smid; }
+  }
+}
+#define TL_STAMP(t, kernel, slot) do { if (threadIdx.x == 0) ::cas::tl_stamp((t), (kernel), (slot)); } while (0)
+#else
+#define TL_STAMP(t, kernel, slot) do { } while (0)
+#endif
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream,
                                      Args... args) {

@@ -194,18 +194,14 @@ __global__ void __launch_bounds__(256) sh_rowtest_kernel(PruneArgs p, const T *_
                                                          const Sel *prev, int has_prev) {
   pdl_wait();
   pdl_launch_dependents();
+  __shared__ IterRaw sc;
   const int lr = blockIdx.x * blockDim.x + threadIdx.x;
   const int nloc = sh_count(k, r, G);
   const int i = lr < nloc ? sh_slot(lr, r, G) : 0;
   const bool valid = lr < nloc && i >= 1;
-  int plo = -1, phi = -1;
-  bool moved = false;
-  if (has_prev) {
-    plo = prev->lo; phi = prev->hi;
-    moved = phi != k;
-  }
-  prune_rowtest<T, NJ>(p, valid, lr, i, Dloc + (int64_t)(valid ? lr : 0) * ld, (valid && NJ) ? R[i] : 0.0, tinv, plo,
-                       phi, moved, prune_wfloor(p, k, tinv));
+  const double Ri = (valid && NJ) ? R[i] : 0.0;
+  iter_raw_load(&sc, p, prev, has_prev != 0);
+  prune_rowtest<T, NJ>(p, sc, valid, lr, i, Ri, tinv, k, iter_wfloor(sc, p.xw != nullptr, k, tinv));
 }
 
 template <typename T, bool NJ>
@@ -219,19 +215,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanA
   const T *__restrict__ D = static_cast<const T *>(a.Dloc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
+  __shared__ IterRaw sc;
+  iter_raw_load(&sc, p, nullptr, false);
   RowScan<T, NJ> rs;
   rs.R = a.R; rs.ids = a.ids; rs.tinv = a.tinv;
-  rs.umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
+  rs.umax = NJ ? a.tinv * __longlong_as_double((long long)sc.rmax) : 0.0;
   rs.bq = INFINITY; rs.b2 = INFINITY; rs.bi = -1; rs.bj = -1; rs.cap = INFINITY;
   rs.sbest = INFINITY; rs.ssi = -1; rs.ssj = -1; rs.uif = 0.f;
-  rs.wfloor = prune_wfloor(p, k, a.tinv);
+  rs.wfloor = iter_wfloor(sc, p.xw != nullptr, k, a.tinv);
   PruneWarp pw;
   pw.gb_seen = INFINITY; pw.nread = 0;
-  const int gw = blockIdx.x * SCAN_WARPS + warp, W = gridDim.x * SCAN_WARPS;
-  const float cnow = prune_cnow(p);
+  const int gw = warp * gridDim.x + blockIdx.x, W = gridDim.x * SCAN_WARPS;  // consecutive units on different SMs
+  const float cnow = iter_cnow(sc);
   {
     const long long upr = (((long long)k - 1 + SW - 1) / SW + PRUNE_UNIT - 1) / PRUNE_UNIT;  // units per row
-    const long long nunits = (long long)__ldcg(p.wcount) * upr;
+    const long long nunits = (long long)sc.wc0 * upr;
     for (long long u = gw; u < nunits; u += W) {
       const int lr = p.worklist[u / upr];
       const int i = sh_slot(lr, a.r, a.G);
@@ -624,6 +622,7 @@ struct ShMergeArgs {
   // exact NJ mode (replicated like R): bounds of the maintained sums, their maxima, id-ordered slot lists
   int exact; double *Eb; double *Ab; unsigned long long *xw; double *apartial;
   const int32_t *order_old; const int32_t *pos_old; int32_t *order_new; int32_t *pos_new;
+  void *newcol; int64_t newcol_stride;  // contiguous copies of the two rewritten columns (PruneArgs), replicated
 };
 
 // Per-rank warm start of the pruned scan's bound (prune_warm_start, agglom_pruned.cuh): only pairs whose row
@@ -637,7 +636,7 @@ __device__ __forceinline__ void sh_warm_start(const ShMergeArgs &a, int lo, int 
                                          [=](int si, int sj) -> const T * {
                                            if (sh_owner(si, G) != r) return nullptr;
                                            return D + (int64_t)sh_local(si, G) * ld + sj;
-                                         });
+                                         }, (int)threadIdx.x);
 }
 
 template <typename T, bool NJ>
@@ -707,13 +706,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
           a.Ab[dst] = abv;
         }
       }
+      const int vdst = (v == last && hi != last) ? hi : v;
       if (hi != last && v != last) {
         const T l = gathered(2, v);
         if (own_hi) row_hi[v] = l;
         if (own_v) row_v[hi] = l;
+        if (a.prune) static_cast<T *>(a.newcol)[a.newcol_stride + v] = l;
       }
       if (own_lo) row_lo[v] = nvs;
       if (own_v) row_v[lo] = nvs;
+      if (a.prune) static_cast<T *>(a.newcol)[vdst] = nvs;
       if (a.prune && a.maintain_R) {
         const bool moves = (v == last && hi != last);
         const float un = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
@@ -792,22 +794,23 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
     sLast = (prev == gridDim.x - 1);
   }
   __syncthreads();
-  if (sLast && threadIdx.x == 0) {
-    __threadfence();
-    double sum = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) sum = __dadd_rn(sum, ((volatile double *)a.partial)[b]);
-    a.R[lo] = sum;
-    atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
-    if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
-    if (a.exact) {
-      double asum = 0.0;
-      for (int b = 0; b < (int)gridDim.x; ++b) asum = __dadd_rn(asum, ((volatile double *)a.apartial)[b]);
-      const double ab = up30(asum);
-      const double eb = up30((double)(16 + (int)gridDim.x) * EXACT_U1 * ab);
-      a.Ab[lo] = ab;
-      a.Eb[lo] = eb;
-      atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(eb));
-      atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(ab));
+  if (sLast) {
+    if (threadIdx.x < 32) {
+      double sum, asum;
+      sum_partials_one_warp(a.partial, a.apartial, (int)gridDim.x, a.exact != 0, sum, asum);  // as merge_kernel
+      if (threadIdx.x == 0) {
+        a.R[lo] = sum;
+        atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
+        if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
+        if (a.exact) {
+          const double ab = up30(asum);
+          const double eb = up30(new_row_sum_depth((int)gridDim.x) * EXACT_U1 * ab);
+          a.Ab[lo] = ab;
+          a.Eb[lo] = eb;
+          atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(eb));
+          atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(ab));
+        }
+      }
     }
   }
   if (sLast && a.prune) sh_warm_start<T, NJ>(a, lo, hi, last);
@@ -1011,6 +1014,7 @@ struct ShWorkspace {
   // exact NJ mode
   double *Eb, *Ab, *apartial; int32_t *order[2], *pos[2], *mark, *mlist, *ulist; unsigned *mcount, *xstate;
   unsigned long long *xstats;
+  double *newcol;
   size_t bytes;
 };
 
@@ -1054,6 +1058,7 @@ static ShWorkspace sh_carve(void *base, int64_t n, int G, size_t esz) {
   w.mcount = c.take<unsigned>(4);
   w.xstate = c.take<unsigned>(8);
   w.xstats = c.take<unsigned long long>(4);
+  w.newcol = c.take<double>(2 * (size_t)n);
   w.bytes = c.used();
   return w;
 }
@@ -1165,6 +1170,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
         pa.sugg = rk.w.sugg; pa.scanned = rk.w.scanned; pa.cta_read = rk.w.cta_read;
         pa.rmaxb = NJ ? rk.w.rmax_bits : nullptr;
         pa.xw = exact ? rk.w.rmax_bits : nullptr;
+        pa.newcol = rk.w.newcol; pa.newcol_stride = n;
         CAS_CUDA_TRY(launch_pdl(sh_rowtest_kernel<T, NJ>, (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1),
                                 256u, stream, pa, (const T *)rk.D, ld, k, G, rk.r, (const double *)rk.w.R, sa.tinv,
                                 (const Sel *)rk.w.sel, t > 0 ? 1 : 0));
@@ -1247,6 +1253,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.tinv_next = k - 3 > 0 ? 1.0 / (double)(k - 3) : 0.0;
       ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.sugg = rk.w.sugg; ma.gbest = rk.w.gbest;
       ma.pool = rk.w.pool; ma.rot = (int)((t * 61) % POOL);
+      ma.newcol = rk.w.newcol; ma.newcol_stride = n;
       ma.exact = exact ? 1 : 0; ma.Eb = rk.w.Eb; ma.Ab = rk.w.Ab; ma.xw = rk.w.rmax_bits; ma.apartial = rk.w.apartial;
       ma.order_old = exact ? rk.w.order[cur] : nullptr; ma.pos_old = exact ? rk.w.pos[cur] : nullptr;
       ma.order_new = exact ? rk.w.order[cur ^ 1] : nullptr; ma.pos_new = exact ? rk.w.pos[cur ^ 1] : nullptr;

@@ -111,7 +111,7 @@ def test_exact_and_strict_modes_equal_oracle_at_4096_cells(seed, monkeypatch):
     assert np.array_equal(got_last, want_last)
     strict, strict_last = engine.agglomerate(D.clone(), nn, "nj", "strict")
     assert np.array_equal(strict, want) and np.array_equal(strict_last, want_last)
-    assert st["scanned_elements"] > 0 and st["ambiguous_iterations"] < 200
+    assert st["scanned_elements"] > 0 and st["ambiguous_iterations"] < 200, st
 
 
 def test_exact_mode_equals_gpu_strict_at_20k_cells(monkeypatch):
