@@ -97,15 +97,14 @@ static __device__ __noinline__ void exact_collect_dense(ScanArgs a, int ncand, d
 // Exact mode: called by every thread of a scan's last CTA with the reduced candidate.  When a second pair lies
 // inside the error window of the minimum the reference's sequential sums decide (agglom_exact.cuh).
 template <bool PRUNED>
-__device__ __forceinline__ void exact_resolve(const ScanArgs &a, const PruneArgs *p, int ncand, Cand &c) {
+__device__ __forceinline__ void exact_resolve(const ScanArgs &a, const PruneArgs *p, int ncand, Cand &c, double W) {
   __shared__ int sWin[2];
-  const double W = exact_window(a.ex.xw, a.k, a.tinv);
   if (c.si < 0 || !(c.q2 - c.q <= W)) return;  // uniform: every thread holds the same candidate
   const double capq = c.q + W;
   const int epoch = a.t + 1;
   if (PRUNED) {
     exact_collect_pruned(static_cast<const double *>(a.D), a.ld, a.k, a.R, a.tinv, *p, a.ex, capq, epoch,
-                         __ldcg(p->wcount), __ldcg(p->wcount + 1));
+                         __ldcg(p->wcount), __ldcg(p->wcount + 1));  // (front, back) lengths of the work list
   } else {
     exact_collect_dense(a, ncand, capq, epoch);
   }
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   // the last CTA reduces all per-CTA candidates
   c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
   if constexpr (NJ && sizeof(T) == 8) {
-    if (a.exact) exact_resolve<false>(a, nullptr, (int)gridDim.x, c);
+    if (a.exact) exact_resolve<false>(a, nullptr, (int)gridDim.x, c, 0.5 * wfloor);
   }
   if (threadIdx.x == 0) {
     if (c.si < 0) {
@@ -221,14 +220,18 @@ __global__ void __launch_bounds__(256) prune_rowtest_kernel(PruneArgs p, const T
   __shared__ IterRaw sc;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i >= 1 && i < k;
-  const double Ri = (valid && NJ) ? R[i] : 0.0;  // in flight while the scalars are staged
+  // the row's own loads are in flight while the scalars are staged
+  const double Ri = (valid && NJ) ? R[i] : 0.0;
+  const unsigned beta0 = valid ? p.beta[i] : 0u;
+  const T *newcol = static_cast<const T *>(p.newcol);
+  const T nc_lo = (valid && has_prev) ? newcol[i] : (T)0, nc_hi = (valid && has_prev) ? newcol[p.newcol_stride + i] : (T)0;
   iter_raw_load(&sc, p, prev, has_prev != 0);
-  prune_rowtest<T, NJ>(p, sc, valid, i, i, Ri, tinv, k, iter_wfloor(sc, p.xw != nullptr, k, tinv));
+  prune_rowtest<T, NJ>(p, sc, valid, i, i, Ri, tinv, k, iter_wfloor(sc, p.xw != nullptr, k, tinv), beta0, nc_lo, nc_hi);
   TL_STAMP(t, 0, 2);
 }
 
 template <typename T, bool NJ>
-__global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a, PruneArgs p) {
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_pruned_kernel(ScanArgs a, PruneArgs p) {
   TL_STAMP(a.t, 1, 0);
   pdl_wait();
   pdl_launch_dependents();
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
   TL_STAMP(a.t, 1, 7);
   if constexpr (NJ && sizeof(T) == 8) {
-    if (a.exact) exact_resolve<true>(a, &p, (int)gridDim.x, c);  // reads the work list: before it is reset below
+    // the error window is half the window floor staged at the kernel's start; reads the work list: before its reset
+    if (a.exact) exact_resolve<true>(a, &p, (int)gridDim.x, c, 0.5 * rs.wfloor);
   }
   const int lo = min(c.si, c.sj), hi = max(c.si, c.sj);
   if (lo < 0) {  // uniform
@@ -333,9 +337,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
   }
   if (threadIdx.x == 96) a.sel->dij = (double)D[(int64_t)lo * a.ld + hi];  // the map element is a DRAM round trip
   if (threadIdx.x == 32) {
-    // every other CTA has finished (counter): clear the per-iteration state, commit the drift
+    // every other CTA has finished (counter): clear the per-iteration state, commit the drift (C := C as of this
+    // scan, which every CTA derived from the same staged words; dmax := 0)
     *p.gbest = enc_f64(INFINITY);
-    prune_commit(p);
+    p.hdr[0] = cnow;
+    *p.dmax = enc_f32(0.f);
     p.beta[lo] = enc_f32(-INFINITY);
     p.beta[hi] = enc_f32(-INFINITY);
   }
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) scan_pruned_kernel(ScanArgs a
     const double gap = c.q2 - c.q;
     if (gap <= 1e-6 * fmax(1.0, fabs(c.q))) atomicAdd(a.stats + 0, 1ull);
     if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
-    atomicAdd(a.stats + 2, (unsigned long long)p.wcount[0] + p.wcount[1]);  // diagnostics: rows listed, whole loop
+    atomicAdd(a.stats + 2, (unsigned long long)sc.wc0 + sc.wc1);  // diagnostics: rows listed, whole loop
     p.wcount[0] = 0u;
     p.wcount[1] = 0u;
   }
@@ -395,11 +401,12 @@ struct MergeArgs {
 constexpr int WARM_THREADS = MERGE_THREADS - 32;  // the merge's last CTA: warp 0 sums, warps 1.. warm-start gbest
 
 template <typename T, bool NJ>
-__device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int hi, int last, int tid) {
+__device__ __forceinline__ void warm_start_gbest(const MergeArgs &a, int lo, int hi, int last, int tid,
+                                                 bool rename_moved) {
   const T *D = static_cast<const T *>(a.D);
   const int64_t ld = a.ld;
   prune_warm_start<T, NJ, WARM_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last, a.rot,
-                                        [=](int si, int sj) { return D + (int64_t)si * ld + sj; }, tid);
+                                        [=](int si, int sj) { return D + (int64_t)si * ld + sj; }, tid, rename_moved);
 }
 
 // Latency notes (profiles/r2_timeline_*.txt): the kernel is a chain of dependent memory round trips, so (1) the
@@ -439,22 +446,19 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
   float uf_up = 0.f;            // pruned scan: increase of this slot's fl32(u) (columns that keep their node)
   double ebv = 0.0, abv = 0.0;  // exact mode: this row's bounds after the update
 
+  // state kept for the deferred stores (write_map below)
+  T st_nvs = (T)0;
+  bool st_other = false, st_moves = false;
+  int st_p_lo = 0, st_p_hi = 0, st_id_last = 0, st_sz_last = 0;
   if (live) {
     // second wave: everything that needs the selection
     const bool other = v != lo && v != hi;
     const double da = other ? (double)D[(int64_t)lo * ld + v] : 0.0;
     const double db = other ? (double)D[(int64_t)hi * ld + v] : 0.0;
-    int p_lo = 0, p_hi = 0;
-    if (a.order_old) { p_lo = a.pos_old[lo]; p_hi = a.pos_old[hi]; }
-    const int id_last = (v == last && hi != last) ? a.ids[last] : 0;
-    const int sz_last = (v == last && hi != last && a.sizes) ? a.sizes[last] : 0;
-    if (v == lo) {
-      D[(int64_t)lo * ld + lo] = (T)0;
-      a.ids[lo] = a.new_id;
-      if (a.sizes) a.sizes[lo] = s.size_lo + s.size_hi;
-    } else if (v == hi) {
-      D[(int64_t)hi * ld + hi] = (T)0;
-    } else {
+    if (a.order_old) { st_p_lo = a.pos_old[lo]; st_p_hi = a.pos_old[hi]; }
+    st_id_last = (v == last && hi != last) ? a.ids[last] : 0;
+    st_sz_last = (v == last && hi != last && a.sizes) ? a.sizes[last] : 0;
+    if (other) {
       double nv;
       if (NJ) {
         // 0.5 * ((d_vi + d_vj) - d_ij)   (NeighborJoiningSolver.py:254-258).  d_ij comes from the scan kernel:
@@ -484,15 +488,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
           a.Ab[vdst] = abv;
         }
       }
-      if (hi != last && v != last) {
-        // the node in the last live slot moves into slot hi
-        D[(int64_t)hi * ld + v] = dl;
-        D[(int64_t)v * ld + hi] = dl;
-        if (a.prune) static_cast<T *>(a.newcol)[a.newcol_stride + v] = dl;
-      }
-      D[(int64_t)lo * ld + v] = nvs;
-      D[(int64_t)v * ld + lo] = nvs;
-      if (a.prune) static_cast<T *>(a.newcol)[vdst] = nvs;
+      st_nvs = nvs;
+      st_other = true;
+      st_moves = moves;
       if (a.prune && a.maintain_R) {
         // u of the next scan, and its increase for the columns that keep their node (the new node's column
         // and the moved node's column are folded into the bounds exactly by the next row test)
@@ -500,21 +498,45 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
         if (!moves) uf_up = un - uf0;
         a.uf[vdst] = un;
       }
-      if (moves) {
-        D[(int64_t)hi * ld + lo] = nvs;
-        D[(int64_t)lo * ld + hi] = nvs;
+    }
+  }
+  // Everything below the grid reduction needs only R, the partial sums and the maxima.  The map itself (two
+  // scattered column stores per row), the copies of the new columns and the id-ordered list are written AFTER this
+  // CTA has signalled, so that its fence does not wait for them; they drain while the last CTA runs the tail.
+  auto write_map = [&]() {
+    if (!live) return;
+    if (v == lo) {
+      D[(int64_t)lo * ld + lo] = (T)0;
+      a.ids[lo] = a.new_id;
+      if (a.sizes) a.sizes[lo] = s.size_lo + s.size_hi;
+    } else if (v == hi) {
+      D[(int64_t)hi * ld + hi] = (T)0;
+    } else if (st_other) {
+      const int vdst = st_moves ? hi : v;
+      if (hi != last && v != last) {
+        // the node in the last live slot moves into slot hi
+        D[(int64_t)hi * ld + v] = dl;
+        D[(int64_t)v * ld + hi] = dl;
+        if (a.prune) static_cast<T *>(a.newcol)[a.newcol_stride + v] = dl;
+      }
+      D[(int64_t)lo * ld + v] = st_nvs;
+      D[(int64_t)v * ld + lo] = st_nvs;
+      if (a.prune) static_cast<T *>(a.newcol)[vdst] = st_nvs;
+      if (st_moves) {
+        D[(int64_t)hi * ld + lo] = st_nvs;
+        D[(int64_t)lo * ld + hi] = st_nvs;
         D[(int64_t)hi * ld + hi] = (T)0;
-        a.ids[hi] = id_last;
-        if (a.sizes) a.sizes[hi] = sz_last;
+        a.ids[hi] = st_id_last;
+        if (a.sizes) a.sizes[hi] = st_sz_last;
       }
     }
     // strict / exact NJ: rebuild the id-ordered list of live slots
     if (a.order_old) {
       const int p = v;  // thread p handles the p-th live node in id order
-      if (p != p_lo && p != p_hi) {
+      if (p != st_p_lo && p != st_p_hi) {
         int sl = ord0;
         if (sl == last) sl = hi;
-        const int np = p - (p > p_lo ? 1 : 0) - (p > p_hi ? 1 : 0);
+        const int np = p - (p > st_p_lo ? 1 : 0) - (p > st_p_hi ? 1 : 0);
         a.order_new[np] = sl;
         a.pos_new[sl] = np;
       }
@@ -523,9 +545,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
         a.pos_new[lo] = k - 2;
       }
     }
-  }
+  };
   TL_STAMP(a.t, 2, 2);
 
+  if (!a.maintain_R) write_map();  // UPGMA / strict NJ: nothing below depends on the ordering
   if (a.prune && !a.maintain_R) {
     // UPGMA: no row sums; the last CTA to finish warm-starts gbest
     __syncthreads();
@@ -535,7 +558,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       sLast = (prev == gridDim.x - 1);
     }
     __syncthreads();
-    if (sLast && threadIdx.x >= 32) warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32);
+    if (sLast && threadIdx.x >= 32) warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32, true);
     return;
   }
   if (!a.maintain_R) return;
@@ -584,6 +607,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     TL_STAMP(a.t, 2, 5);
   }
   __syncthreads();
+  write_map();
   if (!sLast) return;
   // Last CTA.  Everything it reads of the other CTAs' results is read through L2 (no fence needed on this side).
   TL_STAMP(a.t, 2, 6);
@@ -593,11 +617,23 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     sum_partials_one_warp(a.partial, a.apartial, nb, a.exact != 0, sum, asum);
     double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
     unsigned u = enc_f32(0.f);
-    for (int b = lane; b < nb; b += 32) {
-      const double *pm = a.pmax + 4 * (size_t)b;
-      x0 = fmax(x0, __ldcg(pm + 0));
-      if (a.exact) { x1 = fmax(x1, __ldcg(pm + 1)); x2 = fmax(x2, __ldcg(pm + 2)); x3 = fmax(x3, __ldcg(pm + 3)); }
-      if (a.prune) u = max(u, __ldcg(a.pufup + b));
+    for (int b0 = 0; b0 < nb; b0 += 128) {  // four slots per lane in flight
+      double2 pa[4], pb[4];
+      unsigned pu[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int b = b0 + q * 32 + lane;
+        const bool in = b < nb;
+        const double2 *pm = reinterpret_cast<const double2 *>(a.pmax + 4 * (size_t)(in ? b : 0));
+        pa[q] = in ? __ldcg(pm) : make_double2(0.0, 0.0);
+        pb[q] = (in && a.exact) ? __ldcg(pm + 1) : make_double2(0.0, 0.0);
+        pu[q] = (in && a.prune) ? __ldcg(a.pufup + b) : enc_f32(0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        x0 = fmax(x0, pa[q].x); x1 = fmax(x1, pa[q].y); x2 = fmax(x2, pb[q].x); x3 = fmax(x3, pb[q].y);
+        u = max(u, pu[q]);
+      }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -610,28 +646,26 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
     if (lane == 0) {
       a.R[lo] = sum;
       x0 = fmax(x0, fabs(sum));
-      // running maxima: this thread is their only writer while the merge runs
-      if ((unsigned long long)__double_as_longlong(x0) > a.rmax_bits[0]) a.rmax_bits[0] = __double_as_longlong(x0);
+      // running maxima (non-negative doubles order like their bit patterns): reductions without a return value
+      atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(x0));
       if (a.prune) {
         a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
-        if (u > *a.dmax) *a.dmax = u;
+        atomicMax(a.dmax, u);
       }
       if (a.exact) {
         const double ab = up30(asum);
         const double eb = up30(new_row_sum_depth(nb) * EXACT_U1 * ab);
         a.Ab[lo] = ab;
         a.Eb[lo] = eb;
-        x1 = fmax(x1, eb);
-        x2 = fmax(x2, ab);
-        if ((unsigned long long)__double_as_longlong(x1) > a.xw[XW_EBMAX]) a.xw[XW_EBMAX] = __double_as_longlong(x1);
-        if ((unsigned long long)__double_as_longlong(x2) > a.xw[XW_ABMAX]) a.xw[XW_ABMAX] = __double_as_longlong(x2);
-        if ((unsigned long long)__double_as_longlong(x3) > a.xw[XW_DABS]) a.xw[XW_DABS] = __double_as_longlong(x3);
+        atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(fmax(x1, eb)));
+        atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(fmax(x2, ab)));
+        atomicMax(a.xw + XW_DABS, (unsigned long long)__double_as_longlong(x3));
       }
     }
     TL_STAMP(a.t, 2, 7);
   } else if (a.prune) {
     // entries touching slot lo are dropped, so the warm start needs neither R[lo] nor anything warp 0 writes
-    warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32);
+    warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32, false);
   }
   TL_STAMP(a.t, 2, 8);
 }

@@ -282,9 +282,20 @@ __device__ __forceinline__ void sum_partials_one_warp(const double *partial, con
   const int lane = threadIdx.x & 31;
   sum = 0.0;
   asum = 0.0;
-  for (int b = lane; b < count; b += 32) {
-    sum = __dadd_rn(sum, __ldcg(partial + b));
-    if (with_abs) asum = __dadd_rn(asum, __ldcg(apartial + b));
+  // eight loads per lane in flight; out-of-range slots contribute +0.0 (x + 0.0 == x)
+  for (int b0 = 0; b0 < count; b0 += 256) {
+    double pv[8], av[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = b0 + u * 32 + lane;
+      pv[u] = b < count ? __ldcg(partial + b) : 0.0;
+      av[u] = (with_abs && b < count) ? __ldcg(apartial + b) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      sum = __dadd_rn(sum, pv[u]);
+      asum = __dadd_rn(asum, av[u]);
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -293,7 +304,7 @@ __device__ __forceinline__ void sum_partials_one_warp(const double *partial, con
   }
 }
 // bound on the rounded additions any element of the new row passes through: 5 + 8 inside its CTA, then the above
-__device__ __forceinline__ double new_row_sum_depth(int count) { return (double)(13 + count / 32 + 1 + 5 + 2); }
+__device__ __forceinline__ double new_row_sum_depth(int count) { return (double)(13 + count / 32 + 8 + 5 + 2); }
 
 // Warp-wide candidate reduction, order-free and therefore identical to any sequence of cand_merge calls: the winner
 // is the lexicographic minimum of (q, key), the runner-up the smallest value among everything else (the other lanes'
@@ -351,14 +362,22 @@ __device__ __forceinline__ Cand reduce_candidates(const Cand *cand, int count, C
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Cand c;
   c.q = INFINITY; c.key = ~0ull; c.si = -1; c.sj = -1; c.q2 = INFINITY;
-  for (int x = threadIdx.x; x < count; x += blockDim.x) {
-    Cand o;
-    o.q = __ldcg(&cand[x].q);
-    o.key = __ldcg(&cand[x].key);
-    o.si = __ldcg(&cand[x].si);
-    o.sj = __ldcg(&cand[x].sj);
-    o.q2 = __ldcg(&cand[x].q2);
-    cand_merge(c, o);
+  for (int x0 = 0; x0 < count; x0 += 2 * blockDim.x) {  // two candidates per thread in flight
+    Cand o[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int x = x0 + u * blockDim.x + threadIdx.x;
+      o[u].q = INFINITY; o[u].key = ~0ull; o[u].si = -1; o[u].sj = -1; o[u].q2 = INFINITY;
+      if (x < count) {
+        o[u].q = __ldcg(&cand[x].q);
+        o[u].key = __ldcg(&cand[x].key);
+        o[u].si = __ldcg(&cand[x].si);
+        o[u].sj = __ldcg(&cand[x].sj);
+        o[u].q2 = __ldcg(&cand[x].q2);
+      }
+    }
+    cand_merge(c, o[0]);
+    cand_merge(c, o[1]);
   }
   c = warp_cand_reduce(c);
   __syncthreads();

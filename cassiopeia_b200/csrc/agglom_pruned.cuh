@@ -222,22 +222,22 @@ __device__ __forceinline__ bool prune_impossible(float e, float cnow, float uif,
 // prev_* = slots of the previous join (prev_lo < 0: none yet; prev_moved: a node moved into slot prev_hi).
 template <typename T, bool NJ>
 __device__ __forceinline__ void prune_rowtest(const PruneArgs &p, const IterRaw &sc, bool valid, int64_t ridx, int i,
-                                              double Ri, double tinv, int k_prev_last, double wfloor) {
-  const T *newcol = static_cast<const T *>(p.newcol);
+                                              double Ri, double tinv, int k_prev_last, double wfloor, unsigned beta0,
+                                              T nc_lo, T nc_hi) {
   const float cnow = iter_cnow(sc);
   const int prev_lo = sc.plo, prev_hi = sc.phi;
   const bool prev_moved = prev_hi != k_prev_last;  // a node moved into slot hi unless hi was the last live slot
   bool unsafe = false, unknown = false;
   if (valid) {
-    unsigned b = p.beta[ridx];
+    unsigned b = beta0;
     unknown = b == enc_f32(-INFINITY);  // the whole row will be read
     if (prev_lo >= 0 && i != prev_lo && i != prev_hi) {
       unsigned *erow = p.E + ridx * p.stride;
       // both loads first: one round trip for the two read-modify-writes
       const bool fold_lo = i > prev_lo, fold_hi = prev_moved && i > prev_hi;
       const unsigned e_lo_old = fold_lo ? erow[prev_lo / SW] : 0u, e_hi_old = fold_hi ? erow[prev_hi / SW] : 0u;
-      const float x_lo = fold_lo ? screen_value(newcol[i]) : 0.f;
-      const float x_hi = fold_hi ? screen_value(newcol[p.newcol_stride + i]) : 0.f;
+      const float x_lo = fold_lo ? screen_value(nc_lo) : 0.f;
+      const float x_hi = fold_hi ? screen_value(nc_hi) : 0.f;
       if (fold_lo) {
         const float q = x_lo - (NJ ? sc.uf_lo : 0.f);
         const unsigned e = enc_f32((q + cnow) - 1e-6f * (fabsf(x_lo) + fabsf(q) + cnow));
@@ -338,12 +338,26 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
   for (int base_i = 0; base_i < total; base_i += G) {
     int sg[G];
     T v[G][LOADS][V];
+    float su[G][LOADS][V];  // fl32(u_j) of the same columns: loaded in the same wave as the map elements (issued one
+                            // by one between the evaluations they were eight dependent L2 round trips per unit)
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       sg[g] = (base_i + g < total) ? sb + (int)list[base_i + g] : -1;
+#pragma unroll
+      for (int l = 0; l < LOADS; ++l) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) su[g][l][e] = 0.f;
+      }
       if (sg[g] >= 0) {
 #pragma unroll
-        for (int l = 0; l < LOADS; ++l) ld_stream<false>(row + sg[g] * SW + l * 32 * V + lane * V, v[g][l]);
+        for (int l = 0; l < LOADS; ++l) {
+          const int j = sg[g] * SW + l * 32 * V + lane * V;
+          ld_stream<false>(row + j, v[g][l]);
+          if (NJ) {
+            if (V == 4) *reinterpret_cast<float4 *>(su[g][l]) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
+            else *reinterpret_cast<float2 *>(su[g][l]) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
+          }
+        }
       }
     }
 #pragma unroll
@@ -353,14 +367,7 @@ __device__ __forceinline__ void prune_unit(RowScan<T, NJ> &rs, PruneWarp &pw, co
 #pragma unroll
       for (int l = 0; l < LOADS; ++l) {
         const int j = sg[g] * SW + l * 32 * V + lane * V;
-        float su[V];
-#pragma unroll
-        for (int e = 0; e < V; ++e) su[e] = 0.f;
-        if (NJ) {
-          if (V == 4) *reinterpret_cast<float4 *>(su) = __ldg(reinterpret_cast<const float4 *>(p.uf + j));
-          else *reinterpret_cast<float2 *>(su) = __ldg(reinterpret_cast<const float2 *>(p.uf + j));
-        }
-        dm = fminf(dm, rs.template vec<false>(v[g][l], su, j, i));
+        dm = fminf(dm, rs.template vec<false>(v[g][l], su[g][l], j, i));
       }
       const unsigned m = __reduce_min_sync(0xffffffffu, prune_bound(dm, cnow));
       if (lane == 0) erow[sg[g]] = m;
@@ -449,7 +456,8 @@ __device__ __forceinline__ void prune_publish_suggestion(const RowScan<T, NJ> &r
 template <typename T, bool NJ, int NTHREADS, typename Addr>
 __device__ __forceinline__ void prune_warm_start(int32_t *pool, const Cand *cand, int ncand, const int32_t *sugg,
                                                  unsigned long long *gbest, const double *R, double tinv_next,
-                                                 int lo, int hi, int last, int rot, Addr addr, int tid) {
+                                                 int lo, int hi, int last, int rot, Addr addr, int tid,
+                                                 bool rename_moved = true) {
   constexpr int EPT = (POOL + NTHREADS - 1) / NTHREADS;
   int px[EPT][3], py[EPT][3];
 #pragma unroll
@@ -476,7 +484,10 @@ __device__ __forceinline__ void prune_warm_start(int32_t *pool, const Cand *cand
       pd[e][c] = nullptr;
       dv[e][c] = INFINITY; ri[e][c] = 0.0; rj[e][c] = 0.0;
       if (x < 0 || y < 0 || x == lo || y == lo || x == hi || y == hi) continue;
-      if (x == last) x = hi;  // the node of the last slot moved into slot hi (hi != last here)
+      // the node of the last slot moved into slot hi (hi != last here): follow it -- or, when the caller has not yet
+      // written the moved row and column (merge_kernel defers its map stores past the grid reduction), drop the pair
+      if ((x == last || y == last) && !rename_moved) continue;
+      if (x == last) x = hi;
       if (y == last) y = hi;
       if (x >= last || y >= last) continue;
       px[e][c] = max(x, y); py[e][c] = min(x, y);

@@ -200,12 +200,16 @@ __global__ void __launch_bounds__(256) sh_rowtest_kernel(PruneArgs p, const T *_
   const int i = lr < nloc ? sh_slot(lr, r, G) : 0;
   const bool valid = lr < nloc && i >= 1;
   const double Ri = (valid && NJ) ? R[i] : 0.0;
+  const unsigned beta0 = valid ? p.beta[lr] : 0u;
+  const T *newcol = static_cast<const T *>(p.newcol);
+  const T nc_lo = (valid && has_prev) ? newcol[i] : (T)0, nc_hi = (valid && has_prev) ? newcol[p.newcol_stride + i] : (T)0;
   iter_raw_load(&sc, p, prev, has_prev != 0);
-  prune_rowtest<T, NJ>(p, sc, valid, lr, i, Ri, tinv, k, iter_wfloor(sc, p.xw != nullptr, k, tinv));
+  prune_rowtest<T, NJ>(p, sc, valid, lr, i, Ri, tinv, k, iter_wfloor(sc, p.xw != nullptr, k, tinv), beta0, nc_lo,
+                       nc_hi);
 }
 
 template <typename T, bool NJ>
-__global__ void __launch_bounds__(SCAN_THREADS, 3) sh_scan_pruned_kernel(ShScanArgs a, PruneArgs p) {
+__global__ void __launch_bounds__(SCAN_THREADS, 2) sh_scan_pruned_kernel(ShScanArgs a, PruneArgs p) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ Cand sCand[SCAN_WARPS];
