@@ -1,8 +1,14 @@
-"""BASELINE.json config 4 / north-star target: NeighborJoiningSolver on 200k cells x 40 characters,
-dissimilarity map row-sharded over 8 B200s.  A full CPU solve is infeasible at this size, so the run
-checks what can be checked: sampled rows of the GPU map against the CPU oracle (bit-exact after
-float32 rounding), agreement of the join list across ranks, validity of the join list as a tree.
-Launch: python -m torch.distributed.run --nproc-per-node 8 scripts/north_star_200k.py"""
+"""BASELINE.json config 4 / north-star target: NeighborJoiningSolver on 200k cells x 40 characters, dissimilarity
+map and loop row-sharded over the B200s of one node (P2P exchange over NVLink).
+
+Default mode "exact": float64 map, the loop produces the REFERENCE's join list (maintained row sums + the
+reference's sequential sums for the rows of ambiguous pairs, exchanged between the owning ranks).
+A full CPU solve is infeasible at this size, so the run checks what can be checked: sampled rows of the GPU map
+against the CPU oracle (bit-exact), agreement of the full join-list hash across ranks, validity of the join list as a
+tree; the same code path is pinned to the oracle's join lists at <= 6000 cells (tests/test_gpu_sharded.py) and
+`--cells 30000 --compare-single` checks the sharded hash against the single-GPU exact loop at a size one GPU holds.
+Launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+        scripts/north_star_200k.py [--mode exact|fast] [--cells N]"""
 import argparse, json, os, sys, time
 import numpy as np
 import torch
@@ -16,19 +22,26 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cells", type=int, default=200000)
 ap.add_argument("--chars", type=int, default=40)
 ap.add_argument("--states", type=int, default=50)
+ap.add_argument("--missing", type=float, default=0.1)
+ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+ap.add_argument("--compare-single", action="store_true",
+                help="rank 0 also runs the single-GPU loop in the same mode (the map must fit one GPU) and compares")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 lr = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-args = argparse.Namespace(cells=a.cells, chars=a.chars, states=a.states, missing=0.1, mutation_rate=0.1, seed=0)
+args = argparse.Namespace(cells=a.cells, chars=a.chars, states=a.states, missing=a.missing, mutation_rate=0.1, seed=0,
+                          algo="nj", priors=True)
 codes, missing_code, table, n_states = bench.make_workload(args)
 n = codes.shape[0]
+dt = "f32" if a.mode == "fast" else "f64"
+esz = 4 if dt == "f32" else 8
 cm_dev = torch.from_numpy(codes).cuda()
-peers = sharded.PeerGroup(n, "f32")
+peers = sharded.PeerGroup(n, dt)
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.perf_counter()
-shard = sharded.build_shard(cm_dev, missing_code, table, n_states, rank, world, "f32")
+shard = sharded.build_shard(cm_dev, missing_code, table, n_states, rank, world, dt)
 torch.cuda.synchronize(); dist.barrier()
 t1 = time.perf_counter()
 # sampled rows of this rank's shard vs the CPU oracle (reference algorithm), before the loop destroys the map
@@ -38,34 +51,55 @@ got = shard[torch.from_numpy(pick).cuda()][:, :n].cpu().numpy()
 ok_map = True
 for local, g in zip(pick.tolist(), got):
     r = int(rows[local])
-    want = po.whd_map(codes.astype(np.int64), missing_code, table, rows=(r, r + 1), threads=4)[0].astype(np.float32)
-    ok_map &= bool(np.array_equal(g, want))
+    want = po.whd_map(codes.astype(np.int64), missing_code, table, rows=(r, r + 1), threads=4)[0]
+    ok_map &= bool(np.array_equal(g, want.astype(g.dtype)))
+free_b, total_b = torch.cuda.mem_get_info()
 torch.cuda.synchronize(); dist.barrier()
 t2 = time.perf_counter()
-joins, last2 = sharded.sharded_solve_p2p(shard, n, "nj", peers)
+joins, last2 = sharded.sharded_solve_p2p(shard, n, "nj", peers, mode=a.mode)
 torch.cuda.synchronize(); dist.barrier()
 t3 = time.perf_counter()
+stats = dict(sharded.last_exact_stats)
 used = np.concatenate([joins.ravel(), last2])
 ok_tree = bool(np.array_equal(np.sort(used), np.arange(2 * n - 2))) and bool((joins[:, 1] < n + np.arange(n - 2)).all())
-h = torch.tensor([int(joins.astype(np.int64).sum()), int((joins[:, 0].astype(np.int64) * np.arange(1, n - 1)).sum() % (2**61))],
-                 dtype=torch.int64, device="cuda")
-hmax, hmin = h.clone(), h.clone()
-dist.all_reduce(hmax, op=dist.ReduceOp.MAX); dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+jh = bench.join_hash(joins, last2)
+hashes = [None] * world
+dist.all_gather_object(hashes, jh)
 flags = torch.tensor([int(ok_map), int(ok_tree)], device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 scanned = torch.tensor([sharded.last_scanned_elements], dtype=torch.int64, device="cuda")
 dist.all_reduce(scanned, op=dist.ReduceOp.SUM)
+single = None
+del shard
+if a.compare_single and rank == 0:
+    torch.cuda.empty_cache()
+    D = engine.whd_map(cm_dev, missing_code, table, n_states, dtype=dt, method="exact")
+    torch.cuda.synchronize()
+    s0 = time.perf_counter()
+    j1, l1 = engine.agglomerate(D, n, "nj", a.mode)
+    torch.cuda.synchronize()
+    single = {"loop_seconds": time.perf_counter() - s0, "join_hash": bench.join_hash(j1, l1),
+              "identical_to_sharded": bool(np.array_equal(j1, joins) and np.array_equal(l1, last2)),
+              "ambiguous_iterations": engine.last_stats["ambiguous_iterations"]}
+dist.barrier()
 if rank == 0:
     peak = bench.peaks()[0]
-    b_alg = bench.scan_bytes(n, 4)
-    out = {"config": f"NJ {a.cells} cells x {a.chars} chars x {a.states} states, priors, 10% missing, implicit root; "
-                     f"row-sharded over {world} B200 (P2P exchange)",
+    b_alg = bench.scan_bytes(n, esz)
+    out = {"config": f"NJ {a.cells} cells x {a.chars} chars x {a.states} states, priors, {int(a.missing * 100)}% missing, "
+                     f"implicit root; map and loop row-sharded over {world} B200 (P2P exchange)",
+           "mode": a.mode, "dtype": dt, "n_gpus": world,
            "map_seconds": t1 - t0, "loop_seconds": t3 - t2, "solve_seconds": (t1 - t0) + (t3 - t2),
+           "us_per_iteration": 1e6 * (t3 - t2) / max(n - 2, 1),
+           "map_gpairs_per_s": n * (n - 1) / 2 / (t1 - t0) / 1e9,
+           "shard_bytes_per_rank": int(sharded.local_capacity(n, world)) * engine.padded_ld(n) * esz,
+           "free_bytes_rank0_before_loop": int(free_b), "total_bytes": int(total_b),
            "scan": "pruned (exact lower bounds)" if int(scanned.item()) else "dense",
-           "elements_read_fraction_of_dense": int(scanned.item()) * 4 / b_alg,
-           "loop_algorithmic_GBps": b_alg / (t3 - t2) / 1e9, "roofline_frac_of_measured_hbm": b_alg / (t3 - t2) / 1e9 / (peak * world),
+           "elements_read_fraction_of_dense": int(scanned.item()) * esz / b_alg,
+           "loop_algorithmic_GBps": b_alg / (t3 - t2) / 1e9,
+           "algorithmic_over_measured_hbm": b_alg / (t3 - t2) / 1e9 / (peak * world),
            "sampled_map_rows_bit_exact_vs_cpu_oracle": bool(flags[0].item()), "join_list_is_a_valid_tree": bool(flags[1].item()),
-           "ranks_agree_on_join_list": bool(torch.equal(hmax, hmin)), "first_joins": joins[:3].tolist()}
+           "join_hash": jh, "ranks_agree_on_full_join_hash": len(set(hashes)) == 1,
+           "exact_mode_stats": stats, "single_gpu": single, "first_joins": joins[:3].tolist()}
     print(json.dumps(out), flush=True)
 peers.close()
 dist.destroy_process_group()
