@@ -39,6 +39,7 @@ EXPORTS = (
     "cas_agglom_scanned_elements",
     "cas_agglom_prune_diag",
     "cas_agglom_exact_stats",
+    "cas_agglom_exact_log",
     "cas_loop_launch_floor",
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
@@ -106,6 +107,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_agglom_prune_diag.argtypes = [vp, i64, vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]
     L.cas_agglom_exact_stats.restype = ctypes.c_int
     L.cas_agglom_exact_stats.argtypes = [vp, i64, vp, vp]
+    L.cas_agglom_exact_log.restype = ctypes.c_int
+    L.cas_agglom_exact_log.argtypes = [vp, i64, vp, vp, i64]
     L.cas_loop_launch_floor.restype = ctypes.c_int
     L.cas_loop_launch_floor.argtypes = [i64, i64, i32, vp, sz, vp]
     L.cas_tail_preorder.restype = i64

@@ -109,7 +109,11 @@ __device__ __forceinline__ void exact_resolve(const ScanArgs &a, const PruneArgs
     exact_collect_dense(a, ncand, capq, epoch);
   }
   if (threadIdx.x == 0) { sWin[0] = c.si; sWin[1] = c.sj; }
-  exact_finish(static_cast<const double *>(a.D), a.ld, a.k, a.R, a.ids, a.tinv, capq, a.ex, &sWin[0], &sWin[1]);
+  exact_finish(static_cast<const double *>(a.D), a.ld, a.k, a.R, a.ids, a.tinv, capq, a.ex, &sWin[0], &sWin[1], a.t);
+  if (threadIdx.x == 0 && a.ex.xlog) {  // diagnostics: the window itself
+    const unsigned long long slot = a.ex.xstats[0] - 1;
+    if (slot < XLOG_CAP) a.ex.xlog[4 * slot + 3] = __float_as_int((float)W);
+  }
   __syncthreads();
   c.si = sWin[0];
   c.sj = sWin[1];
@@ -125,7 +129,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = a.k;
   const double umax = NJ ? a.tinv * __longlong_as_double(*a.rmax_bits) : 0.0;
-  const double wfloor = (NJ && a.exact) ? 2.0 * exact_window(a.ex.xw, k, a.tinv) : 0.0;
+  const bool strict_now = NJ && a.exact && __ldcg(a.ex.strict_epoch) == a.t;  // strict tail: exact sums, no window
+  const double wfloor = (NJ && a.exact && !strict_now) ? 2.0 * exact_window(a.ex.xw, k, a.tinv) : 0.0;
   double bq = INFINITY, b2 = INFINITY;
   int bi = -1, bj = -1;
   int staged_cb = -1;
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
   // the last CTA reduces all per-CTA candidates
   c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
   if constexpr (NJ && sizeof(T) == 8) {
-    if (a.exact) exact_resolve<false>(a, nullptr, (int)gridDim.x, c, 0.5 * wfloor);
+    if (a.exact && !strict_now) exact_resolve<false>(a, nullptr, (int)gridDim.x, c, 0.5 * wfloor);
   }
   if (threadIdx.x == 0) {
     if (c.si < 0) {
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_pruned_kernel(ScanArgs a
   TL_STAMP(a.t, 1, 7);
   if constexpr (NJ && sizeof(T) == 8) {
     // the error window is half the window floor staged at the kernel's start; reads the work list: before its reset
-    if (a.exact) exact_resolve<true>(a, &p, (int)gridDim.x, c, 0.5 * rs.wfloor);
+    if (a.exact && !sc.strict) exact_resolve<true>(a, &p, (int)gridDim.x, c, 0.5 * rs.wfloor);
   }
   const int lo = min(c.si, c.sj), hi = max(c.si, c.sj);
   if (lo < 0) {  // uniform
@@ -685,10 +690,19 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
                : "memory");
 }
 
+// gate != null (exact mode's strict tail): the kernel does nothing unless *gate is set, and stamps *epoch = t when it
+// runs; launched with programmatic stream serialization inside the pruned loop.
 __global__ void __launch_bounds__(RS_THREADS) rowsum_seq_kernel(const double *__restrict__ D, int64_t ld, int k,
                                                                 const int32_t *__restrict__ order,
                                                                 double *__restrict__ R,
-                                                                unsigned long long *rmax_bits) {
+                                                                unsigned long long *rmax_bits, const unsigned *gate,
+                                                                int *epoch, int t) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (gate) {
+    if (!*gate) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *epoch = t;
+  }
   __shared__ __align__(16) double tile[RS_STAGES][RS_ROWS][RS_COLS];
   const int c0 = blockIdx.x * RS_COLS;
   const int tid = threadIdx.x;
@@ -845,6 +859,8 @@ struct AgglomWorkspace {
   double *Eb, *Ab, *Rex, *apartial; int32_t *mark, *mlist; unsigned *mcount; unsigned long long *xstats;
   double *newcol;  // [2][n] elements of the map's type
   double *pmax; unsigned *pufup;
+  int32_t *xlog;
+  unsigned *strict_flag; int *strict_epoch;
   size_t bytes;
 };
 
@@ -888,6 +904,9 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.newcol = c.take<double>(2 * (size_t)n);
   w.pmax = c.take<double>(4 * ((n + MERGE_THREADS - 1) / MERGE_THREADS + 1));
   w.pufup = c.take<unsigned>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
+  w.xlog = c.take<int32_t>(4 * XLOG_CAP);
+  w.strict_flag = c.take<unsigned>(4);
+  w.strict_epoch = reinterpret_cast<int *>(w.strict_flag + 1);
   w.bytes = c.used();
   return w;
 }
@@ -971,7 +990,12 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
   }
   ExactArgs ex{};
   ex.Eb = w.Eb; ex.Ab = w.Ab; ex.xw = w.rmax_bits; ex.mark = w.mark; ex.mlist = w.mlist; ex.Rex = w.Rex;
-  ex.mcount = w.mcount; ex.xstats = w.xstats;
+  ex.mcount = w.mcount; ex.xstats = w.xstats; ex.xlog = w.xlog;
+  ex.strict_flag = w.strict_flag; ex.strict_epoch = w.strict_epoch;
+  {
+    const int init[4] = {0, -1, 0, 0};  // flag clear, no strict iteration yet
+    CAS_CUDA_TRY(cudaMemcpyAsync(w.strict_flag, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  }
   int64_t k_final = n;
   bool was_pruned = false;
   for (int64_t t = 0; t + 2 < n; ++t) {
@@ -981,7 +1005,14 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     const int cur = (int)(t & 1);
     if (strict_nj) {
       rowsum_seq_kernel<<<(unsigned)((k + RS_COLS - 1) / RS_COLS), RS_THREADS, 0, stream>>>(
-          (const double *)D, ld, k, w.order[cur], w.R, w.rmax_bits);
+          (const double *)D, ld, k, w.order[cur], w.R, w.rmax_bits, nullptr, nullptr, (int)t);
+      CAS_LAUNCH_CHECK();
+    }
+    if (exact_nj && k <= STRICT_TAIL_K) {
+      // strict tail of the exact mode (agglom_exact.cuh): returns at once until a heavy ambiguous iteration occurred
+      CAS_CUDA_TRY(launch_pdl(rowsum_seq_kernel, (unsigned)((k + RS_COLS - 1) / RS_COLS), (unsigned)RS_THREADS, stream,
+                              (const double *)D, ld, k, (const int32_t *)w.order[cur], w.R, w.rmax_bits,
+                              (const unsigned *)w.strict_flag, w.strict_epoch, (int)t));
       CAS_LAUNCH_CHECK();
     }
     ScanArgs sa;
@@ -1022,6 +1053,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
       pa.xw = exact_nj ? w.rmax_bits : nullptr;
       pa.rmaxb = NJ ? w.rmax_bits : nullptr;
       pa.newcol = w.newcol; pa.newcol_stride = n;
+      pa.strict_epoch = exact_nj ? w.strict_epoch : nullptr; pa.t = (int)t;
       CAS_CUDA_TRY(launch_pdl(prune_rowtest_kernel<T, NJ>, (unsigned)((k + 255) / 256), 256u, stream, pa,
                               (const T *)D, ld, k, (const double *)w.R, sa.tinv, (const Sel *)w.sel, t > 0 ? 1 : 0,
                               (int)t));
@@ -1331,6 +1363,15 @@ int agglom_read_exact_stats(const void *workspace, int64_t n, cudaStream_t strea
   CAS_CUDA_TRY(cudaMemcpyAsync(h, w.xstats, sizeof(h), cudaMemcpyDeviceToHost, stream));
   CAS_CUDA_TRY(cudaStreamSynchronize(stream));
   for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
+  return CAS_OK;
+}
+
+// first XLOG_CAP ambiguous iterations of the last exact-mode loop: rows of (iteration, live size, rows resolved, 0)
+int agglom_read_exact_log(const void *workspace, int64_t n, cudaStream_t stream, int32_t *out, int64_t cap_rows) {
+  AgglomWorkspace w = carve_workspace(const_cast<void *>(workspace), n > 0 ? n : 1);
+  const int64_t rows = cap_rows < XLOG_CAP ? cap_rows : XLOG_CAP;
+  CAS_CUDA_TRY(cudaMemcpyAsync(out, w.xlog, (size_t)rows * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  CAS_CUDA_TRY(cudaStreamSynchronize(stream));
   return CAS_OK;
 }
 

@@ -32,7 +32,20 @@ struct ExactArgs {
   unsigned long long *xstats;  // [0] ambiguous iterations, [1] rows resolved, [2] largest row set,
                                // [3] iterations whose pair differs from arg-min q~
   const int32_t *order;        // live slots in id order, this iteration
+  int32_t *xlog;               // [XLOG_CAP][4] diagnostics of the first ambiguous iterations: t, k, rows, window
+  // Strict tail.  Towards the end of a solve on low-information data the remaining nodes form a star: all q are
+  // equal in exact arithmetic, every pair lies inside any error window, and the reference's choice is decided by
+  // the rounding of its sequential sums -- of ALL rows.  The first ambiguous iteration that involves more than
+  // XR_HEAVY rows therefore raises `strict_flag`; from then on (for live sizes <= STRICT_TAIL_K, where the gated
+  // launch exists) rowsum_seq_kernel re-accumulates every row sum sequentially before the scan, stamps
+  // `strict_epoch` with the iteration, and the scan runs with a zero window and no resolver: the strict mode's
+  // arithmetic, at its cost (8 k^2 bytes per iteration), only where it is needed.
+  unsigned *strict_flag;
+  int *strict_epoch;
 };
+constexpr int XLOG_CAP = 4096;
+constexpr int XR_HEAVY = 64;
+constexpr int STRICT_TAIL_K = 16384;
 
 constexpr int XR_ROWS = 8;     // rows whose sequential sums are evaluated together
 constexpr int XR_POS = 256;    // positions staged per step (= threads of the CTA)
@@ -153,7 +166,7 @@ __device__ __forceinline__ void exact_decide(const double *__restrict__ D, int64
 
 // B + C + statistics, after the rows have been marked.  All threads of the last CTA.
 static __device__ __noinline__ void exact_finish(const double *D, int64_t ld, int k, const double *R, const int32_t *ids,
-                                          double tinv, double capq, ExactArgs x, int *psi, int *psj) {
+                                          double tinv, double capq, ExactArgs x, int *psi, int *psj, int t_iter) {
   __shared__ double tile[XR_ROWS][XR_POS + 1];
   __syncthreads();  // every mark of this CTA has been issued
   const int M = (int)__ldcg(x.mcount);
@@ -163,6 +176,14 @@ static __device__ __noinline__ void exact_finish(const double *D, int64_t ld, in
   exact_decide(D, ld, R, ids, tinv, capq, x, M, si, sj);
   if (threadIdx.x == 0) {
     *x.mcount = 0u;
+    const unsigned long long slot = x.xstats[0];
+    if (x.xlog && slot < XLOG_CAP) {
+      x.xlog[4 * slot + 0] = t_iter;
+      x.xlog[4 * slot + 1] = k;
+      x.xlog[4 * slot + 2] = M;
+      x.xlog[4 * slot + 3] = __float_as_int((float)(capq));
+    }
+    if (M > XR_HEAVY && x.strict_flag) *x.strict_flag = 1u;
     atomicAdd(x.xstats + 0, 1ull);
     atomicAdd(x.xstats + 1, (unsigned long long)M);
     atomicMax(x.xstats + 2, (unsigned long long)M);

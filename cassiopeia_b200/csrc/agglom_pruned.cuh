@@ -53,6 +53,9 @@ struct PruneArgs {
   unsigned long long *cta_read;  // [gridDim] per-CTA counts of this launch (summed by the last CTA)
   const unsigned long long *xw;  // exact NJ mode: running maxima behind exact_window() (agglom_common.cuh); else null
   const unsigned long long *rmaxb;  // NJ: bits of the running max |row sum| (umax = tinv * that bounds every |u_j|)
+  const int *strict_epoch;       // exact NJ mode: iteration whose row sums are the reference's sequential sums (the
+                                 // strict tail, agglom_exact.cuh), or null
+  int t;                         // iteration index (only read with strict_epoch)
   const void *newcol;            // [2][newcol_stride] map elements: the two columns the previous merge rewrote, by
   int64_t newcol_stride;         // slot -- d(v, lo) and d(v, hi) as the merge computed them.  The row test reads these
                                  // contiguous copies instead of two map elements per row (one per 2 MB page: the
@@ -68,6 +71,7 @@ struct IterRaw {
   unsigned dmaxw, wc0, wc1;
   float hdr, uf_lo, uf_hi;
   int plo, phi;
+  int strict;  // 1: this iteration's row sums ARE the reference's sequential sums (strict tail): no error window
 };
 
 __device__ __forceinline__ void iter_raw_load(IterRaw *s, const PruneArgs &p, const void *prev_sel, bool want_prev) {
@@ -78,7 +82,11 @@ __device__ __forceinline__ void iter_raw_load(IterRaw *s, const PruneArgs &p, co
   if (t == 96) s->dm = p.xw ? __ldcg(p.xw + XW_DABS) : 0ull;
   if (t == 128) s->gbest = __ldcg(p.gbest);
   if (t == 160) { s->dmaxw = __ldcg(p.dmax); s->hdr = __ldcg(p.hdr); }
-  if (t == 192) { s->wc0 = __ldcg(p.wcount); s->wc1 = __ldcg(p.wcount + 1); }
+  if (t == 192) {
+    s->wc0 = __ldcg(p.wcount);
+    s->wc1 = __ldcg(p.wcount + 1);
+    s->strict = (p.strict_epoch && __ldcg(p.strict_epoch) == p.t) ? 1 : 0;
+  }
   if (t == 224) {
     int plo = -1, phi = -1;
     if (want_prev && prev_sel) {
@@ -98,7 +106,7 @@ __device__ __forceinline__ float iter_cnow(const IterRaw &s) {
   return __fadd_ru(s.hdr, __fmul_ru(d, 1.000001f));
 }
 __device__ __forceinline__ double iter_wfloor(const IterRaw &s, bool exact, int k, double tinv) {
-  if (!exact) return 0.0;
+  if (!exact || s.strict) return 0.0;
   const double rmax = __longlong_as_double((long long)s.rmax), eb = __longlong_as_double((long long)s.eb);
   const double ab = __longlong_as_double((long long)s.ab), dm = __longlong_as_double((long long)s.dm);
   const double delta = eb + (double)k * EXACT_U1 * ab;

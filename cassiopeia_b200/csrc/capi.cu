@@ -61,6 +61,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
               void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int agglom_read_scanned(const void *workspace, int64_t n, cudaStream_t stream, int64_t *elements);
 int agglom_read_exact_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *out4);
+int agglom_read_exact_log(const void *workspace, int64_t n, cudaStream_t stream, int32_t *out, int64_t cap_rows);
 int loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, void *workspace, cudaStream_t stream);
 #ifdef CAS_TIMELINE
 int timeline_set(void *buf, int t0, int t1);
@@ -191,6 +192,11 @@ int cas_loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, vo
 int cas_agglom_exact_stats(const void *workspace, int64_t n, void *stream, int64_t *out4) {
   CAS_REQUIRE(workspace && out4, "null pointer argument");
   return agglom_read_exact_stats(workspace, n, (cudaStream_t)stream, out4);
+}
+
+int cas_agglom_exact_log(const void *workspace, int64_t n, void *stream, int32_t *out, int64_t cap_rows) {
+  CAS_REQUIRE(workspace && out && cap_rows >= 0, "bad argument");
+  return agglom_read_exact_log(workspace, n, (cudaStream_t)stream, out, cap_rows);
 }
 
 int cas_agglom_scanned_elements(const void *workspace, int64_t n, void *stream, int64_t *elements) {

@@ -167,6 +167,15 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     _lib.check(L.cas_agglom_exact_stats(ws.data_ptr(), int(n), _stream_ptr(torch), x4), "cas_agglom_exact_stats")
     (last_stats["ambiguous_iterations"], last_stats["rows_resolved"], last_stats["max_rows_resolved"],
      last_stats["pairs_changed"]) = (int(v) for v in x4)
+    if last_stats["ambiguous_iterations"]:
+        rows = min(last_stats["ambiguous_iterations"], 4096)
+        log = np.zeros((rows, 4), dtype=np.int32)
+        _lib.check(L.cas_agglom_exact_log(ws.data_ptr(), int(n), _stream_ptr(torch), log.ctypes.data, rows),
+                   "cas_agglom_exact_log")
+        last_stats["ambiguous_log"] = log[:, :3]  # (iteration, live size, rows resolved)
+        last_stats["ambiguous_window"] = log[:, 3].copy().view(np.float32)  # the error window W of those iterations
+    else:
+        last_stats["ambiguous_log"] = np.zeros((0, 3), dtype=np.int32)
     done = njoin if max_iters < 0 else min(njoin, int(max_iters))
     joins_h = joins[:done].cpu().numpy()
     last2_h = last2.cpu().numpy()

@@ -239,6 +239,9 @@ CAS_API int cas_agglom_stats(const void *workspace_dev, int64_t n, void *stream,
  * out4[1] rows whose sequential sum was evaluated, out4[2] largest such row set in one iteration,
  * out4[3] iterations whose pair differs from the arg-min of the maintained criterion. */
 CAS_API int cas_agglom_exact_stats(const void *workspace_dev, int64_t n, void *stream, int64_t *out4);
+/* the first (at most 4096) ambiguous iterations of that loop, one row of four int32 each:
+ * iteration index, live size k, rows whose sequential sum was evaluated, 0 */
+CAS_API int cas_agglom_exact_log(const void *workspace_dev, int64_t n, void *stream, int32_t *out_host, int64_t cap_rows);
 
 /* Map elements the scan kernels of the last loop run with this workspace actually read (synchronises
  * the stream).  The pruned scan (default for every mode but strict NJ; CAS_PRUNE=0 selects the dense

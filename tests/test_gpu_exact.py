@@ -71,7 +71,7 @@ def test_exact_mode_equals_oracle_on_simulated_maps(n, m, S, rate, miss, weighte
 
 
 @pytest.mark.parametrize("policy,env", POLICIES)
-@pytest.mark.parametrize("kind", ["uniform", "small_ints", "gaussian", "duplicates", "all_equal"])
+@pytest.mark.parametrize("kind", ["uniform", "small_ints", "gaussian", "duplicates", "all_equal", "star"])
 @pytest.mark.parametrize("n", [9, 257, 1100])
 def test_exact_mode_equals_oracle_on_arbitrary_symmetric_maps(n, kind, policy, env, monkeypatch):
     """Non-metric inputs: negative entries (absolute-sum bound), massive exact ties (every tie resolved by the
@@ -85,6 +85,12 @@ def test_exact_mode_equals_oracle_on_arbitrary_symmetric_maps(n, kind, policy, e
         A = rng.normal(size=(n, n)) * 3.0
     elif kind == "all_equal":
         A = np.ones((n, n))
+    elif kind == "star":
+        # additive star d_ij = a_i + a_j: every q is equal in exact arithmetic, so the reference's choice is decided
+        # by the rounding of its sequential row sums in every single iteration (the "strict tail" regime that the
+        # end of a solve on low-information lineage data runs into)
+        leg = rng.random(n) + 0.5
+        A = leg[:, None] + leg[None, :]
     else:
         base = rng.random((n // 3 + 1, 12))
         pts = base[rng.integers(0, base.shape[0], n)]
@@ -97,6 +103,9 @@ def test_exact_mode_equals_oracle_on_arbitrary_symmetric_maps(n, kind, policy, e
     got, got_last, st = _exact(_upload(D), n, env, monkeypatch)
     assert _first_diff(got, want) is None, (policy, kind, _first_diff(got, want))
     assert np.array_equal(got_last, want_last)
+    if kind == "star" and n > 100:
+        assert st["max_rows_resolved"] > 64  # the heavy iteration that switches the strict tail on
+        assert st["ambiguous_iterations"] < n // 4  # ... after which no iteration needs the resolver
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
