@@ -59,16 +59,18 @@ __host__ __device__ __forceinline__ int sh_chunk(int k, int G) {
 // ---- direct NVLink exchange (P2P): every rank owns an exchange buffer that its peers map
 // (cudaIpc) and write into with plain stores; iteration-tagged flags replace the collectives.
 constexpr int SH_MAXG = 16;
-constexpr int XT = 128;  // exact mode: most slots whose sequential sums one ambiguous iteration may need
+constexpr int XT = 1024;  // exact mode: most slots whose sequential sums one ambiguous iteration may need (the first
+                          // iteration that involves more than XR_SH_HEAVY switches the strict tail on)
 struct ShExHeader {
   unsigned long long flag1[SH_MAXG];  // flag1[r] = tag: rank r's candidate for that iteration has landed
   unsigned long long flag2[SH_MAXG];  // flag2[r] = tag: rank r's rows (lo, hi, last) chunk has landed
   unsigned long long flagA[SH_MAXG];  // exact mode: rank r's list of marked slots has landed
   unsigned long long flagB[SH_MAXG];  // exact mode: rank r's sequential sums (of the marked slots it owns) have landed
+  unsigned long long flagS[SH_MAXG];  // exact mode, strict tail: rank r's sequential sums of ALL its rows have landed
   Cand cand[SH_MAXG];
   int countA[SH_MAXG];                // exact mode: entries of listA[r]
   int error;                          // 1: a spin-wait timed out, 2: more than XT marked slots
-  int pad[47];
+  int pad[15];
   // exact mode, one ambiguous iteration at a time:
   int listA[SH_MAXG][XT];             // marked slots found by rank r among its rows
   double xsum[XT];                    // sequential row sum of the u-th slot of the sorted union (written by its owner)
@@ -286,6 +288,86 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) sh_scan_pruned_kernel(ShScanA
   }
 }
 
+static size_t sh_sums_offset(int64_t n, int world, int dtype) {
+  const size_t esz = dtype == CAS_F64 ? 8 : 4;
+  const size_t chunk = (size_t)sh_chunk((int)(n > 0 ? n : 1), world > 0 ? world : 1);
+  size_t per = 3 * chunk * esz;
+  if (per < chunk * 8) per = chunk * 8;
+  return align_up(sizeof(ShExHeader) + per * (size_t)(world > 0 ? world : 1), 256);
+}
+
+// ---- exact mode, strict tail (agglom_exact.cuh): once an ambiguous iteration involved more than XR_SH_HEAVY slots
+// every rank re-accumulates the reference's sequential sums of ITS rows before each scan (rows are whole on their
+// owner, so the chains are local), publishes them to every rank's `sums` area and the scatter kernel installs them
+// as R.  Both kernels are launched for live sizes <= STRICT_TAIL_K and return at once until the flag is raised.
+constexpr int XR_SH_HEAVY = 16;
+
+struct ShStrictArgs {
+  const double *Dloc;
+  int64_t ld;
+  int k, G, r, t;
+  ShPeers peers;
+  size_t sums_off;        // byte offset of the [n] doubles `sums` area inside an exchange buffer
+  unsigned long long tag;
+  const int32_t *order;   // live slots in id order (replicated)
+  const unsigned *gate;
+  unsigned *counter;
+  double *R;
+  unsigned long long *rmax_bits;
+  int *epoch;
+};
+
+__global__ void __launch_bounds__(256) sh_rowsum_seq_kernel(ShStrictArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (!*a.gate) return;
+  __shared__ double tile[XR_ROWS][XR_POS + 1];
+  __shared__ bool sLast;
+  const int nloc = sh_count(a.k, a.r, a.G);
+  const int l0 = blockIdx.x * XR_ROWS;
+  const int M = max(0, min(XR_ROWS, nloc - l0));
+  const double *Dl = a.Dloc;
+  const int64_t ld = a.ld;
+  const int G = a.G, r = a.r;
+  ShPeers peers = a.peers;
+  const size_t off = a.sums_off;
+  exact_rowsums_generic(
+      a.k, a.order, M, tile, [&](int m) { return Dl + (int64_t)(l0 + m) * ld; },
+      [&](int m, double sum) {
+        const int slot = sh_slot(l0 + m, r, G);
+        for (int pr = 0; pr < G; ++pr) reinterpret_cast<double *>(peers.ex[pr] + off)[slot] = sum;
+      });
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (sLast && threadIdx.x < a.G) {
+    __threadfence_system();
+    post_flag(&ex_header(a.peers.ex[threadIdx.x])->flagS[a.r], a.tag);
+  }
+}
+
+__global__ void __launch_bounds__(256) sh_strict_scatter_kernel(ShStrictArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (!*a.gate) return;
+  ShExHeader *own = ex_header(a.peers.ex[a.r]);
+  if (threadIdx.x < a.G) wait_flag(&own->flagS[threadIdx.x], a.tag, &own->error);
+  __syncthreads();
+  const double *sums = reinterpret_cast<const double *>(a.peers.ex[a.r] + a.sums_off);
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (v < a.k) {
+    s = sums[v];
+    a.R[v] = s;
+  }
+  warp_atomic_absmax(a.rmax_bits, s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.epoch = a.t;
+}
+
 struct ShColsArgs {
   const void *Dloc;
   int64_t ld;
@@ -305,6 +387,7 @@ struct ShColsArgs {
   unsigned *E; int64_t e_stride; unsigned *beta;
   // exact NJ mode (P2P exchange only): see "exact mode, sharded" below
   int exact; const double *R; double tinv; PruneArgs p; ExactArgs ex; unsigned *xstate;
+  const int *strict_epoch;  // exact mode: == t when this iteration runs on the reference's sequential sums
 };
 
 // The part of the cols kernel that needs the selected pair: marks the two rows the merge rewrites unknown,
@@ -417,7 +500,7 @@ __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
   __shared__ bool sLastX;
   const Cand c = sh_cols_reduce<T>(a, sCand);
   if constexpr (sizeof(T) == 8) {
-    if (a.exact) {
+    if (a.exact && __ldcg(a.strict_epoch) != a.t) {
       const double W = exact_window(a.p.xw, a.k, a.tinv);
       if (c.si >= 0 && c.q2 - c.q <= W) {
         // X1: collect among this rank's listed rows (work-list entries, E and beta are indexed by LOCAL row)
@@ -460,12 +543,15 @@ __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
         return;
       }
       if (blockIdx.x == 0 && threadIdx.x == 0) a.xstate[0] = 0u;
+    } else if (a.exact) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) a.xstate[0] = 0u;  // strict tail: nothing to resolve
     }
   }
   sh_cols_body<T>(a, c.si, c.sj);
 }
 
 struct ShSumsArgs {
+  unsigned *strict_flag;  // raised when the union of marked slots exceeds XR_SH_HEAVY (identical on every rank)
   const double *Dloc;
   int64_t ld;
   int k, G, r;
@@ -525,7 +611,10 @@ __global__ void __launch_bounds__(256) sh_exact_sums_kernel(ShSumsArgs a) {
     a.ulist[u] = sU[u];
     if (sh_owner(sU[u], a.G) == a.r) sMine[atomicAdd(&sNm, 1)] = u;
   }
-  if (threadIdx.x == 0) a.xstate[2] = (unsigned)T;
+  if (threadIdx.x == 0) {
+    a.xstate[2] = (unsigned)T;
+    if (T > XR_SH_HEAVY) *a.strict_flag = 1u;
+  }
   __syncthreads();
   // the slots this rank owns: sequential sums (reference order) and distances to every marked slot
   const int nm = sNm;
@@ -1019,6 +1108,7 @@ struct ShWorkspace {
   double *Eb, *Ab, *apartial; int32_t *order[2], *pos[2], *mark, *mlist, *ulist; unsigned *mcount, *xstate;
   unsigned long long *xstats;
   double *newcol;
+  unsigned *strict_flag; int *strict_epoch;
   size_t bytes;
 };
 
@@ -1063,6 +1153,8 @@ static ShWorkspace sh_carve(void *base, int64_t n, int G, size_t esz) {
   w.xstate = c.take<unsigned>(8);
   w.xstats = c.take<unsigned long long>(4);
   w.newcol = c.take<double>(2 * (size_t)n);
+  w.strict_flag = c.take<unsigned>(4);
+  w.strict_epoch = reinterpret_cast<int *>(w.strict_flag + 1);
   w.bytes = c.used();
   return w;
 }
@@ -1106,6 +1198,10 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
         exact ? rk.w.pos[0] : nullptr, rk.w.mark, rk.w.xstats, rk.w.xstate);
     CAS_LAUNCH_CHECK();
     CAS_CUDA_TRY(cudaMemsetAsync(rk.w.mcount, 0, 4 * sizeof(unsigned), stream));
+    {
+      const int init[4] = {0, -1, 0, 0};  // strict tail: flag clear, no strict iteration yet
+      CAS_CUDA_TRY(cudaMemcpyAsync(rk.w.strict_flag, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    }
     if (prune) {
       sh_prune_init_kernel<<<sms * 4, 256, 0, stream>>>(rk.w.E, rk.w.lb_stride * sh_chunk((int)n, G), rk.w.beta,
                                                         sh_chunk((int)n, G), rk.w.hdr, rk.w.dmax, rk.w.gbest,
@@ -1147,6 +1243,26 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     const unsigned long long tag = tag0 + 2 + (unsigned long long)t;
     // one-way switch to the dense scan once a rank's share of the map is small (cf. PRUNE_MIN_K in agglom.cu)
     const bool prune_it = prune && (double)k * (double)k > (double)min_k * (double)min_k * (double)G;
+    // --- exact mode, strict tail: gated re-accumulation of every row sum (returns at once until the flag is raised)
+    if (exact && k <= STRICT_TAIL_K) {
+      const size_t sums_off = sh_sums_offset(n, G, sizeof(T) == 8 ? CAS_F64 : CAS_F32);
+      std::vector<ShStrictArgs> sx(ranks.size());
+      for (size_t x = 0; x < ranks.size(); ++x) {
+        ShRank &rk = ranks[x];
+        ShStrictArgs &st = sx[x];
+        st.Dloc = (const double *)rk.D; st.ld = ld; st.k = k; st.G = G; st.r = rk.r; st.t = (int)t; st.peers = peers;
+        st.sums_off = sums_off; st.tag = tag; st.order = rk.w.order[cur]; st.gate = rk.w.strict_flag;
+        st.counter = rk.w.counters + 3; st.R = rk.w.R; st.rmax_bits = rk.w.rmax_bits; st.epoch = rk.w.strict_epoch;
+        const int nloc = sh_count(k, rk.r, G);
+        const unsigned g1 = (unsigned)((nloc + XR_ROWS - 1) / XR_ROWS > 0 ? (nloc + XR_ROWS - 1) / XR_ROWS : 1);
+        CAS_CUDA_TRY(launch_pdl(sh_rowsum_seq_kernel, g1, 256u, stream, st));
+        CAS_LAUNCH_CHECK();
+      }
+      for (size_t x = 0; x < ranks.size(); ++x) {
+        CAS_CUDA_TRY(launch_pdl(sh_strict_scatter_kernel, (unsigned)((k + 255) / 256), 256u, stream, sx[x]));
+        CAS_LAUNCH_CHECK();
+      }
+    }
     // --- scan
     for (auto &rk : ranks) {
       ShScanArgs sa;
@@ -1175,6 +1291,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
         pa.rmaxb = NJ ? rk.w.rmax_bits : nullptr;
         pa.xw = exact ? rk.w.rmax_bits : nullptr;
         pa.newcol = rk.w.newcol; pa.newcol_stride = n;
+        pa.strict_epoch = exact ? rk.w.strict_epoch : nullptr; pa.t = (int)t;
         CAS_CUDA_TRY(launch_pdl(sh_rowtest_kernel<T, NJ>, (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1),
                                 256u, stream, pa, (const T *)rk.D, ld, k, G, rk.r, (const double *)rk.w.R, sa.tinv,
                                 (const Sel *)rk.w.sel, t > 0 ? 1 : 0));
@@ -1213,6 +1330,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ca.ex.Eb = rk.w.Eb; ca.ex.Ab = rk.w.Ab; ca.ex.xw = rk.w.rmax_bits; ca.ex.mark = rk.w.mark;
       ca.ex.mlist = rk.w.mlist; ca.ex.mcount = rk.w.mcount; ca.ex.xstats = rk.w.xstats; ca.ex.order = rk.w.order[cur];
       ca.xstate = rk.w.xstate;
+      ca.strict_epoch = rk.w.strict_epoch;
       const int nloc = sh_count(k, rk.r, G);
       const unsigned cgrid = (unsigned)((nloc + 255) / 256 > 0 ? (nloc + 255) / 256 : 1);
       if (prune_it) {
@@ -1226,6 +1344,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       // the two resolver kernels of an ambiguous iteration (return at once otherwise)
       for (auto &rk : ranks) {
         ShSumsArgs xa;
+        xa.strict_flag = rk.w.strict_flag;
         xa.Dloc = (const double *)rk.D; xa.ld = ld; xa.k = k; xa.G = G; xa.r = rk.r; xa.peers = peers; xa.tag = tag;
         xa.order = rk.w.order[cur]; xa.ulist = rk.w.ulist; xa.xstate = rk.w.xstate;
         CAS_CUDA_TRY(launch_pdl(sh_exact_sums_kernel, 1u, 256u, stream, xa));
@@ -1417,7 +1536,8 @@ size_t cas_exchange_bytes(int64_t n, int32_t world, int32_t dtype) {
   const size_t chunk = (size_t)sh_chunk((int)(n > 0 ? n : 1), world > 0 ? world : 1);
   size_t per = 3 * chunk * esz;
   if (per < chunk * 8) per = chunk * 8;
-  return sizeof(ShExHeader) + per * (size_t)(world > 0 ? world : 1) + 256;
+  // header | gather area | [n] doubles: sequential sums of the exact mode's strict tail
+  return sh_sums_offset(n, world, dtype) + align_up((size_t)(n > 0 ? n : 1) * 8, 256) + 256;
 }
 
 int cas_exchange_alloc(size_t bytes, void **ptr_out, void *handle64_out) {

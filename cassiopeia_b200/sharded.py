@@ -143,7 +143,7 @@ def _raise_exchange_error(code: int) -> None:
     if code == 1:
         raise _lib.B200LibraryError("a P2P flag wait timed out (peer rank stalled or died)")
     if code == 2:
-        raise _lib.B200LibraryError("exact mode: more than 128 slots tie inside the error window in one iteration "
+        raise _lib.B200LibraryError("exact mode: more than 1024 slots tie inside the error window in one iteration "
                                     "(de-duplicate the cells or solve on one GPU)")
     if code:
         raise _lib.B200LibraryError(f"P2P exchange error {code}")

@@ -201,7 +201,7 @@ CAS_API int cas_exchange_free(void *ptr);
 CAS_API int cas_exchange_error(const void *own_exchange_dev, void *stream, int32_t *error_out);
 /* mode: CAS_MODE_FAST (float32 or float64 map, maintained sums) or CAS_MODE_EXACT (float64 map, NJ: the reference's
  * join list -- in an ambiguous iteration the ranks exchange their marked slots, the owners evaluate the reference's
- * sequential row sums of those slots and every rank decides identically; at most 128 slots per iteration, else the
+ * sequential row sums of those slots and every rank decides identically; at most 1024 slots per iteration, else the
  * exchange error flag is set to 2).  cas_sharded_exact_stats: as cas_agglom_exact_stats, for a sharded workspace. */
 CAS_API int cas_sharded_solve_p2p(void *D_local_dev, int64_t n, int64_t ld, int32_t dtype, int32_t algo, int32_t mode,
                           int64_t max_iters, int32_t rank, int32_t world, void *const *exchange_ptrs,
