@@ -300,7 +300,7 @@ static size_t sh_sums_offset(int64_t n, int world, int dtype) {
 // every rank re-accumulates the reference's sequential sums of ITS rows before each scan (rows are whole on their
 // owner, so the chains are local), publishes them to every rank's `sums` area and the scatter kernel installs them
 // as R.  Both kernels are launched for live sizes <= STRICT_TAIL_K and return at once until the flag is raised.
-constexpr int XR_SH_HEAVY = 16;
+constexpr int XR_SH_HEAVY = 64;
 
 struct ShStrictArgs {
   const double *Dloc;
