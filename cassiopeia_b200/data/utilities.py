@@ -27,10 +27,12 @@ def _require_gpu_function(dissimilarity_function: Optional[Callable]) -> str:
 
 
 def device_map(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dict[int, float]]],
-               dtype: str = "f64", method: str = "exact", function: str = "weighted_hamming_distance"):
+               dtype: str = "f64", method: str = "exact", function: str = "weighted_hamming_distance",
+               count_rows: Optional[int] = None):
     """[n, ld] CUDA tensor holding the full symmetric map of the int matrix `cm` (rows as given)."""
     lookup = "match" if function in _MATCH_LOOKUP else "mismatch"
-    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing, weights, lookup=lookup)
+    codes, missing_code, table, n_states = host_prep.compact_states(cm, missing, weights, lookup=lookup,
+                                                                    count_rows=count_rows)
     if function != "weighted_hamming_distance":
         method = "exact"
     return engine.whd_map(codes, missing_code, table, n_states, dtype=dtype, method=method, function=function)
@@ -68,11 +70,32 @@ def dissimilarity_map_frame_inputs(character_matrix, priors, missing_state_indic
     cm = host_prep.as_int_matrix(character_matrix)
     order = host_prep.reference_row_order(cm)
     names = np.asarray(character_matrix.index, dtype=object)[order].tolist()  # one gather, not n __getitem__ calls
-    D = device_map(cm[order], missing_state_indicator, weights, dtype=dtype, method=method, function=function)
+    n_unique, rep = host_prep.duplicate_groups(cm, order)
+    D = device_map(cm[order], missing_state_indicator, weights, dtype=dtype, method=method, function=function,
+                   count_rows=n_unique)
+    if n_unique < cm.shape[0] and function not in ("weighted_hamming_distance", "hamming_distance"):
+        # The reference evaluates the function on the distinct rows only and copies a distinct row -- zero
+        # diagonal included -- into each of its duplicates (CassiopeiaTree.py:1937-1951): cells with identical
+        # rows are at 0 from each other whatever the function (a similarity of a row with itself is not 0).
+        _zero_duplicate_groups(D, rep, n_unique)
     if to_host:
         n = cm.shape[0]
         return names, D[:, :n].cpu().numpy()
     return names, D
+
+
+def _zero_duplicate_groups(D, rep: np.ndarray, n_unique: int) -> None:
+    """D[p, q] = 0 for every pair of rows of the same duplicate group (device tensor, in place)."""
+    import torch
+
+    n = rep.shape[0]
+    dup_pos = np.arange(n_unique, n, dtype=np.int64)
+    groups = {}
+    for p, r in zip(dup_pos.tolist(), rep[n_unique:].tolist()):
+        groups.setdefault(r, [r]).append(p)
+    for members in groups.values():
+        idx = torch.as_tensor(members, dtype=torch.long, device=D.device)
+        D[idx[:, None], idx[None, :]] = 0
 
 
 def row_to_all_distances(character_matrix, row_name, priors, missing_state_indicator: int,

@@ -66,6 +66,21 @@ def _first_occurrence(cm: np.ndarray) -> np.ndarray:
     return first
 
 
+def duplicate_groups(cm: np.ndarray, order: np.ndarray):
+    """(n_unique, rep) for the matrix permuted by `order` = reference_row_order(cm): the first n_unique rows are
+    the distinct rows; rep[p] = position (in the permuted matrix) of the distinct row that row p duplicates
+    (rep[p] == p for the distinct rows)."""
+    cm = np.ascontiguousarray(cm)
+    n = cm.shape[0]
+    if n == 0 or cm.shape[1] == 0:
+        return (min(n, 1), np.zeros(n, dtype=np.int64))
+    first = _first_occurrence(cm)
+    pos_of = np.empty(n, dtype=np.int64)
+    pos_of[order] = np.arange(n, dtype=np.int64)
+    n_unique = int((first == np.arange(n)).sum())
+    return n_unique, pos_of[first[order]]
+
+
 def reference_row_order(cm: np.ndarray) -> np.ndarray:
     cm = np.ascontiguousarray(cm)
     n = cm.shape[0]
@@ -85,8 +100,14 @@ def reference_row_order(cm: np.ndarray) -> np.ndarray:
 
 
 def compact_states(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dict[int, float]]],
-                   lookup: str = "mismatch") -> Tuple[np.ndarray, int, Optional[np.ndarray], int]:
+                   lookup: str = "mismatch", count_rows: Optional[int] = None
+                   ) -> Tuple[np.ndarray, int, Optional[np.ndarray], int]:
     """Returns (codes int32 [n, m], missing_code, weight_table or None, n_states).
+
+    `count_rows`: only the first `count_rows` rows decide which weights are looked up (the tree-level map of the
+    reference evaluates the function on the DISTINCT rows only, CassiopeiaTree.py:1920-1932, so a state shared
+    only by duplicated cells is never looked up there); every state present anywhere still gets its weight if the
+    priors hold one.
 
     Raises KeyError where the reference's numba dict lookup would.  lookup="mismatch"
     (weighted_hamming_distance, exponential_negative_hamming_distance): a weighted character
@@ -151,8 +172,12 @@ def compact_states(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dic
         else:
             shifted = np.where(codes != missing_code, codes, -1).astype(itype) + offsets
         hist2d = np.bincount(shifted.ravel(), minlength=m * width).reshape(m, width)[:, 1:]
+        if count_rows is not None and count_rows < n:
+            hist_rule = np.bincount(shifted[:count_rows].ravel(), minlength=m * width).reshape(m, width)[:, 1:]
+        else:
+            hist_rule = hist2d
         for c in range(m):
-            hist = hist2d[c]
+            hist = hist_rule[c]
             seen = np.flatnonzero(hist)
             counts = hist[seen]
             if lookup == "mismatch":
@@ -171,4 +196,11 @@ def compact_states(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dic
                 if label not in wc:
                     raise KeyError(label)
                 table[c, code] = wc[label]
+            if hist_rule is not hist2d:
+                # states carried only by duplicated rows: not part of the rule above, weight filled in when known
+                for code in np.flatnonzero(hist2d[c]).tolist():
+                    if code != 0 and table[c, code] == 0.0:
+                        label = code if label_of is None else int(label_of[c][code])
+                        if label in wc:
+                            table[c, code] = wc[label]
     return np.ascontiguousarray(codes), missing_code, table, int(n_states)

@@ -76,6 +76,13 @@ class DistanceSolver(abc.ABC):
             return "exact"
         if dissimilarity_functions.gpu_kernel_name(self.dissimilarity_function) != "weighted_hamming_distance":
             return "exact"
+        # the one-hot operands of the tensor path are m * (largest state label + 2) bytes per cell: sparse, large
+        # labels (compact_states keeps labels <= 4094 as they are) would make it slower than the CUDA-core kernel
+        # and its workspace enormous
+        values = character_matrix.to_numpy()
+        largest = int(values.max()) if values.size else 0
+        if character_matrix.shape[1] * (max(largest, 1) + 2) > 16384:
+            return "exact"
         return "tensor"
 
     # ------------------------------------------------------------ map handling

@@ -152,3 +152,40 @@ def test_b200_solver_as_joining_solver_of_the_reference_percolation_solver(ref):
         solver.solve(tree)
         out.append(_clades(tree))
     assert out[0][1] == out[1][1] and _same(out[0][0], out[1][0])
+
+
+@pytest.mark.parametrize("fn_name", ["weighted_hamming_distance", "hamming_similarity_without_missing",
+                                     "hamming_similarity_normalized_over_missing", "weighted_hamming_similarity",
+                                     "exponential_negative_hamming_distance"])
+@pytest.mark.parametrize("use_priors", [False, True])
+def test_tree_level_map_with_duplicate_cells_equals_reference_for_every_pair_function(ref, fn_name, use_priors):
+    """The reference evaluates the function on the distinct rows and copies rows into the duplicates
+    (CassiopeiaTree.py:1920-1951): cells with identical rows are at 0 from each other for EVERY function, also the
+    similarities (f(x, x) != 0) and exp(-d) (f(x, x) = 1); a state carried only by duplicated cells is never looked
+    up in the priors."""
+    import cassiopeia_b200 as cb
+    from cassiopeia_b200.solver import dissimilarity_functions as b200_fns
+
+    frame, priors = _inputs(n=40, m=8, seed=21, missing=0.1, dup=True)
+    frame.iloc[30] = frame.iloc[12]
+    frame.iloc[31] = frame.iloc[12]
+    # a state (9) carried only by two identical cells, without a prior: the reference never looks it up
+    frame.iloc[33, 2] = 9
+    frame.iloc[34] = frame.iloc[33]
+    pri = priors if use_priors else None
+    want_tree = ref.CassiopeiaTree(character_matrix=frame.copy(), priors=pri)
+    got_tree = cb.CassiopeiaTree(character_matrix=frame.copy(), priors=pri)
+    try:
+        want_tree.compute_dissimilarity_map(getattr(ref.dissimilarity_functions, fn_name), "negative_log")
+    except KeyError as e:
+        # the distance functions look a state up when it takes part in a mismatch: state 9 does (against the other
+        # distinct rows), so the reference raises for them -- and so must the product, with the same key
+        with pytest.raises(KeyError) as got_err:
+            got_tree.compute_dissimilarity_map(getattr(b200_fns, fn_name), "negative_log")
+        assert got_err.value.args == e.args
+        assert use_priors and fn_name in ("weighted_hamming_distance", "exponential_negative_hamming_distance")
+        return
+    got_tree.compute_dissimilarity_map(getattr(b200_fns, fn_name), "negative_log")
+    want, got = want_tree.get_dissimilarity_map(), got_tree.get_dissimilarity_map()
+    assert list(want.index) == list(got.index)
+    np.testing.assert_array_equal(want.to_numpy(), got.to_numpy())
