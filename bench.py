@@ -354,7 +354,7 @@ def run_b200(args):
     esz = 4 if dt == "f32" else 8
     codes, missing_code, table, n_states = make_workload(args)
     # unweighted maps: the int8 tcgen05 kernel (bit-exact); prior-weighted maps: the exact CUDA-core kernel
-    method = args.map_method or ("exact" if table is not None else "tensor")
+    method = args.map_method or ("tensor" if (table is None or (args.mode == "fast" and n_states <= 64)) else "exact")
     n = codes.shape[0]
     cm_dev = torch.from_numpy(codes).cuda()
     ld = engine.padded_ld(n)
@@ -408,7 +408,8 @@ def run_b200(args):
                 "peak_source": peak_src, "map_ms": map_ms, "loop_ms": loop_ms,
                 "map_gpairs_per_s": n * (n - 1) / 2 / (map_ms * 1e-3) / 1e9,
                 "map_kernel": "whd_exact_kernel (CUDA cores, float64 in character order)" if method == "exact"
-                              else "whd_gemm2_kernel (tcgen05 int8, SM pair)",
+                              else ("whd_gemm2_kernel (tcgen05 int8, SM pair)" if table is None else
+                                    "whd_gemm_kernel<2> (tcgen05 int8, four 7-bit digit planes of the weights)"),
                 "algorithmic_bytes_per_step": b_alg, "algorithmic_bytes_per_launch_mean": b_alg / n_scans}
     if pruned:
         per_iter_us = 1e3 * loop_ms / n_scans

@@ -18,6 +18,17 @@
 //   realistic weight ranges) and the planes are added in float64 in the epilogue.  Relative
 //   error vs the exact kernel <= 1e-6 (tests/test_gpu_gemm.py).
 //
+// Weighted, fixed point (default for prior-weighted maps; `CAS_GEMM_WEIGHTED=bf16` selects the path above) --
+//   kind::i8 again.  Every weight is quantised to a 28-bit integer W = round(w 2^F) (F from the largest weight, so
+//   the absolute error per weight is 2^-(F+1) and that of a distance at most 2^-F: 6e-8 for weights below 16) and
+//   split into four 7-bit digits; digit plane p has its own int32 accumulator in TMEM and
+//     acc_p = U_p[I] . P[J] + P[I] . U_p[J] - 2 X_p[I] . X[J]
+//   (U_p = digit of the cell's own weight per character, X_p = the digit at the one-hot position) is EXACT integer
+//   arithmetic, so the subtraction form needs no cancellation-free doubling; the epilogue recombines
+//   num = sum_p 128^p acc_p in int64.  The big one-hot operand of the column block (X[J], -2 folded in) is shared by
+//   the four planes: five tile loads feed four MMA groups per K chunk (the bf16 path: eight loads for six groups of
+//   half-rate MMAs over twice the bytes).
+//
 // Kernel: one CTA per 128x128 lower-triangle output tile (tiles rasterised in bands of 12 tile
 // rows, column-major inside a band, so concurrently running CTAs share operand blocks in L2),
 // 6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5
@@ -37,7 +48,7 @@ constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int SLOTS = 9;            // operand-tile ring (16 KB each)
 constexpr int MAXPW = 8;           // presence-mask words per cell (m <= 512)
 constexpr int BAND = 12;           // tile rows per rasterisation band
-constexpr int MAX_MAPS = 5;
+constexpr int MAX_MAPS = 10;  // fixed-point weighted path: X_p (4), -2 X, U_p (4), P
 
 struct GemmParams {
   CUtensorMap maps[MAX_MAPS];
@@ -48,6 +59,8 @@ struct GemmParams {
   int64_t n;
   void *D;
   int64_t ld;
+  int head_chunks;       // fixed-point weighted path: 128-byte chunks of the [U_p | P] operands (ceil(m / 128))
+  const double *scale;   // fixed-point weighted path: device scalar 2^-F
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------
@@ -201,12 +214,24 @@ __device__ __forceinline__ void tile_of(int64_t t, int T, int &ti, int &tj) {
 // Persistent kernel, one CTA per SM.  NACC accumulator buffers in TMEM: 2 for int8 (the epilogue of
 // tile t overlaps the MMAs of tile t+1), 1 for bf16 (3 planes x 128 columns leave no room for a
 // second set; the TMA producer still runs ahead into the next tile during the epilogue).
-template <bool I8, typename TO, int PW>
+// KIND: 0 = bf16 x 3 planes (weighted), 1 = int8 (unweighted, exact), 2 = int8 x 4 digit planes (weighted, fixed point)
+template <int KIND> struct ProgOf { using type = Prog<KIND == 1>; };
+struct ProgW8 {
+  // per K chunk: load 0 = the operand shared by the four planes, loads 1..4 = the plane operands; MMA group m
+  // pairs plane m with the shared tile; chunk types: 0 U_p[I] x P[J], 1 P[I] x U_p[J], 2 X_p[I] x (-2 X)[J]
+  static constexpr int NL = 5, NM = 4;
+  __device__ static __forceinline__ unsigned release(int m) { return m == 3 ? 0x11u : (1u << (m + 1)); }
+};
+template <> struct ProgOf<2> { using type = ProgW8; };
+
+template <int KIND, typename TO, int PW>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using P = Prog<I8>;
-  constexpr int NACC = I8 ? 2 : 1;
-  constexpr int ACCW = (I8 ? 1 : 3) * GT;           // TMEM columns per accumulator buffer
-  constexpr uint32_t TMEM_COLS = I8 ? 256u : 512u;  // power of two >= NACC * ACCW
+  constexpr bool I8 = KIND != 0;  // int8 operands, int32 accumulators
+  using P = typename ProgOf<KIND>::type;
+  constexpr int NPL = KIND == 2 ? 4 : (KIND == 0 ? 3 : 1);  // accumulator planes
+  constexpr int NACC = KIND == 1 ? 2 : 1;
+  constexpr int ACCW = NPL * GT;                       // TMEM columns per accumulator buffer
+  constexpr uint32_t TMEM_COLS = KIND == 1 ? 256u : 512u;  // power of two >= NACC * ACCW
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   GemmSmem<TO> &sm = *reinterpret_cast<GemmSmem<TO> *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,7 +241,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
     for (int s = 0; s < SLOTS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < (I8 ? 2 : 4); ++i)
+    for (int i = 0; i < (KIND == 2 ? 10 : (KIND == 1 ? 2 : 4)); ++i)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[i]) : "memory");
   }
   if (warp == 1) {
@@ -246,8 +271,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
             const uint32_t slot = lc % SLOTS, phase = (lc / SLOTS) & 1u;
             mbar_wait(&sm.empty[slot], phase ^ 1u);
             mbar_expect_tx(&sm.full[slot], TILE_BYTES);
-            tma_load_2d(sm.tile[slot], &p.maps[P::load_map(l)], &sm.full[slot], c * elems_per_chunk,
-                        P::load_side(l) ? col0 : row0);
+            if constexpr (KIND == 2) {
+              // maps: 0..3 X_p, 4 -2 X, 5..8 U_p, 9 P
+              const int hc = p.head_chunks;
+              const int type = c < hc ? 0 : (c < 2 * hc ? 1 : 2);
+              const int kc = (type == 0 ? c : (type == 1 ? c - hc : c - 2 * hc)) * CHUNK_BYTES;
+              int map, side;  // side 1 = column block J
+              if (type == 0) { map = l == 0 ? 9 : 4 + l; side = l == 0 ? 1 : 0; }
+              else if (type == 1) { map = l == 0 ? 9 : 4 + l; side = l == 0 ? 0 : 1; }
+              else { map = l == 0 ? 4 : l - 1; side = l == 0 ? 1 : 0; }
+              tma_load_2d(sm.tile[slot], &p.maps[map], &sm.full[slot], kc, side ? col0 : row0);
+            } else {
+              tma_load_2d(sm.tile[slot], &p.maps[P::load_map(l)], &sm.full[slot], c * elems_per_chunk,
+                          P::load_side(l) ? col0 : row0);
+            }
           }
         }
       }
@@ -269,15 +306,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
         for (int c = 0; c < p.chunks; ++c, lc0 += P::NL) {
 #pragma unroll
           for (int m = 0; m < P::NM; ++m) {
-            const uint32_t la = lc0 + P::mma_a(m), lb = lc0 + P::mma_b(m);
+            uint32_t la, lb;
+            int acc_plane;
+            if constexpr (KIND == 2) {
+              const int hc = p.head_chunks;
+              const bool shared_is_a = c >= hc && c < 2 * hc;  // chunk type 1: P[I] x U_p[J]
+              la = lc0 + (shared_is_a ? 0 : 1 + m);
+              lb = lc0 + (shared_is_a ? 1 + m : 0);
+              acc_plane = m;
+            } else {
+              la = lc0 + P::mma_a(m);
+              lb = lc0 + P::mma_b(m);
+              acc_plane = P::mma_acc(m);
+            }
             const uint32_t sa = la % SLOTS, sb = lb % SLOTS;
             mbar_wait(&sm.full[sa], (la / SLOTS) & 1u);
             mbar_wait(&sm.full[sb], (lb / SLOTS) & 1u);
             tcgen05_fence_after();
             const uint64_t adesc = make_smem_desc(smem_u32(sm.tile[sa]));
             const uint64_t bdesc = make_smem_desc(smem_u32(sm.tile[sb]));
-            const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACCW + P::mma_acc(m) * GT);
-            const bool first = (c == 0) && (m < (I8 ? 1 : 3));  // first MMA group into this accumulator
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACCW + acc_plane * GT);
+            const bool first = (c == 0) && (m < NPL);  // first MMA group into this accumulator
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               // advance 32 bytes of K inside the swizzle atom: +2 in the (>>4) start-address field
@@ -302,6 +351,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
     const int et = threadIdx.x - 64;       // 0..255
     TO *__restrict__ D = static_cast<TO *>(p.D);
     TO(*stage)[HALF + 1] = sm.stage[warp - 2];
+    const double wscale = KIND == 2 ? *p.scale : 1.0;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       int ti, tj;
@@ -327,16 +377,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
       // The accumulator row of a lane is written twice: mirrored (column gi of rows gj: the 32 lanes
       // hit 32 consecutive addresses) straight from registers, and direct (row gi) through the
       // warp's transpose tile so that those stores are coalesced too.
+      if constexpr (KIND == 2 && sizeof(TO) == 4) {
+        // Fixed-point weighted, float32 output.  The four digit planes fill TMEM (no second accumulator set), so
+        // the numerators of the thread's 64 columns are first pulled into registers -- digits recombined with three
+        // fused multiply-adds in float32, 2^-23 relative, inside the stated 1e-6 -- and the accumulator is handed
+        // back at once: popcounts, divisions and stores then overlap the next tile's MMAs.
+        const int cbase = ch * 64;
+        float numf[64];
+        const float sc = (float)wscale;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v0[16], v1[16], v2[16], v3[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACCW + cbase + g * 16);
+          tmem_ld16(taddr, v0);
+          tmem_ld16(taddr + GT, v1);
+          tmem_ld16(taddr + 2 * GT, v2);
+          tmem_ld16(taddr + 3 * GT, v3);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float x = fmaf((float)(int)v3[e], 128.f, (float)(int)v2[e]);
+            x = fmaf(x, 128.f, (float)(int)v1[e]);
+            x = fmaf(x, 128.f, (float)(int)v0[e]);
+            numf[g * 16 + e] = x * sc;
+          }
+        }
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.tempty[as])) : "memory");
+        TO *mir0 = D + ((int64_t)col0 + cbase) * p.ld + gi;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) {
+          int den = 0;
+#pragma unroll
+          for (int w = 0; w < PW; ++w) den += __popcll(mrow[w] & sm.pm[cbase + e][w]);
+          float d = den > 0 ? __fdividef(numf[e], (float)den) : 0.f;
+          if (diag_tile && (cbase + e == lrow)) d = 0.f;
+          stage[lane][e] = (TO)d;
+          if (!diag_tile && (whole || (gi < p.n && (int64_t)col0 + cbase + e < p.n))) mir0[(int64_t)e * p.ld] = (TO)d;
+        }
+        __syncwarp();
+        TO *dst = D + ((int64_t)row0 + q * 32) * p.ld + col0 + cbase;
+        for (int rr = 0; rr < 32; ++rr, dst += p.ld) {
+          if (!whole && (int64_t)row0 + q * 32 + rr >= p.n) break;
+#pragma unroll
+          for (int h = 0; h < HALF; h += 32)
+            if (whole || (int64_t)col0 + cbase + h + lane < p.n) dst[h + lane] = stage[rr][h + lane];
+        }
+        __syncwarp();
+      } else
       for (int part = 0; part < 64; part += HALF) {
         const int cbase = ch * 64 + part;
         for (int cb = cbase; cb < cbase + HALF; cb += 16) {
-          uint32_t v0[16], v1[16], v2[16];
+          uint32_t v0[16], v1[16], v2[16], v3[16];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACCW + cb);
           tmem_ld16(taddr, v0);
-          if (!I8) {
+          if (KIND != 1) {
             tmem_ld16(taddr + GT, v1);
             tmem_ld16(taddr + 2 * GT, v2);
           }
+          if (KIND == 2) tmem_ld16(taddr + 3 * GT, v3);
           tmem_ld_wait();
           TO *mir = D + ((int64_t)col0 + cb) * p.ld + gi;  // element (gj0, gi), next column = + ld
 #pragma unroll
@@ -345,13 +444,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
 #pragma unroll
             for (int w = 0; w < PW; ++w) den += __popcll(mrow[w] & sm.pm[cb + e][w]);
             double num;
-            if (I8) num = (double)(int)v0[e];
-            else num = ((double)__uint_as_float(v0[e]) + (double)__uint_as_float(v1[e])) + (double)__uint_as_float(v2[e]);
+            if (KIND == 1) {
+              num = (double)(int)v0[e];
+            } else if (KIND == 2) {
+              // digits recombined in int64 (exact), then one scaling by the power of two 2^-F
+              const long long fixed = (long long)(int)v0[e] + ((long long)(int)v1[e] << 7) +
+                                      ((long long)(int)v2[e] << 14) + ((long long)(int)v3[e] << 21);
+              num = (double)fixed * wscale;
+            } else {
+              num = ((double)__uint_as_float(v0[e]) + (double)__uint_as_float(v1[e])) + (double)__uint_as_float(v2[e]);
+            }
             TO d = (TO)0;
             if (den > 0) {
               if (sizeof(TO) == 8) {
                 d = (TO)__ddiv_rn(num, (double)den);
-              } else if (I8) {
+              } else if (KIND == 1) {
                 // small integers: the correctly rounded float quotient equals fl32(fl64(num/den))
                 d = (TO)__fdiv_rn((float)num, (float)den);
               } else {
@@ -804,6 +911,60 @@ __global__ void encode_bf16_kernel(const int32_t *__restrict__ cm, int64_t n, in
   }
 }
 
+// ---- fixed-point weighted path: scale and operand encoding ----------------------------------
+// scale[0] = 2^-F, scale[1] = 2^F with F the largest integer such that round(wmax 2^F) < 2^27 (one bit of slack
+// below the 28 bits the four 7-bit digits hold).  One CTA.
+__global__ void wscale_kernel(const double *__restrict__ w, int64_t count, double *__restrict__ scale,
+                              int *__restrict__ err_flag) {
+  __shared__ double sm[32];
+  double mx = 0.0;
+  for (int64_t e = threadIdx.x; e < count; e += blockDim.x) {
+    const double x = w[e];
+    if (!(x >= 0.0) || !isfinite(x)) atomicExch(err_flag, 2);  // negative / NaN / inf weight
+    else mx = fmax(mx, x);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sm[i]);
+    int e = 0;
+    frexp(mx > 0.0 ? mx : 1.0, &e);  // mx < 2^e
+    const int F = 27 - e;
+    scale[0] = ldexp(1.0, -F);
+    scale[1] = ldexp(1.0, F);
+  }
+}
+
+// one thread per (cell, character); buffers are zero-filled beforehand.  Xp / Up: four digit planes.
+__global__ void encode_w8_kernel(const int32_t *__restrict__ cm, int64_t n, int m, int S, int32_t missing,
+                                 const double *__restrict__ w, const double *__restrict__ scale,
+                                 int8_t *__restrict__ Xp, int64_t plane_x, int8_t *__restrict__ Xm2,
+                                 int8_t *__restrict__ Up, int64_t plane_u, int8_t *__restrict__ Pm, int64_t Kx,
+                                 int64_t Km, int *__restrict__ err_flag) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * m) return;
+  const int64_t i = idx / m;
+  const int c = (int)(idx - i * m);
+  const int32_t s = cm[idx];
+  if (s == missing) return;
+  if (s < 0 || s > S) { atomicExch(err_flag, 1); return; }
+  Pm[i * Km + c] = 1;
+  if (s != 0) {
+    const double wt = w[(int64_t)c * (S + 1) + s];
+    const long long W = (wt >= 0.0 && isfinite(wt)) ? llrint(wt * scale[1]) : 0ll;
+    const int64_t k = i * Kx + (int64_t)c * S + (s - 1);
+    Xm2[k] = -2;
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) {
+      const int8_t digit = (int8_t)((W >> (7 * pl)) & 127);
+      Xp[pl * plane_x + k] = digit;
+      Up[pl * plane_u + i * Km + c] = digit;
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -856,6 +1017,12 @@ static GemmLayout layout_of(int m, int S) {
 // CAS_GEMM_CTA_GROUP=1 forces the single-SM 128 x 128 kernel, =2 the SM-pair kernel.  Default: the
 // SM-pair kernel for int8 (operand-feed bound: 1.2-1.7x faster, 75 % tensor-pipe activity at K = 20k)
 // and the single-SM kernel for bf16 (bound by operand latency, not bandwidth; measured 7 % faster).
+// weighted maps: "i8" (default) = four 7-bit digit planes on the int8 path, "bf16" = three bf16 planes
+static bool weighted_fixed_point() {
+  const char *e = getenv("CAS_GEMM_WEIGHTED");
+  return !(e && e[0] == 'b');
+}
+
 static int gemm_cta_group(bool weighted) {
   const char *e = getenv("CAS_GEMM_CTA_GROUP");
   if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
@@ -872,7 +1039,11 @@ size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t 
     c.take<int8_t>((size_t)n * L.Kp);
     c.take<int8_t>((size_t)n * L.Kp);
   } else {
-    for (int i = 0; i < 4; ++i) c.take<__nv_bfloat16>((size_t)n * L.Kx);
+    // the larger of the two weighted layouts (the choice is an environment switch read at call time)
+    const size_t bf16_bytes = 4 * align_up((size_t)n * L.Kx * 2, 256);
+    const int64_t Kx8 = round_up64((int64_t)m * S, CHUNK_BYTES), Km = round_up64(m, CHUNK_BYTES);
+    const size_t w8_bytes = 256 + 5 * align_up((size_t)n * Kx8, 256) + 5 * align_up((size_t)n * Km, 256);
+    c.take<char>(bf16_bytes > w8_bytes ? bf16_bytes : w8_bytes);
   }
   return c.used();
 }
@@ -919,6 +1090,58 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     if (rc != CAS_OK) return rc;
     map_bases[0] = A; map_bases[1] = B;
     p.chunks = (int)(L.Kp / CHUNK_BYTES);
+  } else if (weighted_fixed_point()) {
+    const int64_t Kx8 = round_up64((int64_t)m * S, CHUNK_BYTES), Km = round_up64(m, CHUNK_BYTES);
+    double *scale = carve.take<double>(32);
+    int8_t *Xp = carve.take<int8_t>(4 * (size_t)n * Kx8);
+    int8_t *Xm2 = carve.take<int8_t>((size_t)n * Kx8);
+    int8_t *Up = carve.take<int8_t>(4 * (size_t)n * Km);
+    int8_t *Pm = carve.take<int8_t>((size_t)n * Km);
+    CAS_CUDA_TRY(cudaMemsetAsync(Xp, 0, 4 * (size_t)n * Kx8, stream));
+    CAS_CUDA_TRY(cudaMemsetAsync(Xm2, 0, (size_t)n * Kx8, stream));
+    CAS_CUDA_TRY(cudaMemsetAsync(Up, 0, 4 * (size_t)n * Km, stream));
+    CAS_CUDA_TRY(cudaMemsetAsync(Pm, 0, (size_t)n * Km, stream));
+    wscale_kernel<<<1, 1024, 0, stream>>>(w, (int64_t)m * (S + 1), scale, err_flag);
+    CAS_LAUNCH_CHECK();
+    encode_w8_kernel<<<eb, 256, 0, stream>>>(cm, n, m, S, missing, w, scale, Xp, (int64_t)n * Kx8, Xm2, Up,
+                                             (int64_t)n * Km, Pm, Kx8, Km, err_flag);
+    CAS_LAUNCH_CHECK();
+    for (int i = 0; i < 4; ++i) {
+      int rc = make_map(&p.maps[i], Xp + (size_t)i * n * Kx8, n, Kx8, 1);
+      if (rc != CAS_OK) return rc;
+      rc = make_map(&p.maps[5 + i], Up + (size_t)i * n * Km, n, Km, 1);
+      if (rc != CAS_OK) return rc;
+    }
+    int rc = make_map(&p.maps[4], Xm2, n, Kx8, 1);
+    if (rc != CAS_OK) return rc;
+    rc = make_map(&p.maps[9], Pm, n, Km, 1);
+    if (rc != CAS_OK) return rc;
+    p.head_chunks = (int)(Km / CHUNK_BYTES);
+    p.chunks = 2 * p.head_chunks + (int)(Kx8 / CHUNK_BYTES);
+    p.scale = scale;
+    const int64_t tiles8 = (n + GT - 1) / GT;
+    const int64_t ntiles8 = tiles8 * (tiles8 + 1) / 2;
+    CAS_REQUIRE(ntiles8 < 2147483647LL, "too many tiles");
+#define LAUNCH_W8(TO, PWV)                                                                         \
+  do {                                                                                             \
+    const size_t smem = sizeof(GemmSmem<TO>) + 1024;                                               \
+    CAS_CUDA_TRY(cudaFuncSetAttribute(whd_gemm_kernel<2, TO, PWV>,                                 \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    const int64_t grid = ntiles8 < sm_count() ? ntiles8 : sm_count();                              \
+    whd_gemm_kernel<2, TO, PWV><<<(unsigned)grid, GEMM_THREADS, smem, stream>>>(p);                \
+  } while (0)
+#define LAUNCH_W8_PW(TO)                                                                           \
+  do {                                                                                             \
+    if (pw == 1) LAUNCH_W8(TO, 1);                                                                 \
+    else if (pw == 2) LAUNCH_W8(TO, 2);                                                            \
+    else if (pw <= 4) LAUNCH_W8(TO, 4);                                                            \
+    else LAUNCH_W8(TO, 8);                                                                         \
+  } while (0)
+    if (dtype == CAS_F64) LAUNCH_W8_PW(double); else LAUNCH_W8_PW(float);
+#undef LAUNCH_W8_PW
+#undef LAUNCH_W8
+    CAS_LAUNCH_CHECK();
+    return CAS_OK;
   } else {
     __nv_bfloat16 *XW[3];
     for (int i = 0; i < 3; ++i) XW[i] = carve.take<__nv_bfloat16>((size_t)n * L.Kx);

@@ -63,16 +63,19 @@ class DistanceSolver(abc.ABC):
     def _map_dtype(self) -> str:
         return "f32" if self.precision == "fast" else "f64"
 
-    #: "auto" | "exact" | "tensor".  auto: unweighted maps go to the int8 tensor-core kernel (bit-exact
-    #: and ~4x faster than the CUDA-core kernel); prior-weighted maps stay on the exact CUDA-core
-    #: kernel, which is bit-identical to the reference and, because of the one-hot inflation of the
-    #: GEMM recast, also faster than the 3-plane bf16 tensor path at realistic state counts.
+    #: "auto" | "exact" | "tensor".  auto:
+    #: * unweighted maps -> the int8 tcgen05 kernel (bit-exact and ~4x faster than the CUDA-core kernel);
+    #: * prior-weighted maps in the reference-exact modes -> the exact CUDA-core kernel (the reference accumulates
+    #:   float64 weights in character order: reproducing those roundings bit for bit is not a GEMM);
+    #: * prior-weighted maps in fast mode with at most 64 states per character -> the fixed-point int8 tcgen05
+    #:   kernel (four 7-bit digit planes, |error| <= 2^-23 of the largest weight; 1.6x the CUDA-core kernel at
+    #:   50k x 40 x 50), else the CUDA-core kernel (the one-hot operand grows with the state count).
     map_method = "auto"
 
     def _map_method_for(self, cassiopeia_tree, character_matrix) -> str:
         if self.map_method != "auto":
             return self.map_method
-        if cassiopeia_tree.priors or character_matrix.shape[1] > 512:
+        if character_matrix.shape[1] > 512:
             return "exact"
         if dissimilarity_functions.gpu_kernel_name(self.dissimilarity_function) != "weighted_hamming_distance":
             return "exact"
@@ -83,6 +86,8 @@ class DistanceSolver(abc.ABC):
         largest = int(values.max()) if values.size else 0
         if character_matrix.shape[1] * (max(largest, 1) + 2) > 16384:
             return "exact"
+        if cassiopeia_tree.priors:
+            return "tensor" if (self.precision == "fast" and largest <= 64) else "exact"
         return "tensor"
 
     # ------------------------------------------------------------ map handling

@@ -17,6 +17,13 @@ def cta_group(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(params=["i8", "bf16"], ids=["fixed_point_int8", "bf16_planes"], autouse=True)
+def weighted_path(request, monkeypatch):
+    """Both weighted tensor paths: four 7-bit digit planes on the int8 MMAs (default) and three bf16 planes."""
+    monkeypatch.setenv("CAS_GEMM_WEIGHTED", request.param)
+    return request.param
+
+
 def _inputs(g):
     w = g.weights
     if w is not None:
@@ -45,7 +52,7 @@ def test_int8_gemm_is_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if not n.endswith("plain")])
-def test_bf16_gemm_within_tolerance(name):
+def test_weighted_gemm_within_tolerance(name):
     from cassiopeia_b200 import engine
 
     g = Golden(name)
@@ -65,7 +72,8 @@ def test_gemm_sizes_not_multiple_of_tile():
     from cassiopeia_b200 import engine
     from cassiopeia_b200.synthetic import simulate_character_matrix
 
-    for n, m, S in ((5, 3, 2), (129, 7, 3), (255, 20, 9), (257, 20, 9), (300, 33, 17), (1000, 40, 50), (1537, 70, 20)):
+    for n, m, S in ((5, 3, 2), (129, 7, 3), (255, 20, 9), (257, 20, 9), (300, 33, 17), (1000, 40, 50), (1537, 70, 20),
+                    (700, 150, 6)):
         cm, priors, table = simulate_character_matrix(n, m, S, seed=n, mutation_rate=0.7, missing_fraction=0.15)
         with np.errstate(invalid="ignore"):
             w = np.nan_to_num(-np.log(table))
