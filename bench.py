@@ -457,7 +457,7 @@ def run_b200(args):
             "max_rows_resolved": int(stats.get("max_rows_resolved", 0)),
             "pairs_changed_by_resolution": int(stats.get("pairs_changed", 0)),
             "checked_against": "tests/test_gpu_exact.py (oracle join lists up to 4096 cells x 3 seeds, GPU strict at "
-                               "20k); profiles/r2_exact_vs_oracle.md"},
+                               "20k); profiles/r2_exact_time.md"},
     }
 
     if not args.no_e2e:
