@@ -809,6 +809,12 @@ __global__ void prune_init_kernel(unsigned *E, int64_t count, unsigned *beta, in
   }
 }
 
+// Test hook (CAS_EXACT_EB_FLOOR): raises the running maximum of the row-sum error bounds, which only WIDENS the
+// exact mode's ambiguity window -- more iterations go through the resolver, the join list must not change.
+__global__ void xw_floor_kernel(unsigned long long *xw, double floor_eb) {
+  atomicMax(xw + XW_EBMAX, (unsigned long long)__double_as_longlong(floor_eb));
+}
+
 __global__ void init_state_kernel(int n, int32_t *ids, int32_t *sizes, int32_t *order, int32_t *pos,
                                   unsigned *counters, unsigned long long *rmax_bits, int32_t *mark,
                                   unsigned long long *xstats) {
@@ -988,6 +994,8 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
         exact_nj ? w.Eb : nullptr, exact_nj ? w.Ab : nullptr);
     CAS_LAUNCH_CHECK();
   }
+  const double eb_floor = (exact_nj && getenv("CAS_EXACT_EB_FLOOR")) ? atof(getenv("CAS_EXACT_EB_FLOOR")) : 0.0;
+  if (eb_floor > 0.0) xw_floor_kernel<<<1, 1, 0, stream>>>(w.rmax_bits, eb_floor);
   ExactArgs ex{};
   ex.Eb = w.Eb; ex.Ab = w.Ab; ex.xw = w.rmax_bits; ex.mark = w.mark; ex.mlist = w.mlist; ex.Rex = w.Rex;
   ex.mcount = w.mcount; ex.xstats = w.xstats; ex.xlog = w.xlog;
@@ -1042,6 +1050,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
       rowsum_init_kernel<T><<<(unsigned)((k + 7) / 8), 256, 0, stream>>>((const T *)D, ld, k, w.R, w.rmax_bits, nullptr,
                                                                           sa.tinv, w.Eb, w.Ab);
       CAS_LAUNCH_CHECK();
+      if (eb_floor > 0.0) xw_floor_kernel<<<1, 1, 0, stream>>>(w.rmax_bits, eb_floor);
     }
     was_pruned = prune_it;
     if (prune_it) {

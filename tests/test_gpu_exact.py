@@ -71,7 +71,7 @@ def test_exact_mode_equals_oracle_on_simulated_maps(n, m, S, rate, miss, weighte
 
 
 @pytest.mark.parametrize("policy,env", POLICIES)
-@pytest.mark.parametrize("kind", ["uniform", "small_ints", "gaussian", "duplicates", "all_equal", "star"])
+@pytest.mark.parametrize("kind", ["uniform", "small_ints", "gaussian", "duplicates", "all_equal", "star", "wide_range"])
 @pytest.mark.parametrize("n", [9, 257, 1100])
 def test_exact_mode_equals_oracle_on_arbitrary_symmetric_maps(n, kind, policy, env, monkeypatch):
     """Non-metric inputs: negative entries (absolute-sum bound), massive exact ties (every tie resolved by the
@@ -85,6 +85,9 @@ def test_exact_mode_equals_oracle_on_arbitrary_symmetric_maps(n, kind, policy, e
         A = rng.normal(size=(n, n)) * 3.0
     elif kind == "all_equal":
         A = np.ones((n, n))
+    elif kind == "wide_range":
+        # 16 decades of magnitude: the error window is dominated by the largest entries, the decisions by the smallest
+        A = 10.0 ** rng.uniform(-8.0, 8.0, (n, n))
     elif kind == "star":
         # additive star d_ij = a_i + a_j: every q is equal in exact arithmetic, so the reference's choice is decided
         # by the rounding of its sequential row sums in every single iteration (the "strict tail" regime that the
@@ -121,6 +124,27 @@ def test_exact_and_strict_modes_equal_oracle_at_4096_cells(seed, monkeypatch):
     strict, strict_last = engine.agglomerate(D.clone(), nn, "nj", "strict")
     assert np.array_equal(strict, want) and np.array_equal(strict_last, want_last)
     assert st["scanned_elements"] > 0 and st["ambiguous_iterations"] < 200, st
+
+
+@pytest.mark.parametrize("policy,env", POLICIES)
+@pytest.mark.parametrize("floor", ["1e-7", "1e-4"])
+def test_widened_error_window_changes_the_counters_not_the_join_list(floor, policy, env, monkeypatch):
+    """CAS_EXACT_EB_FLOOR (test hook) raises the running maximum of the row-sum error bounds, i.e. widens the window
+    inside which the maintained sums are not trusted: many more iterations go through the resolver (or through the
+    strict tail once an iteration involves more than 64 rows), and the join list must still be the oracle's -- the
+    resolver, not the narrowness of the real window, is what decides near-ties."""
+    D, nn = _sim_map(3000, 40, 50, 0.1, 0.1, True, 11)
+    want, want_last = po.nj(D[:, :nn].cpu().numpy())
+    base, base_last, st0 = _exact(D, nn, env, monkeypatch)
+    wide, wide_last, st1 = _exact(D, nn, dict(env, CAS_EXACT_EB_FLOOR=floor), monkeypatch)
+    monkeypatch.delenv("CAS_EXACT_EB_FLOOR", raising=False)
+    assert _first_diff(base, want) is None and np.array_equal(base_last, want_last)
+    assert _first_diff(wide, want) is None, (floor, policy, _first_diff(wide, want))
+    assert np.array_equal(wide_last, want_last)
+    print(f"floor {floor} {policy}: ambiguous {st0['ambiguous_iterations']} -> {st1['ambiguous_iterations']}, "
+          f"rows {st0['rows_resolved']} -> {st1['rows_resolved']} (max {st1['max_rows_resolved']})")
+    assert st1["ambiguous_iterations"] > st0["ambiguous_iterations"]
+    assert st1["rows_resolved"] > st0["rows_resolved"]
 
 
 def test_exact_mode_equals_gpu_strict_at_20k_cells(monkeypatch):
