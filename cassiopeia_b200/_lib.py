@@ -41,6 +41,7 @@ EXPORTS = (
     "cas_agglom_exact_stats",
     "cas_agglom_exact_log",
     "cas_loop_launch_floor",
+    "cas_int8_mma_peak",
     "cas_sharded_local_rows",
     "cas_sharded_local_capacity",
     "cas_sharded_workspace_bytes",
@@ -111,6 +112,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_agglom_exact_log.argtypes = [vp, i64, vp, vp, i64]
     L.cas_loop_launch_floor.restype = ctypes.c_int
     L.cas_loop_launch_floor.argtypes = [i64, i64, i32, vp, sz, vp]
+    L.cas_int8_mma_peak.restype = ctypes.c_int
+    L.cas_int8_mma_peak.argtypes = [i32, vp, vp]
     L.cas_tail_preorder.restype = i64
     L.cas_tail_preorder.argtypes = [vp, vp, i64, i64, vp, vp]
     L.cas_tail_heights.restype = ctypes.c_int

@@ -50,6 +50,7 @@ int pairwise_exact_map(int32_t fn, int32_t flags, const int32_t *cm, int64_t n, 
                        int cyc_r = 0);
 int whd_read_error_flag(const void *workspace, cudaStream_t stream, int *flag);
 size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t weighted);
+int int8_mma_peak(int iters, cudaStream_t stream, double *ops_per_s);
 int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
                  int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -187,6 +188,11 @@ int cas_loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, vo
   CAS_REQUIRE(workspace && k >= 1 && iters >= 0 && kernels_per_iter >= 1 && kernels_per_iter <= 3, "bad argument");
   CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(k), "workspace too small");
   return loop_launch_floor(k, iters, kernels_per_iter, workspace, (cudaStream_t)stream);
+}
+
+int cas_int8_mma_peak(int32_t iters, void *stream, double *ops_per_s) {
+  CAS_REQUIRE(ops_per_s && iters >= 1, "bad argument");
+  return int8_mma_peak(iters, (cudaStream_t)stream, ops_per_s);
 }
 
 int cas_agglom_exact_stats(const void *workspace, int64_t n, void *stream, int64_t *out4) {

@@ -1249,6 +1249,74 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
   return CAS_OK;
 }
 
+// ---- measured peak of the int8 tensor pipe ---------------------------------------------------
+// One CTA per SM issues `iters` x 4 back-to-back tcgen05.mma kind::i8 (M = 128, N = 256, K = 32) on operand tiles that
+// already sit in shared memory (zero-filled: the pipe's rate does not depend on the data), accumulating in TMEM.  No
+// loads, no epilogue: what is timed is the issue rate of the MMA pipe itself, the denominator the map kernels'
+// tensor fractions are quoted against (scripts/map_sweep.py).  cuBLASLt's int8 GEMM reached through torch._int_mm
+// is far below it on this image (636 TOP/s at 16384^3), so it is no roofline.
+__global__ void __launch_bounds__(128) i8_peak_kernel(int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *tileA = base;               // [128 rows][128 bytes]
+  uint8_t *tileB = base + 128 * 128;   // [256 rows][128 bytes]
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < (128 + 256) * 128 / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(base)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async-proxy (MMA) reads
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc = make_smem_desc(smem_u32(tileA)), bdesc = make_smem_desc(smem_u32(tileB));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma<true>(tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (it | kk) ? 1u : 0u);
+    }
+    tcgen05_commit(&done_bar);
+    mbar_wait(&done_bar, 0);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
+int int8_mma_peak(int iters, cudaStream_t stream, double *ops_per_s) {
+  const size_t smem = (128 + 256) * 128 + 1024;
+  CAS_CUDA_TRY(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = sm_count();
+  cudaEvent_t e0, e1;
+  CAS_CUDA_TRY(cudaEventCreate(&e0));
+  CAS_CUDA_TRY(cudaEventCreate(&e1));
+  i8_peak_kernel<<<grid, 128, smem, stream>>>(iters / 8 + 1);  // warm-up
+  CAS_CUDA_TRY(cudaEventRecord(e0, stream));
+  i8_peak_kernel<<<grid, 128, smem, stream>>>(iters);
+  CAS_CUDA_TRY(cudaEventRecord(e1, stream));
+  CAS_LAUNCH_CHECK();
+  CAS_CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CAS_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ops_per_s = (double)grid * iters * 4.0 * (2.0 * 128 * 256 * 32) / ((double)ms * 1e-3);
+  return CAS_OK;
+}
+
 int whd_gemm_read_error_flag(const void *workspace, cudaStream_t stream, int *flag) {
   CAS_CUDA_TRY(cudaMemcpyAsync(flag, workspace, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CAS_CUDA_TRY(cudaStreamSynchronize(stream));

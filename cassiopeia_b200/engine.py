@@ -184,6 +184,16 @@ def agglomerate(D, n: int, algo: str, mode: str, max_iters: int = -1):
     return joins_h, last2_h
 
 
+def int8_mma_peak_tops(iters: int = 20000) -> float:
+    """Measured issue rate of the int8 tensor pipe, TOP/s over the whole GPU (``cas_int8_mma_peak``: tcgen05.mma
+    kind::i8 128 x 256 x 32 back to back on shared-memory operands, one CTA per SM)."""
+    torch = _torch()
+    L = _lib.load()
+    out = ctypes.c_double(0.0)
+    _lib.check(L.cas_int8_mma_peak(int(iters), _stream_ptr(torch), ctypes.byref(out)), "cas_int8_mma_peak")
+    return out.value / 1e12
+
+
 def loop_launch_floor_us(k: int, iters: int = 2000, kernels_per_iter: int = 3) -> float:
     """Device microseconds per iteration of the pruned loop's bare launch pattern at live size k
     (``cas_loop_launch_floor``: same grids and programmatic dependent launches, kernels that do nothing)."""

@@ -260,6 +260,11 @@ CAS_API int cas_agglom_prune_diag(const void *workspace_dev, int64_t n, void *st
 CAS_API int cas_loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, void *workspace_dev,
                           size_t workspace_bytes, void *stream);
 
+/* Measurement aid (scripts/map_sweep.py): issue rate of the int8 tensor pipe -- every SM issues iters x 4
+ * tcgen05.mma kind::i8 (128 x 256 x 32) on operands resident in shared memory; *ops_per_s = 2 M N K ops / s over the
+ * device.  The measured denominator of the tensor-core map's roofline fraction. */
+CAS_API int cas_int8_mma_peak(int32_t iters, void *stream, double *ops_per_s);
+
 /* number of kernels the last cas_*_solve / cas_whd_map / cas_solve_host call on this
  * thread launched (bench.py's gpu_launches) */
 CAS_API int64_t cas_last_launch_count(void);

@@ -56,6 +56,28 @@ def test_fast_nj_20k_is_a_valid_tree_and_sharding_does_not_change_it():
     assert np.array_equal(joins, j2) and np.array_equal(last2, l2)
 
 
+def test_upgma_10k_float64_join_list_equals_the_oracle():
+    """BASELINE config 2 exactly (UPGMASolver, 10 000 cells x 40 characters, plain Hamming, float64): the GPU join
+    list against the CPU oracle's (oracle/oracle.c: oracle_upgma, all host threads; about half a minute), with the
+    default (dense) and the pruned scan."""
+    from cassiopeia_b200 import engine
+    from oracle import pyoracle as po
+    import os
+
+    n, m, S = 10000, 40, 50
+    cm, _ = _workload(n, m, S, 0.1, seed=7)
+    D = engine.whd_map(cm, -1, None, S, dtype="f64", method="tensor")
+    want, want_last = po.upgma(D[:, :n].cpu().numpy())
+    got, got_last = engine.agglomerate(D.clone(), n, "upgma", "strict")
+    assert np.array_equal(got, want) and np.array_equal(got_last, want_last)
+    os.environ["CAS_PRUNE"] = "1"
+    try:
+        pruned, pruned_last = engine.agglomerate(D, n, "upgma", "strict")
+    finally:
+        del os.environ["CAS_PRUNE"]
+    assert np.array_equal(pruned, want) and np.array_equal(pruned_last, want_last)
+
+
 def test_upgma_10k_float64_strict_equals_fast_and_values_are_monotone():
     """BASELINE config 2 (UPGMA, 10k x 40, plain Hamming): the loop has no reductions, so the strict and
     the fast float64 paths must give the identical join list; UPGMA merge heights never decrease."""
