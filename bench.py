@@ -415,7 +415,10 @@ def run_b200(args):
         per_iter_us = 1e3 * loop_ms / n_scans
         floor_us = engine.loop_launch_floor_us(n, 2000, 3)
         roofline.update({
-            "kernel": f"scan_pruned_kernel<{tname},{aname}> (+ prune_rowtest_kernel, merge_kernel): the timed loop",
+            "kernel": (f"scan_pruned_kernel<{tname},NJ> (+ prune_rowtest_kernel, merge_kernel): the timed loop"
+                       if args.algo == "nj" else
+                       f"keyed_scan_kernel<{tname}> (+ keyed_rowtest_kernel, merge_kernel<{tname},UPGMA>): the timed "
+                       "loop, tie-aware bounds (DESIGN 4.5)"),
             "traffic": scanned * esz / n_scans,
             "read_fraction_of_algorithmic": scanned * esz / b_alg,
             "note": "exact pruned scan (DESIGN 4.1): bounds on the criterion prove almost every algorithmic byte "

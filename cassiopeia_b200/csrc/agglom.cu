@@ -28,6 +28,7 @@
 #include <stdlib.h>
 
 #include "agglom_exact.cuh"
+#include "agglom_keyed.cuh"
 
 namespace cas {
 
@@ -375,6 +376,134 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_pruned_kernel(ScanArgs a
   TL_STAMP(a.t, 1, 9);
 }
 
+// UPGMA pruned scan with tie-aware bounds (agglom_keyed.cuh): same skeleton as scan_pruned_kernel.
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) keyed_scan_kernel(ScanArgs a, KeyedArgs p) {
+  using KE = KeyedEnc<T>;
+  using BT = typename KE::BT;
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ Cand sCand[SCAN_WARPS];
+  __shared__ bool sLast;
+  __shared__ unsigned long long sRead[SCAN_WARPS];
+  __shared__ unsigned short sList[SCAN_WARPS][PRUNE_WIDE];
+  __shared__ KeyedIter sc;
+  const T *__restrict__ D = static_cast<const T *>(a.D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = a.k;
+  keyed_iter_load(&sc, p, nullptr, false);
+  KeyedLane ls;
+  ls.bq = INFINITY; ls.b2 = INFINITY; ls.bk = ~0ull; ls.bi = -1; ls.bj = -1;
+  PruneWarp pw;
+  pw.gb_seen = INFINITY; pw.nread = 0;
+  const int gw = warp * gridDim.x + blockIdx.x, W = gridDim.x * SCAN_WARPS;
+  constexpr int UNIT_S = sizeof(T) == 8 ? PRUNE_UNIT / 2 : PRUNE_UNIT;
+  {
+    const long long nsub_max = ((long long)k - 1 + SW - 1) / SW;
+    const long long upr_s = (nsub_max + UNIT_S - 1) / UNIT_S;
+    const long long upr_w = (nsub_max + PRUNE_WIDE - 1) / PRUNE_WIDE;
+    const long long ushort = (long long)sc.c_new1 * upr_s;
+    const long long nunits = ushort + (long long)sc.c_new0 * upr_w;
+    for (long long u = gw; u < nunits; u += W) {
+      const bool shrt = u < ushort;
+      const long long v = shrt ? u : u - ushort;
+      const long long upr = shrt ? upr_s : upr_w;
+      const int unit = shrt ? UNIT_S : PRUNE_WIDE;
+      const long long r = v / upr;
+      const int i = p.list_new[shrt ? p.wlast - (int)r : (int)r];
+      const int sb = (int)(v - r * upr) * unit;
+      if ((long long)sb * SW >= i) continue;
+      keyed_unit<T>(ls, pw, D + (int64_t)i * a.ld, i, i, __ldcg(a.ids + i), sb, p, sc, sList[warp], lane, unit);
+    }
+  }
+  if (lane == 0) sRead[warp] = pw.nread;
+  Cand c = block_best(ls.bq, ls.bi, ls.bj, ls.b2, a.ids, sCand);  // contains a __syncthreads
+  if (threadIdx.x == 0) {
+    a.cand[blockIdx.x] = c;
+    unsigned long long tot = 0;
+    for (int w2 = 0; w2 < SCAN_WARPS; ++w2) tot += sRead[w2];
+    p.cta_read[blockIdx.x] = tot;
+    __threadfence();
+    unsigned prev = atomicInc(a.counter, gridDim.x - 1);
+    sLast = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sLast) return;
+  c = reduce_candidates(a.cand, (int)gridDim.x, sCand);
+  const int lo = min(c.si, c.sj), hi = max(c.si, c.sj);
+  if (lo < 0) {  // uniform
+    if (threadIdx.x == 0) {
+      publish_no_candidate(a);
+      p.cnt_old[0] = 0u;
+      p.cnt_old[1] = 0u;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    a.sel->lo = lo;
+    a.sel->hi = hi;
+    a.sel->size_lo = a.sizes ? a.sizes[lo] : 1;
+    a.sel->size_hi = a.sizes ? a.sizes[hi] : 1;
+    const int id_lo = a.ids[lo], id_hi = a.ids[hi];
+    a.sel->id_lo = id_lo;
+    a.sel->id_hi = id_hi;
+    a.joins[2 * a.t] = min(id_lo, id_hi);
+    a.joins[2 * a.t + 1] = max(id_lo, id_hi);
+  }
+  if (threadIdx.x == 96) a.sel->dij = (double)D[(int64_t)lo * a.ld + hi];
+  if (threadIdx.x == 32) {
+    // every other CTA has finished (counter): clear the per-iteration state; the two rows the merge is about to
+    // rewrite become unknown; the list the NEXT row test builds (this iteration's dirty list) is emptied
+    *p.gbest = enc_f64(INFINITY);
+    p.gstart[0] = enc_f64(INFINITY);
+    p.gstart[1] = ~0ull;
+    BT *betaV = static_cast<BT *>(p.betaV);
+    betaV[lo] = KE::enc(-INFINITY);
+    betaV[hi] = KE::enc(-INFINITY);
+    p.betaP[lo] = KEYED_NOPID;
+    p.betaP[hi] = KEYED_NOPID;
+    p.cnt_old[0] = 0u;
+    p.cnt_old[1] = 0u;
+  }
+  if (threadIdx.x == 64) {
+    const double gap = c.q2 - c.q;
+    if (gap <= 1e-6 * fmax(1.0, fabs(c.q))) atomicAdd(a.stats + 0, 1ull);
+    if (gap == 0.0) atomicAdd(a.stats + 1, 1ull);
+    atomicAdd(a.stats + 2, (unsigned long long)sc.c_new0 + sc.c_new1);  // diagnostics: rows listed, whole loop
+  }
+  {
+    unsigned long long tot = 0;
+    for (int x = threadIdx.x; x < (int)gridDim.x; x += SCAN_THREADS) tot += __ldcg(p.cta_read + x);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if (lane == 0 && tot) atomicAdd(p.scanned, tot);
+  }
+  const int nsk = (k + SW - 1) / SW;
+  BT *Ev = static_cast<BT *>(p.Ev);
+  for (int sgm = threadIdx.x; sgm < nsk; sgm += SCAN_THREADS) {
+    Ev[(int64_t)lo * p.stride + sgm] = KE::enc(-INFINITY);
+    Ev[(int64_t)hi * p.stride + sgm] = KE::enc(-INFINITY);
+  }
+}
+
+// keyed bounds: everything unknown, lists empty, no warm-start pair
+template <typename BT>
+__global__ void keyed_init_kernel(BT *Ev, int64_t count, BT *betaV, int32_t *betaP, int64_t nrows, BT ninf,
+                                  unsigned long long *gbest, unsigned long long *gstart, unsigned *cnt,
+                                  unsigned long long *scanned, int32_t *pool) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t e = x; e < count; e += (int64_t)gridDim.x * blockDim.x) Ev[e] = ninf;
+  for (int64_t e = x; e < nrows; e += (int64_t)gridDim.x * blockDim.x) { betaV[e] = ninf; betaP[e] = KEYED_NOPID; }
+  if (x < 2 * POOL) pool[x] = -1;
+  if (x == 0) {
+    *gbest = enc_f64(INFINITY);
+    gstart[0] = enc_f64(INFINITY);
+    gstart[1] = ~0ull;
+    cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0u;
+    *scanned = 0ull;
+  }
+}
+
 struct MergeArgs {
   void *D;
   int64_t ld;
@@ -401,6 +530,7 @@ struct MergeArgs {
   int t;  // iteration index
   void *newcol; int64_t newcol_stride;  // pruned scan: contiguous copies of the two rewritten columns (PruneArgs)
   double *pmax; unsigned *pufup;        // per-CTA maxima ([grid][4]) and largest uf increase ([grid])
+  int keyed; unsigned long long *gstart;  // UPGMA tie-aware pruned scan (agglom_keyed.cuh)
 };
 
 constexpr int WARM_THREADS = MERGE_THREADS - 32;  // the merge's last CTA: warp 0 sums, warps 1.. warm-start gbest
@@ -563,7 +693,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeArgs a) {
       sLast = (prev == gridDim.x - 1);
     }
     __syncthreads();
-    if (sLast && threadIdx.x >= 32) warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32, true);
+    if (sLast && a.keyed) {
+      if constexpr (!NJ)
+        keyed_warm_start<T, MERGE_THREADS>(static_cast<const T *>(a.D), a.ld, a.ids, a.pool, a.cand, a.ncand, a.gbest,
+                                           a.gstart, lo, hi, last, a.rot);
+    } else if (sLast && threadIdx.x >= 32) {
+      warm_start_gbest<T, NJ>(a, lo, hi, last, (int)threadIdx.x - 32, true);
+    }
     return;
   }
   if (!a.maintain_R) return;
@@ -867,6 +1003,9 @@ struct AgglomWorkspace {
   double *pmax; unsigned *pufup;
   int32_t *xlog;
   unsigned *strict_flag; int *strict_epoch;
+  // UPGMA tie-aware pruned scan (agglom_keyed.cuh)
+  unsigned long long *kEv; int32_t *kEp; unsigned long long *kbetaV; int32_t *kbetaP; int32_t *klist[2];
+  unsigned *kcnt; unsigned long long *gstart;
   size_t bytes;
 };
 
@@ -913,21 +1052,41 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.xlog = c.take<int32_t>(4 * XLOG_CAP);
   w.strict_flag = c.take<unsigned>(4);
   w.strict_epoch = reinterpret_cast<int *>(w.strict_flag + 1);
+  w.kEv = c.take<unsigned long long>((size_t)w.lb_stride * (size_t)n);  // float maps use the first half as unsigned
+  w.kEp = c.take<int32_t>((size_t)w.lb_stride * (size_t)n);
+  w.kbetaV = c.take<unsigned long long>((size_t)n + 32);
+  w.kbetaP = c.take<int32_t>((size_t)n + 32);
+  w.klist[0] = w.worklist;
+  w.klist[1] = c.take<int32_t>((size_t)n + 32);
+  w.kcnt = c.take<unsigned>(4);
+  w.gstart = c.take<unsigned long long>(2);
   w.bytes = c.used();
   return w;
 }
 
-// Scan selection.  Default: the pruned scan for fast NJ, the dense scan for UPGMA (on tie-heavy,
-// low-information inputs every zero-distance pair lies inside the tie window and has to be re-read each
-// iteration, which measured slower than streaming: 13.6 s vs ~10 s at 50k cells; on informative inputs the
-// pruned UPGMA scan is 2.6x faster, so it stays available).  CAS_PRUNE=1 forces the pruned scan for every
-// mode except strict NJ (whose sequential row sums read the whole map each iteration anyway), CAS_PRUNE=0
-// the dense scan (every live pair read every iteration).
-bool prune_enabled(bool nj) {
+// Scan selection.  Default: the pruned scan for NJ (fast / exact) and for UPGMA.  UPGMA uses the tie-aware bounds of
+// agglom_keyed.cuh: with value-only bounds every pair tied with the minimum (zero distances between duplicated cells,
+// the few distinct values of unweighted Hamming distances) had to be re-read each iteration, which measured slower
+// than the dense scan on such inputs; CAS_UPGMA_KEYED=0 keeps that variant available.  CAS_PRUNE=1 forces the pruned
+// scan for every mode except strict NJ (whose sequential row sums read the whole map each iteration anyway),
+// CAS_PRUNE=0 the dense scan (every live pair read every iteration).
+// UPGMA, pruned scan: tie-aware bounds (agglom_keyed.cuh) unless CAS_UPGMA_KEYED=0 asks for the value-only bounds
+static bool upgma_keyed() {
+  const char *e = getenv("CAS_UPGMA_KEYED");
+  return !(e && e[0] == '0');
+}
+// the row-sharded loop has value-only bounds: pruned by default for NJ only
+bool prune_enabled_sharded(bool nj) {
   const char *e = getenv("CAS_PRUNE");
   if (e && e[0] == '0') return false;
   if (e && e[0] == '1') return true;
   return nj;
+}
+bool prune_enabled(bool nj) {
+  const char *e = getenv("CAS_PRUNE");
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  return nj || upgma_keyed();
 }
 
 size_t agglom_workspace_bytes(int64_t n) { return carve_workspace(nullptr, n > 0 ? n : 1).bytes; }
@@ -981,7 +1140,18 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
   const int min_k = prune_min_k();
   // CAS_PRUNE_WIDE=0: every listed row in short units (the behaviour before the split work list)
   const int prune_wide = getenv("CAS_PRUNE_WIDE") ? (atoi(getenv("CAS_PRUNE_WIDE")) != 0) : 1;
-  if (prune) {
+  const bool keyed = prune && !NJ && upgma_keyed();
+  using KBT = typename KeyedEnc<T>::BT;
+  if (keyed) {
+    // the encoded -inf (enc_f32 / enc_f64 are device functions): ~bits(-inf)
+    keyed_init_kernel<KBT><<<sms * 4, 256, 0, stream>>>(reinterpret_cast<KBT *>(w.kEv), w.lb_stride * n,
+                                                        reinterpret_cast<KBT *>(w.kbetaV), w.kbetaP, n,
+                                                        (KBT)(sizeof(T) == 8 ? 0x000FFFFFFFFFFFFFull : 0x007FFFFFull),
+                                                        w.gbest, w.gstart, w.kcnt,
+                                                        w.scanned, w.pool);
+    CAS_LAUNCH_CHECK();
+    CAS_CUDA_TRY(cudaMemsetAsync(w.hdr, 0, 8 * sizeof(float), stream));  // no drift in this scheme (diagnostics read it)
+  } else if (prune) {
     prune_init_kernel<<<sms * 4, 256, 0, stream>>>(w.E, w.lb_stride * n, w.beta, n, w.hdr, w.dmax, w.gbest, w.wcount,
                                                    w.scanned, w.pool);
     CAS_LAUNCH_CHECK();
@@ -1053,7 +1223,24 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
       if (eb_floor > 0.0) xw_floor_kernel<<<1, 1, 0, stream>>>(w.rmax_bits, eb_floor);
     }
     was_pruned = prune_it;
-    if (prune_it) {
+    if (prune_it && keyed) {
+      if constexpr (!NJ) {
+        KeyedArgs ka{};
+        ka.Ev = w.kEv; ka.Ep = w.kEp; ka.stride = w.lb_stride; ka.betaV = w.kbetaV; ka.betaP = w.kbetaP;
+        ka.list_new = w.klist[cur]; ka.cnt_new = w.kcnt + 2 * cur;
+        ka.list_old = w.klist[cur ^ 1]; ka.cnt_old = w.kcnt + 2 * (cur ^ 1);
+        ka.wlast = (int)n + 31;
+        ka.gbest = w.gbest; ka.gstart = w.gstart; ka.ids = w.ids;
+        ka.newcol = w.newcol; ka.newcol_stride = n;
+        ka.scanned = w.scanned; ka.cta_read = w.cta_read;
+        const int nrow_ctas = (k + 255) / 256;
+        CAS_CUDA_TRY(launch_pdl(keyed_rowtest_kernel<T>, (unsigned)(nrow_ctas + sms), 256u, stream, ka, k,
+                                (const Sel *)w.sel, t > 0 ? 1 : 0, (int)(n + t - 1), nrow_ctas, (int)t));
+        CAS_LAUNCH_CHECK();
+        grid = sms * 2;
+        CAS_CUDA_TRY(launch_pdl(keyed_scan_kernel<T>, (unsigned)grid, (unsigned)SCAN_THREADS, stream, sa, ka));
+      }
+    } else if (prune_it) {
       PruneArgs pa{};
       pa.E = w.E; pa.stride = w.lb_stride; pa.beta = w.beta; pa.uf = w.uf; pa.hdr = w.hdr; pa.dmax = w.dmax;
       pa.gbest = w.gbest; pa.worklist = w.worklist; pa.wcount = w.wcount; pa.sugg = w.sugg;
@@ -1090,6 +1277,7 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.t = (int)t;
     ma.newcol = w.newcol; ma.newcol_stride = n;
     ma.pmax = w.pmax; ma.pufup = w.pufup;
+    ma.keyed = (prune_it && keyed) ? 1 : 0; ma.gstart = w.gstart;
     if (prune_it) {
       CAS_CUDA_TRY(launch_pdl(merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
                               (unsigned)MERGE_THREADS, stream, ma));

@@ -31,7 +31,7 @@
 
 namespace cas {
 
-bool prune_enabled(bool nj);  // agglom.cu
+bool prune_enabled_sharded(bool nj);  // agglom.cu
 int prune_min_k();             // agglom.cu
 
 constexpr int SHB = 64;  // rows per ownership block
@@ -1190,7 +1190,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
     set_error("the sharded exact mode needs the P2P exchange (CAS_SHARDED_EXCHANGE=p2p)");
     return CAS_ERR_UNSUPPORTED;
   }
-  const bool prune = (exact || prune_enabled(NJ)) && n > 2;
+  const bool prune = (exact || prune_enabled_sharded(NJ)) && n > 2;
   const int min_k = exact ? 0 : prune_min_k();  // exact pruned scan (agglom_pruned.cuh; policy in agglom.cu)
   for (auto &rk : ranks) {
     sh_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(

@@ -20,10 +20,11 @@ def _map(n, m, S, dtype, rate, miss, weighted, seed):
     return engine.whd_map(cm, -1, w if weighted else None, S, dtype=dtype, method="exact"), n + 1
 
 
-def _run(D, n, algo, mode, prune, monkeypatch):
+def _run(D, n, algo, mode, prune, monkeypatch, keyed=True):
     from cassiopeia_b200 import engine
 
     monkeypatch.setenv("CAS_PRUNE", "1" if prune else "0")
+    monkeypatch.setenv("CAS_UPGMA_KEYED", "1" if keyed else "0")  # UPGMA: tie-aware bounds (default) / value-only
     monkeypatch.setenv("CAS_PRUNE_MIN_K", "0")  # keep the pruned scan down to the last iteration
     joins, last2 = engine.agglomerate(D.clone(), n, algo, mode)
     return joins, last2, dict(engine.last_stats)
@@ -39,7 +40,16 @@ def test_pruned_equals_dense(n, m, S, rate, miss, algo, mode, dtype, weighted, m
     jd, ld, sd = _run(D, nn, algo, mode, False, monkeypatch)
     jp, lp, sp = _run(D, nn, algo, mode, True, monkeypatch)
     assert np.array_equal(jd, jp) and np.array_equal(ld, lp)
-    assert (sd["near_ties"], sd["exact_ties"]) == (sp["near_ties"], sp["exact_ties"])
+    if algo == "upgma":
+        # tie-aware bounds skip tied pairs that lose on the id key: its tie counters see only the pairs that were read
+        # (diagnostics, not part of the result); the value-only variant reproduces the dense scan's counters
+        jv, lv, sv = _run(D, nn, algo, mode, True, monkeypatch, keyed=False)
+        assert np.array_equal(jd, jv) and np.array_equal(ld, lv)
+        # (exact ties only: which runner-ups inside the near-tie window are evaluated depends on the order in which the
+        # scan meets them, for UPGMA the screening threshold carries no window)
+        assert sd["exact_ties"] == sv["exact_ties"] and sp["exact_ties"] <= sd["exact_ties"]
+    else:
+        assert (sd["near_ties"], sd["exact_ties"]) == (sp["near_ties"], sp["exact_ties"])
     assert sd["scanned_elements"] == 0
     dense = sum(k * (k - 1) // 2 for k in range(3, nn + 1))
     assert 0 < sp["scanned_elements"] <= dense
@@ -47,6 +57,37 @@ def test_pruned_equals_dense(n, m, S, rate, miss, algo, mode, dtype, weighted, m
         # float64 UPGMA has no reductions: the GPU loop is the reference's arithmetic
         oj, ol = po.upgma(D[:, :nn].cpu().numpy())
         assert np.array_equal(jp, oj)
+
+
+@pytest.mark.parametrize("n,m,S,rate,miss,dup", [(300, 10, 3, 0.05, 0.0, 3), (1500, 20, 4, 0.1, 0.1, 4),
+                                                 (5000, 40, 50, 0.1, 0.1, 2), (6000, 12, 2, 0.3, 0.0, 1)])
+@pytest.mark.parametrize("dtype,mode", [("f64", "strict"), ("f32", "fast")])
+def test_upgma_tie_heavy_inputs_keyed_bounds(n, m, S, rate, miss, dup, dtype, mode, monkeypatch):
+    """Plain Hamming distances over few characters and duplicated cells: thousands of pairs tie with the minimum at
+    most iterations (distance 0 inside duplicate groups, then a handful of distinct rationals).  The tie-aware
+    pruned scan must select the dense scan's pairs -- the reference's first row-major arg-min -- and read far less
+    than the value-only pruned scan, which has to re-read every tied pair every iteration."""
+    from cassiopeia_b200 import engine
+    from cassiopeia_b200.synthetic import simulate_character_matrix
+
+    cm, _, _ = simulate_character_matrix(n, m, S, seed=n + dup, mutation_rate=rate, missing_fraction=miss)
+    rng = np.random.default_rng(n)
+    cm = np.concatenate([cm] + [cm[rng.integers(0, n, n // 2)] for _ in range(dup - 1)])  # duplicated cells, shuffled
+    cm = cm[rng.permutation(cm.shape[0])]
+    nn = cm.shape[0]
+    D = engine.whd_map(cm, -1, None, S, dtype=dtype, method="exact")
+    jd, ld, sd = _run(D, nn, "upgma", mode, False, monkeypatch)
+    jk, lk, sk = _run(D, nn, "upgma", mode, True, monkeypatch)
+    assert np.array_equal(jd, jk) and np.array_equal(ld, lk)
+    assert sd["exact_ties"] > nn // 4  # the input really is tie-heavy
+    jv, lv, sv = _run(D, nn, "upgma", mode, True, monkeypatch, keyed=False)
+    assert np.array_equal(jd, jv)
+    print(f"n={nn} {dtype}: elements read keyed {sk['scanned_elements']:.3e} value-only {sv['scanned_elements']:.3e}")
+    if nn >= 1500:
+        assert sk["scanned_elements"] < 0.5 * sv["scanned_elements"]
+    if dtype == "f64" and nn <= 4000:
+        oj, ol = po.upgma(D[:, :nn].cpu().numpy())
+        assert np.array_equal(jk, oj) and np.array_equal(lk, ol)
 
 
 def test_default_policy_switches_to_dense_at_small_sizes(monkeypatch):
@@ -96,10 +137,11 @@ def test_short_units_for_every_row_equal_wide_units(algo, monkeypatch):
     """CAS_PRUNE_WIDE=0 (every listed row in 8-sub-segment units) and the default split work list (rows with a
     known bound in 32-sub-segment units) select the same pairs."""
     D, nn = _map(5000, 40, 50, "f32", 0.3, 0.2, True, seed=9)
+    # the switch belongs to the value-only bounds (NJ, and UPGMA with CAS_UPGMA_KEYED=0)
     monkeypatch.setenv("CAS_PRUNE_WIDE", "0")
-    j0, l0, s0 = _run(D, nn, algo, "fast", True, monkeypatch)
+    j0, l0, s0 = _run(D, nn, algo, "fast", True, monkeypatch, keyed=False)
     monkeypatch.setenv("CAS_PRUNE_WIDE", "1")
-    j1, l1, s1 = _run(D, nn, algo, "fast", True, monkeypatch)
+    j1, l1, s1 = _run(D, nn, algo, "fast", True, monkeypatch, keyed=False)
     assert np.array_equal(j0, j1) and np.array_equal(l0, l1)
     assert (s0["near_ties"], s0["exact_ties"]) == (s1["near_ties"], s1["exact_ties"])
     assert s0["rows_listed"] > 0 and s1["rows_listed"] > 0
