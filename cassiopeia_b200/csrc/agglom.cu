@@ -1006,6 +1006,7 @@ struct AgglomWorkspace {
   // UPGMA tie-aware pruned scan (agglom_keyed.cuh)
   unsigned long long *kEv; int32_t *kEp; unsigned long long *kbetaV; int32_t *kbetaP; int32_t *klist[2];
   unsigned *kcnt; unsigned long long *gstart;
+  size_t bytes_core;  // without the UPGMA-only arrays above (carved last: NJ workspaces end here)
   size_t bytes;
 };
 
@@ -1052,6 +1053,7 @@ static AgglomWorkspace carve_workspace(void *base, int64_t n) {
   w.xlog = c.take<int32_t>(4 * XLOG_CAP);
   w.strict_flag = c.take<unsigned>(4);
   w.strict_epoch = reinterpret_cast<int *>(w.strict_flag + 1);
+  w.bytes_core = c.used();
   w.kEv = c.take<unsigned long long>((size_t)w.lb_stride * (size_t)n);  // float maps use the first half as unsigned
   w.kEp = c.take<int32_t>((size_t)w.lb_stride * (size_t)n);
   w.kbetaV = c.take<unsigned long long>((size_t)n + 32);
@@ -1089,7 +1091,11 @@ bool prune_enabled(bool nj) {
   return nj || upgma_keyed();
 }
 
-size_t agglom_workspace_bytes(int64_t n) { return carve_workspace(nullptr, n > 0 ? n : 1).bytes; }
+// upgma = false: without the arrays of the tie-aware UPGMA scan (n * ceil(n / 128) * 12 bytes: 3.7 GB at 200k cells)
+size_t agglom_workspace_bytes(int64_t n, bool upgma) {
+  const AgglomWorkspace w = carve_workspace(nullptr, n > 0 ? n : 1);
+  return upgma ? w.bytes : w.bytes_core;
+}
 
 // choose rows-per-tile so that the persistent grid has a few tiles per CTA
 static inline void plan_scan(int k, int target_ctas, int &tr, int &nrb, int &ncb, int &ntiles) {
@@ -1414,7 +1420,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) smj_update_kernel(SmjArgs a) {
 
 size_t smj_workspace_bytes(int64_t n, int32_t m) {
   Carver c(nullptr);
-  c.take<char>(agglom_workspace_bytes(n));
+  c.take<char>(agglom_workspace_bytes(n, false));
   c.take<int32_t>((size_t)m * (size_t)(n > 0 ? n : 1));
   c.take<int32_t>((size_t)m + 32);
   return c.used();
@@ -1427,7 +1433,7 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
   CAS_REQUIRE(workspace_bytes >= smj_workspace_bytes(n, m), "workspace too small for the SMJ loop");
   CAS_REQUIRE(fn >= 0 && fn <= 5 && fn != CAS_FN_HAMMING_DISTANCE, "pair function %d cannot drive the SMJ loop", fn);
   Carver carve(workspace);
-  void *aws = carve.take<char>(agglom_workspace_bytes(n));
+  void *aws = carve.take<char>(agglom_workspace_bytes(n, false));
   int32_t *chars = carve.take<int32_t>((size_t)m * (size_t)n);
   int32_t *lca = carve.take<int32_t>((size_t)m + 32);
   AgglomWorkspace wk = carve_workspace(aws, n);
@@ -1482,7 +1488,7 @@ int agglom_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t algo, in
   CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
   CAS_REQUIRE(mode == CAS_MODE_STRICT || mode == CAS_MODE_FAST || mode == CAS_MODE_EXACT, "bad mode %d", mode);
   CAS_REQUIRE(!(mode != CAS_MODE_FAST && dtype != CAS_F64), "strict and exact modes require a float64 map");
-  CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(n), "workspace too small for agglomeration");
+  CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(n, algo == CAS_ALGO_UPGMA), "workspace too small for agglomeration");
   CAS_REQUIRE(((uintptr_t)D & 15) == 0, "D must be 16-byte aligned");
   if (algo == CAS_ALGO_NJ) {
     if (dtype == CAS_F64) return agglom_run<double, true>(D, n, ld, mode, max_iters, joins, last2, workspace, stream);

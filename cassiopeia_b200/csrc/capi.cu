@@ -54,7 +54,7 @@ int int8_mma_peak(int iters, cudaStream_t stream, double *ops_per_s);
 int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
                  int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
-size_t agglom_workspace_bytes(int64_t n);
+size_t agglom_workspace_bytes(int64_t n, bool upgma);
 int agglom_read_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *near_ties, int64_t *exact_ties);
 size_t smj_workspace_bytes(int64_t n, int32_t m);
 int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w, int32_t n_states,
@@ -153,8 +153,8 @@ int cas_whd_map_cyclic(const int32_t *cm, int64_t n, int32_t m, int32_t missing,
 }
 
 size_t cas_agglom_workspace_bytes(int64_t n, int32_t algo, int32_t mode) {
-  (void)algo; (void)mode;
-  return agglom_workspace_bytes(n);
+  (void)mode;
+  return agglom_workspace_bytes(n, algo == CAS_ALGO_UPGMA);
 }
 
 int cas_agglom_stats(const void *workspace, int64_t n, void *stream, int64_t *near_ties, int64_t *exact_ties) {
@@ -186,7 +186,7 @@ int cas_loop_launch_floor(int64_t k, int64_t iters, int32_t kernels_per_iter, vo
                           void *stream) {
   reset_launch_count();
   CAS_REQUIRE(workspace && k >= 1 && iters >= 0 && kernels_per_iter >= 1 && kernels_per_iter <= 3, "bad argument");
-  CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(k), "workspace too small");
+  CAS_REQUIRE(workspace_bytes >= agglom_workspace_bytes(k, false), "workspace too small");
   return loop_launch_floor(k, iters, kernels_per_iter, workspace, (cudaStream_t)stream);
 }
 
