@@ -392,8 +392,11 @@ struct ShColsArgs {
 
 // The part of the cols kernel that needs the selected pair: marks the two rows the merge rewrites unknown,
 // publishes this rank's pieces of columns lo / hi / last, the selection and the join.  All threads of all CTAs.
+// `vl_pre` (have_vl): this thread's element of column `last`, loaded by the caller before it waited for the peers'
+// candidates -- the column does not depend on the selection, and its scattered loads (one per 400 KB row) are the
+// slowest of the three.
 template <typename T>
-__device__ __forceinline__ void sh_cols_body(const ShColsArgs &a, int si, int sj) {
+__device__ __forceinline__ void sh_cols_body(const ShColsArgs &a, int si, int sj, bool have_vl = false, T vl_pre = (T)0) {
   __shared__ bool sLast;
   const bool p2p = a.peers.ex[0] != nullptr;
   const int lo = min(si, sj), hi = max(si, sj), last = a.k - 1;
@@ -422,7 +425,7 @@ __device__ __forceinline__ void sh_cols_body(const ShColsArgs &a, int si, int sj
     const int lr = blockIdx.x * 256 + threadIdx.x;
     if (lr < sh_count(a.k, a.r, a.G)) {
       const T *row = D + (int64_t)lr * a.ld;
-      const T va = row[lo], vb = row[hi], vl = row[last];
+      const T va = row[lo], vb = row[hi], vl = have_vl ? vl_pre : row[last];
       if (p2p) {
         // write this rank's chunk straight into every rank's gather area over NVLink
         for (int pr = 0; pr < a.G; ++pr) {
@@ -453,10 +456,11 @@ __device__ __forceinline__ void sh_cols_body(const ShColsArgs &a, int si, int sj
   }
   if (p2p) {
     // last block of this kernel signals "chunk landed" to every rank (also when nothing could be selected:
-    // the peers' merge kernels must not wait for ever)
-    __threadfence_system();
+    // the peers' merge kernels must not wait for ever).  One system-scope fence per CTA, after the barrier that orders
+    // every thread's peer stores before it (fences are cumulative), instead of one per thread.
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();
       unsigned prev = atomicInc(a.counter, gridDim.x - 1);
       sLast = (prev == gridDim.x - 1);
     }
@@ -498,9 +502,14 @@ __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
   pdl_launch_dependents();
   __shared__ Cand sCand[8];
   __shared__ bool sLastX;
+  // independent of the peers' candidates: in flight during the flag wait
+  const int lr_pre = blockIdx.x * 256 + threadIdx.x;
+  const bool have_vl = lr_pre < sh_count(a.k, a.r, a.G);
+  const T vl_pre = have_vl ? static_cast<const T *>(a.Dloc)[(int64_t)lr_pre * a.ld + (a.k - 1)] : (T)0;
+  const int epoch_pre = (a.exact && a.strict_epoch) ? __ldcg(a.strict_epoch) : 0;
   const Cand c = sh_cols_reduce<T>(a, sCand);
   if constexpr (sizeof(T) == 8) {
-    if (a.exact && __ldcg(a.strict_epoch) != a.t) {
+    if (a.exact && epoch_pre != a.t) {
       const double W = exact_window(a.p.xw, a.k, a.tinv);
       if (c.si >= 0 && c.q2 - c.q <= W) {
         // X1: collect among this rank's listed rows (work-list entries, E and beta are indexed by LOCAL row)
@@ -547,7 +556,7 @@ __global__ void __launch_bounds__(256) sh_cols_kernel(ShColsArgs a) {
       if (blockIdx.x == 0 && threadIdx.x == 0) a.xstate[0] = 0u;  // strict tail: nothing to resolve
     }
   }
-  sh_cols_body<T>(a, c.si, c.sj);
+  sh_cols_body<T>(a, c.si, c.sj, have_vl, vl_pre);
 }
 
 struct ShSumsArgs {
@@ -716,46 +725,88 @@ struct ShMergeArgs {
   int exact; double *Eb; double *Ab; unsigned long long *xw; double *apartial;
   const int32_t *order_old; const int32_t *pos_old; int32_t *order_new; int32_t *pos_new;
   void *newcol; int64_t newcol_stride;  // contiguous copies of the two rewritten columns (PruneArgs), replicated
+  double *pmax; unsigned *pufup;        // per-CTA maxima ([grid][4]) and largest uf increase ([grid])
 };
 
 // Per-rank warm start of the pruned scan's bound (prune_warm_start, agglom_pruned.cuh): only pairs whose row
 // this rank owns can be evaluated here, and only those enter its pool.
+// Called either by all MERGE_THREADS threads (UPGMA) or by warps 1.. of the last CTA while warp 0 sums (NJ with
+// maintained sums): WARM_SH threads with indices 0 .. WARM_SH - 1.
 template <typename T, bool NJ>
 __device__ __forceinline__ void sh_warm_start(const ShMergeArgs &a, int lo, int hi, int last) {
   const T *D = static_cast<const T *>(a.Dloc);
   const int64_t ld = a.ld;
   const int G = a.G, r = a.r;
-  prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last, a.rot,
-                                         [=](int si, int sj) -> const T * {
-                                           if (sh_owner(si, G) != r) return nullptr;
-                                           return D + (int64_t)sh_local(si, G) * ld + sj;
-                                         }, (int)threadIdx.x);
+  auto addr = [=](int si, int sj) -> const T * {
+    if (sh_owner(si, G) != r) return nullptr;
+    return D + (int64_t)sh_local(si, G) * ld + sj;
+  };
+  if (a.maintain_R)
+    prune_warm_start<T, NJ, MERGE_THREADS - 32>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last,
+                                                a.rot, addr, (int)threadIdx.x - 32);
+  else
+    prune_warm_start<T, NJ, MERGE_THREADS>(a.pool, a.cand, a.ncand, a.sugg, a.gbest, a.R, a.tinv_next, lo, hi, last, a.rot,
+                                           addr, (int)threadIdx.x);
 }
 
+// Latency structure as in merge_kernel (agglom.cu; profiles/r2_ncu_kernels.md has the per-line stall profile that
+// motivated it: a chain of ~8 lazily issued, dependent loads): (1) the thread's replicated state is loaded before the
+// NVLink flag wait, the gathered values right after it, all in one wave; (2) the selection and the handful of
+// broadcast values that depend on it are loaded once per CTA into shared memory; (3) running maxima go through
+// per-CTA slots that the last CTA reduces instead of per-warp load + atomic pairs; (4) in the last CTA warp 0 sums
+// while the other warps warm-start gbest.  The arithmetic is unchanged (the merged row is computed redundantly and
+// identically on every rank, and identically to the single-GPU loop).
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ double sPart[MERGE_THREADS / 32];
   __shared__ double sPartA[MERGE_THREADS / 32];
+  __shared__ double sMax[4][MERGE_THREADS / 32];
+  __shared__ unsigned sUfUp[MERGE_THREADS / 32];
+  __shared__ Sel sSel;
+  __shared__ double sDij, sG0l, sG1l;
+  __shared__ int sPlo, sPhi, sIdLast, sSzLast;
   __shared__ bool sLast;
   T *__restrict__ D = static_cast<T *>(a.Dloc);
   const T *g = static_cast<const T *>(a.gath);
+  const int k = a.k, last = k - 1, G = a.G;
+  const int64_t ld = a.ld;
+  const int64_t cstride = 3 * (int64_t)a.chunk;
+  const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = v < k;
+  // replicated state of this slot: independent of the exchange, in flight during the flag wait
+  const double Rv0 = (live && a.maintain_R) ? a.R[v] : 0.0;
+  const double Eb0 = (live && a.exact) ? a.Eb[v] : 0.0, Ab0 = (live && a.exact) ? a.Ab[v] : 0.0;
+  const float uf0 = (live && a.prune && a.maintain_R) ? a.uf[v] : 0.f;
+  const int ord0 = (live && a.order_old) ? a.order_old[v] : 0;
   if (a.peers.ex[0] != nullptr) {
     ShExHeader *own = ex_header(a.peers.ex[a.r]);
     if (threadIdx.x < a.G) wait_flag(&own->flag2[threadIdx.x], a.tag, &own->error);
     __syncthreads();
     g = reinterpret_cast<const T *>(ex_gath(a.peers.ex[a.r]));
   }
-  const Sel s = *a.sel;
-  if (s.lo < 0) return;  // no candidate (sh_cols_body)
-  const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1, G = a.G;
-  const int64_t ld = a.ld;
-  const int64_t cstride = 3 * (int64_t)a.chunk;
   auto gathered = [&](int which, int slot) -> T {
     return g[(int64_t)sh_owner(slot, G) * cstride + (int64_t)which * a.chunk + sh_local(slot, G)];
   };
-  const double dij = (double)gathered(0, hi);  // d(hi, lo)
+  // the slot's three gathered values and the selection: one wave
+  const T gv0 = live ? gathered(0, v) : (T)0, gv1 = live ? gathered(1, v) : (T)0, gv2 = live ? gathered(2, v) : (T)0;
+  if (threadIdx.x == 0) sSel = *a.sel;
+  __syncthreads();
+  const Sel s = sSel;
+  if (s.lo < 0) return;  // no candidate (sh_cols_body)
+  const int lo = s.lo, hi = s.hi;
+  // broadcast values that depend on the selection: one thread each, then shared memory
+  if (threadIdx.x == 0) sDij = (double)gathered(0, hi);  // d(hi, lo)
+  if (threadIdx.x == 32) sG0l = (double)gathered(0, last);
+  if (threadIdx.x == 64) sG1l = (double)gathered(1, last);
+  if (threadIdx.x == 96) sPlo = a.order_old ? a.pos_old[lo] : 0;
+  if (threadIdx.x == 128) sPhi = a.order_old ? a.pos_old[hi] : 0;
+  if (threadIdx.x == 160) sIdLast = a.ids[last];
+  if (threadIdx.x == 192) sSzLast = a.sizes ? a.sizes[last] : 0;
+  __syncthreads();
+  const double dij = sDij;
   auto merged = [&](double da, double db) -> double {
     if (NJ) return __dmul_rn(0.5, __dsub_rn(__dadd_rn(da, db), dij));
     const double zi = (double)s.size_lo, zj = (double)s.size_hi;
@@ -766,13 +817,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
   T *row_hi = own_hi ? D + (int64_t)sh_local(hi, G) * ld : nullptr;
   // merged distance of the node that sits in the last slot (needed at (lo,hi) / (hi,lo))
   T nv_last = (T)0;
-  if (hi != last) nv_last = round_to<T>(merged((double)gathered(0, last), (double)gathered(1, last)));
+  if (hi != last) nv_last = round_to<T>(merged(sG0l, sG1l));
 
-  const int v = blockIdx.x * MERGE_THREADS + threadIdx.x;
   double contrib = 0.0, mine = 0.0;
   float uf_up = 0.f;
   double ebv = 0.0, abv = 0.0;
-  if (v < k) {
+  if (live) {
     const bool own_v = sh_owner(v, G) == a.r;
     T *row_v = own_v ? D + (int64_t)sh_local(v, G) * ld : nullptr;
     if (v == lo) {
@@ -784,24 +834,26 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
       if (own_hi) row_hi[hi] = (T)0;
       if (own_lo && hi != last) row_lo[hi] = nv_last;
     } else {
-      const double da = (double)gathered(0, v), db = (double)gathered(1, v);
+      const double da = (double)gv0, db = (double)gv1;
       const T nvs = round_to<T>(merged(da, db));
       contrib = (double)nvs;
+      const bool moves = (v == last && hi != last);
+      const int vdst = moves ? hi : v;
       double Rv = 0.0;
       if (a.maintain_R) {
-        const double x1 = __dsub_rn(a.R[v], da), x2 = __dsub_rn(x1, db);
+        const double x1 = __dsub_rn(Rv0, da), x2 = __dsub_rn(x1, db);
         Rv = __dadd_rn(x2, contrib);
+        mine = Rv;
+        a.R[vdst] = Rv;
         if (a.exact) {  // as in merge_kernel (agglom.cu)
-          ebv = __dadd_ru(a.Eb[v], __dmul_ru(__dadd_ru(__dadd_ru(fabs(x1), fabs(x2)), fabs(Rv)), EXACT_U1));
-          abv = fmax(__dsub_ru(__dsub_ru(__dadd_ru(a.Ab[v], fabs(contrib)), fabs(da)), fabs(db)), 0.0);
-          const int dst = (v == last && hi != last) ? hi : v;
-          a.Eb[dst] = ebv;
-          a.Ab[dst] = abv;
+          ebv = __dadd_ru(Eb0, __dmul_ru(__dadd_ru(__dadd_ru(fabs(x1), fabs(x2)), fabs(Rv)), EXACT_U1));
+          abv = fmax(__dsub_ru(__dsub_ru(__dadd_ru(Ab0, fabs(contrib)), fabs(da)), fabs(db)), 0.0);
+          a.Eb[vdst] = ebv;
+          a.Ab[vdst] = abv;
         }
       }
-      const int vdst = (v == last && hi != last) ? hi : v;
       if (hi != last && v != last) {
-        const T l = gathered(2, v);
+        const T l = gv2;
         if (own_hi) row_hi[v] = l;
         if (own_v) row_v[hi] = l;
         if (a.prune) static_cast<T *>(a.newcol)[a.newcol_stride + v] = l;
@@ -810,26 +862,21 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
       if (own_v) row_v[lo] = nvs;
       if (a.prune) static_cast<T *>(a.newcol)[vdst] = nvs;
       if (a.prune && a.maintain_R) {
-        const bool moves = (v == last && hi != last);
         const float un = __double2float_rn(__dmul_rn(a.tinv_next, Rv));
-        if (!moves) uf_up = un - a.uf[v];
-        a.uf[moves ? hi : v] = un;
+        if (!moves) uf_up = un - uf0;
+        a.uf[vdst] = un;
       }
-      if (v == last && hi != last) {
-        a.ids[hi] = a.ids[last];
-        if (a.sizes) a.sizes[hi] = a.sizes[last];
-        if (a.maintain_R) { a.R[hi] = Rv; mine = Rv; }
-      } else if (a.maintain_R) {
-        a.R[v] = Rv;
-        mine = Rv;
+      if (moves) {
+        a.ids[hi] = sIdLast;
+        if (a.sizes) a.sizes[hi] = sSzLast;
       }
     }
     // id-ordered list of live slots (exact mode), as in merge_kernel
     if (a.order_old) {
       const int p = v;
-      const int p_lo = a.pos_old[lo], p_hi = a.pos_old[hi];
+      const int p_lo = sPlo, p_hi = sPhi;
       if (p != p_lo && p != p_hi) {
-        int sl = a.order_old[p];
+        int sl = ord0;
         if (sl == last) sl = hi;
         const int np = p - (p > p_lo ? 1 : 0) - (p > p_hi ? 1 : 0);
         a.order_new[np] = sl;
@@ -840,10 +887,6 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
         a.pos_new[lo] = k - 2;
       }
     }
-  }
-  if (a.prune && a.maintain_R) {
-    const unsigned m = __reduce_max_sync(0xffffffffu, enc_f32(uf_up));
-    if ((threadIdx.x & 31) == 0 && m > __ldcg(a.dmax)) atomicMax(a.dmax, m);
   }
   if (a.prune && !a.maintain_R) {
     __syncthreads();
@@ -857,56 +900,103 @@ __global__ void __launch_bounds__(MERGE_THREADS) sh_merge_kernel(ShMergeArgs a) 
     return;
   }
   if (!a.maintain_R) return;
-  warp_atomic_absmax(a.rmax_bits, mine);
+  // per-warp reductions: the new row's sum (fixed shuffle tree: deterministic), |new row| and the maxima
   double acontrib = fabs(contrib);
-  if (a.exact) {
-    warp_atomic_max_nonneg(a.xw + XW_EBMAX, ebv);
-    warp_atomic_max_nonneg(a.xw + XW_ABMAX, abv);
-    warp_atomic_max_nonneg(a.xw + XW_DABS, acontrib);
+  double m0 = fabs(mine), m1 = ebv, m2 = abv, m3 = acontrib;
+  unsigned up = enc_f32(uf_up);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
+    m0 = fmax(m0, __shfl_down_sync(0xffffffffu, m0, off));
+    if (a.exact) {
+      acontrib = __dadd_rn(acontrib, __shfl_down_sync(0xffffffffu, acontrib, off));
+      m1 = fmax(m1, __shfl_down_sync(0xffffffffu, m1, off));
+      m2 = fmax(m2, __shfl_down_sync(0xffffffffu, m2, off));
+      m3 = fmax(m3, __shfl_down_sync(0xffffffffu, m3, off));
+    }
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) contrib = __dadd_rn(contrib, __shfl_down_sync(0xffffffffu, contrib, off));
-  if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = contrib;
-  if (a.exact) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acontrib = __dadd_rn(acontrib, __shfl_down_sync(0xffffffffu, acontrib, off));
-    if ((threadIdx.x & 31) == 0) sPartA[threadIdx.x >> 5] = acontrib;
+  if (a.prune) up = __reduce_max_sync(0xffffffffu, up);
+  if (lane == 0) {
+    sPart[warp] = contrib; sPartA[warp] = acontrib;
+    sMax[0][warp] = m0; sMax[1][warp] = m1; sMax[2][warp] = m2; sMax[3][warp] = m3;
+    sUfUp[warp] = up;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double sum = 0.0;
-    for (int w = 0; w < MERGE_THREADS / 32; ++w) sum = __dadd_rn(sum, sPart[w]);
-    a.partial[blockIdx.x] = sum;
-    if (a.exact) {
-      double asum = 0.0;
-      for (int w = 0; w < MERGE_THREADS / 32; ++w) asum = __dadd_rn(asum, sPartA[w]);
-      a.apartial[blockIdx.x] = asum;
+    double sum = 0.0, asum = 0.0, x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    unsigned u = enc_f32(0.f);
+    for (int w = 0; w < MERGE_THREADS / 32; ++w) {
+      sum = __dadd_rn(sum, sPart[w]);
+      asum = __dadd_rn(asum, sPartA[w]);
+      x0 = fmax(x0, sMax[0][w]); x1 = fmax(x1, sMax[1][w]); x2 = fmax(x2, sMax[2][w]); x3 = fmax(x3, sMax[3][w]);
+      u = max(u, sUfUp[w]);
     }
+    a.partial[blockIdx.x] = sum;
+    a.apartial[blockIdx.x] = asum;
+    double *pm = a.pmax + 4 * (size_t)blockIdx.x;
+    pm[0] = x0; pm[1] = x1; pm[2] = x2; pm[3] = x3;
+    a.pufup[blockIdx.x] = u;
     __threadfence();
     unsigned prev = atomicInc(a.counter, gridDim.x - 1);
     sLast = (prev == gridDim.x - 1);
   }
   __syncthreads();
-  if (sLast) {
-    if (threadIdx.x < 32) {
-      double sum, asum;
-      sum_partials_one_warp(a.partial, a.apartial, (int)gridDim.x, a.exact != 0, sum, asum);  // as merge_kernel
-      if (threadIdx.x == 0) {
-        a.R[lo] = sum;
-        atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(fabs(sum)));
-        if (a.prune) a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
-        if (a.exact) {
-          const double ab = up30(asum);
-          const double eb = up30(new_row_sum_depth((int)gridDim.x) * EXACT_U1 * ab);
-          a.Ab[lo] = ab;
-          a.Eb[lo] = eb;
-          atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(eb));
-          atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(ab));
-        }
+  if (!sLast) return;
+  // Last CTA (everything it reads of the other CTAs' results is read through L2)
+  if (warp == 0) {
+    const int nb = (int)gridDim.x;
+    double sum, asum;
+    sum_partials_one_warp(a.partial, a.apartial, nb, a.exact != 0, sum, asum);  // as merge_kernel
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    unsigned u = enc_f32(0.f);
+    for (int b0 = 0; b0 < nb; b0 += 128) {  // four slots per lane in flight
+      double2 pa[4], pb[4];
+      unsigned pu[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int b = b0 + q * 32 + lane;
+        const bool in = b < nb;
+        const double2 *pm = reinterpret_cast<const double2 *>(a.pmax + 4 * (size_t)(in ? b : 0));
+        pa[q] = in ? __ldcg(pm) : make_double2(0.0, 0.0);
+        pb[q] = (in && a.exact) ? __ldcg(pm + 1) : make_double2(0.0, 0.0);
+        pu[q] = (in && a.prune) ? __ldcg(a.pufup + b) : enc_f32(0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        x0 = fmax(x0, pa[q].x); x1 = fmax(x1, pa[q].y); x2 = fmax(x2, pb[q].x); x3 = fmax(x3, pb[q].y);
+        u = max(u, pu[q]);
       }
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      x0 = fmax(x0, __shfl_down_sync(0xffffffffu, x0, off));
+      x1 = fmax(x1, __shfl_down_sync(0xffffffffu, x1, off));
+      x2 = fmax(x2, __shfl_down_sync(0xffffffffu, x2, off));
+      x3 = fmax(x3, __shfl_down_sync(0xffffffffu, x3, off));
+    }
+    u = __reduce_max_sync(0xffffffffu, u);
+    if (lane == 0) {
+      a.R[lo] = sum;
+      x0 = fmax(x0, fabs(sum));
+      atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(x0));
+      if (a.prune) {
+        a.uf[lo] = __double2float_rn(__dmul_rn(a.tinv_next, sum));
+        atomicMax(a.dmax, u);
+      }
+      if (a.exact) {
+        const double ab = up30(asum);
+        const double eb = up30(new_row_sum_depth(nb) * EXACT_U1 * ab);
+        a.Ab[lo] = ab;
+        a.Eb[lo] = eb;
+        atomicMax(a.xw + XW_EBMAX, (unsigned long long)__double_as_longlong(fmax(x1, eb)));
+        atomicMax(a.xw + XW_ABMAX, (unsigned long long)__double_as_longlong(fmax(x2, ab)));
+        atomicMax(a.xw + XW_DABS, (unsigned long long)__double_as_longlong(x3));
+      }
+    }
+  } else if (a.prune) {
+    // entries touching slot lo are dropped, so the warm start needs neither R[lo] nor anything warp 0 writes
+    sh_warm_start<T, NJ>(a, lo, hi, last);
   }
-  if (sLast && a.prune) sh_warm_start<T, NJ>(a, lo, hi, last);
 }
 
 // initial row sums of the local rows (same lane-strided order as rowsum_init_kernel)
@@ -1109,6 +1199,7 @@ struct ShWorkspace {
   unsigned long long *xstats;
   double *newcol;
   unsigned *strict_flag; int *strict_epoch;
+  double *pmax; unsigned *pufup;
   size_t bytes;
 };
 
@@ -1155,6 +1246,8 @@ static ShWorkspace sh_carve(void *base, int64_t n, int G, size_t esz) {
   w.newcol = c.take<double>(2 * (size_t)n);
   w.strict_flag = c.take<unsigned>(4);
   w.strict_epoch = reinterpret_cast<int *>(w.strict_flag + 1);
+  w.pmax = c.take<double>(4 * ((n + MERGE_THREADS - 1) / MERGE_THREADS + 1));
+  w.pufup = c.take<unsigned>((n + MERGE_THREADS - 1) / MERGE_THREADS + 1);
   w.bytes = c.used();
   return w;
 }
@@ -1377,6 +1470,7 @@ static int sh_run(std::vector<ShRank> &ranks, int64_t n, int64_t ld, int G, int6
       ma.cand = rk.w.cand; ma.ncand = rk_grid[rk.r % SH_MAXG]; ma.sugg = rk.w.sugg; ma.gbest = rk.w.gbest;
       ma.pool = rk.w.pool; ma.rot = (int)((t * 61) % POOL);
       ma.newcol = rk.w.newcol; ma.newcol_stride = n;
+      ma.pmax = rk.w.pmax; ma.pufup = rk.w.pufup;
       ma.exact = exact ? 1 : 0; ma.Eb = rk.w.Eb; ma.Ab = rk.w.Ab; ma.xw = rk.w.rmax_bits; ma.apartial = rk.w.apartial;
       ma.order_old = exact ? rk.w.order[cur] : nullptr; ma.pos_old = exact ? rk.w.pos[cur] : nullptr;
       ma.order_new = exact ? rk.w.order[cur ^ 1] : nullptr; ma.pos_new = exact ? rk.w.pos[cur ^ 1] : nullptr;
