@@ -90,6 +90,42 @@ def test_upgma_tie_heavy_inputs_keyed_bounds(n, m, S, rate, miss, dup, dtype, mo
         assert np.array_equal(jk, oj) and np.array_equal(lk, ol)
 
 
+@pytest.mark.parametrize("kind", ["small_ints", "gaussian", "all_equal", "two_values", "uniform"])
+@pytest.mark.parametrize("n", [6, 200, 1300])
+def test_upgma_keyed_bounds_on_arbitrary_symmetric_maps(n, kind, monkeypatch):
+    """User-supplied maps: massive ties (integers, a single value, two values), negative entries, no ties at all.
+    Tie-aware pruned UPGMA == dense == the oracle's first row-major arg-min."""
+    import torch
+    from cassiopeia_b200 import engine
+
+    rng = np.random.default_rng(n * 13 + len(kind))
+    if kind == "small_ints":
+        A = rng.integers(0, 3, (n, n)).astype(np.float64)
+    elif kind == "gaussian":
+        A = rng.normal(size=(n, n))
+    elif kind == "all_equal":
+        A = np.full((n, n), 0.25)
+    elif kind == "two_values":
+        A = np.where(rng.random((n, n)) < 0.02, 0.0, 1.0 / 3.0)
+    else:
+        A = rng.random((n, n))
+    D = np.triu(A, 1)
+    D = D + D.T
+    host = np.zeros((n, engine.padded_ld(n)), dtype=np.float64)
+    host[:, :n] = D
+    dev = torch.from_numpy(host).cuda()
+    want, want_last = po.upgma(D)
+    jk, lk, sk = _run(dev, n, "upgma", "strict", True, monkeypatch)
+    assert np.array_equal(jk, want) and np.array_equal(lk, want_last), kind
+    jd, ld, sd = _run(dev, n, "upgma", "strict", False, monkeypatch)
+    assert np.array_equal(jd, want) and np.array_equal(ld, want_last)
+    # float32 copy of the same map (values exactly representable or not: the loop's own arithmetic decides)
+    dev32 = dev.float()
+    j32k, l32k, _ = _run(dev32, n, "upgma", "fast", True, monkeypatch)
+    j32d, l32d, _ = _run(dev32, n, "upgma", "fast", False, monkeypatch)
+    assert np.array_equal(j32k, j32d) and np.array_equal(l32k, l32d)
+
+
 def test_default_policy_switches_to_dense_at_small_sizes(monkeypatch):
     """Default: NJ prunes above 3072 live nodes and finishes with the dense scan; same joins either way."""
     from cassiopeia_b200 import engine
