@@ -53,7 +53,7 @@ size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t 
 int int8_mma_peak(int iters, cudaStream_t stream, double *ops_per_s);
 int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w,
                  int32_t n_states, void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1,
-                 void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                 void *workspace, size_t workspace_bytes, cudaStream_t stream, int world = 1, int rank = 0);
 size_t agglom_workspace_bytes(int64_t n, bool upgma);
 int agglom_read_stats(const void *workspace, int64_t n, cudaStream_t stream, int64_t *near_ties, int64_t *exact_ties);
 size_t smj_workspace_bytes(int64_t n, int32_t m);
@@ -147,7 +147,13 @@ int cas_whd_map_cyclic(const int32_t *cm, int64_t n, int32_t m, int32_t missing,
   CAS_REQUIRE(n >= 1 && m >= 1 && ld >= n, "bad sizes");
   CAS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d of %d", rank, world);
   CAS_REQUIRE(dtype == CAS_F32 || dtype == CAS_F64, "bad dtype %d", dtype);
-  CAS_REQUIRE(method == CAS_MAP_EXACT, "only CAS_MAP_EXACT builds block-cyclic shards");
+  CAS_REQUIRE(method == CAS_MAP_EXACT || method == CAS_MAP_TENSOR, "bad map method %d", method);
+  if (method == CAS_MAP_TENSOR && world > 1)
+    return whd_gemm_map(cm, n, m, missing, w, n_states, D_local, ld, dtype, 0, n, workspace, workspace_bytes,
+                        (cudaStream_t)stream, world, rank);
+  if (method == CAS_MAP_TENSOR)  // one rank: the shard is the whole map
+    return whd_gemm_map(cm, n, m, missing, w, n_states, D_local, ld, dtype, 0, n, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
   return whd_exact_map(cm, n, m, missing, w, n_states, D_local, ld, dtype, 0, n, workspace,
                        workspace_bytes, (cudaStream_t)stream, world, rank);
 }

@@ -61,7 +61,19 @@ struct GemmParams {
   int64_t ld;
   int head_chunks;       // fixed-point weighted path: 128-byte chunks of the [U_p | P] operands (ceil(m / 128))
   const double *scale;   // fixed-point weighted path: device scalar 2^-F
+  // Shard mode (shard_world > 0): D holds this rank's rows of the block-cyclic layout (64-row blocks r, r + G, ...:
+  // local row lr is global row ((lr / 64) * G + r) * 64 + lr % 64), every column of each: a 128-row tile is two
+  // 64-row blocks that are G blocks apart in the operand arrays, loaded as two half boxes; no mirrored stores.
+  CUtensorMap maps_half[MAX_MAPS];  // box 128 B x 64 rows
+  int shard_world, shard_rank;
+  int nloc_rows;   // rows of this rank's shard
+  int nloc_tiles;  // ceil(nloc_rows / 128)
+  int ncol_tiles;  // ceil(n / 128)
 };
+
+__host__ __device__ __forceinline__ int64_t shard_global_row(int64_t lr, int G, int r) {
+  return ((lr >> 6) * G + r) * 64 + (lr & 63);
+}
 
 // ---- PTX helpers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -235,14 +247,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   GemmSmem<TO> &sm = *reinterpret_cast<GemmSmem<TO> *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ntiles = (int64_t)p.ntile_rows * (p.ntile_rows + 1) / 2;
+  const bool shard = p.shard_world > 0;
+  const int64_t ntiles = shard ? (int64_t)p.nloc_tiles * p.ncol_tiles
+                               : (int64_t)p.ntile_rows * (p.ntile_rows + 1) / 2;
+  // shard mode: consecutive CTAs take different row tiles of the same column tile (the column operand is shared in L2)
+  auto tile_pos = [&](int64_t tile, int &ti, int &tj) {
+    if (shard) { tj = (int)(tile / p.nloc_tiles); ti = (int)(tile - (int64_t)tj * p.nloc_tiles); }
+    else tile_of(tile, p.ntile_rows, ti, tj);
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SLOTS; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.tfull[s], 1); mbar_init(&sm.tempty[s], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < (KIND == 2 ? 10 : (KIND == 1 ? 2 : 4)); ++i)
+    for (int i = 0; i < (KIND == 2 ? 10 : (KIND == 1 ? 2 : 4)); ++i) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[i]) : "memory");
+      if (shard) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps_half[i]) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -261,10 +282,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
     if (lane == 0) {
       uint32_t lc = 0;  // loads issued so far
       const int elems_per_chunk = I8 ? CHUNK_BYTES : CHUNK_BYTES / 2;
+      // one operand tile: 128 rows starting at `row` -- or, for the row side of a shard, two 64-row half boxes
+      auto load_tile = [&](uint32_t slot, int map, int kc, bool row_side, int ti, int col0) {
+        if (shard && row_side) {
+          const int r0 = (int)shard_global_row((int64_t)ti * GT, p.shard_world, p.shard_rank);
+          const int r1 = (int)shard_global_row((int64_t)ti * GT + 64, p.shard_world, p.shard_rank);
+          tma_load_2d(sm.tile[slot], &p.maps_half[map], &sm.full[slot], kc, r0);
+          tma_load_2d(sm.tile[slot] + 64 * CHUNK_BYTES, &p.maps_half[map], &sm.full[slot], kc, r1);
+        } else {
+          tma_load_2d(sm.tile[slot], &p.maps[map], &sm.full[slot], kc, row_side ? ti * GT : col0);
+        }
+      };
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int ti, tj;
-        tile_of(tile, p.ntile_rows, ti, tj);
-        const int row0 = ti * GT, col0 = tj * GT;
+        tile_pos(tile, ti, tj);
+        const int col0 = tj * GT;
         for (int c = 0; c < p.chunks; ++c) {
 #pragma unroll
           for (int l = 0; l < P::NL; ++l, ++lc) {
@@ -280,10 +312,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
               if (type == 0) { map = l == 0 ? 9 : 4 + l; side = l == 0 ? 1 : 0; }
               else if (type == 1) { map = l == 0 ? 9 : 4 + l; side = l == 0 ? 0 : 1; }
               else { map = l == 0 ? 4 : l - 1; side = l == 0 ? 1 : 0; }
-              tma_load_2d(sm.tile[slot], &p.maps[map], &sm.full[slot], kc, side ? col0 : row0);
+              load_tile(slot, map, kc, side == 0, ti, col0);
             } else {
-              tma_load_2d(sm.tile[slot], &p.maps[P::load_map(l)], &sm.full[slot], c * elems_per_chunk,
-                          P::load_side(l) ? col0 : row0);
+              load_tile(slot, P::load_map(l), c * elems_per_chunk, P::load_side(l) == 0, ti, col0);
             }
           }
         }
@@ -355,11 +386,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       int ti, tj;
-      tile_of(tile, p.ntile_rows, ti, tj);
-      const int row0 = ti * GT, col0 = tj * GT;
-      const int64_t gi = (int64_t)row0 + lrow;  // global row
-      const bool diag_tile = (ti == tj);
-      const bool whole = (int64_t)row0 + GT <= p.n && (int64_t)col0 + GT <= p.n;
+      tile_pos(tile, ti, tj);
+      const int row0 = ti * GT, col0 = tj * GT;  // row0: first row of the tile in D (a LOCAL row in shard mode)
+      // global row of this thread's accumulator lane
+      const int64_t gi = shard ? ((int64_t)row0 + lrow < p.nloc_rows
+                                      ? shard_global_row((int64_t)row0 + lrow, p.shard_world, p.shard_rank) : p.n)
+                               : (int64_t)row0 + lrow;
+      // rows of D this tile may write; global row of the tile's row rr (diagonal test)
+      const int64_t row_limit = shard ? (int64_t)p.nloc_rows : p.n;
+      auto global_row = [&](int rr) -> int64_t {
+        return shard ? shard_global_row((int64_t)row0 + rr, p.shard_world, p.shard_rank) : (int64_t)row0 + rr;
+      };
+      // the diagonal crosses the tile: same tile indices (full map) / the tile's global rows overlap its columns (shard)
+      const bool diag_tile = shard ? true : (ti == tj);
+      const bool mirror = !shard && !diag_tile;  // the transposed tile is written too (full map, off-diagonal tiles)
+      const bool whole = (int64_t)row0 + GT <= row_limit && (int64_t)col0 + GT <= p.n &&
+                         (!shard || global_row(GT - 1) < p.n);
       // presence masks: this thread's row in registers, the tile's columns in shared memory
       unsigned long long mrow[PW];
       asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with sm.pm
@@ -411,14 +453,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
 #pragma unroll
           for (int w = 0; w < PW; ++w) den += __popcll(mrow[w] & sm.pm[cbase + e][w]);
           float d = den > 0 ? __fdividef(numf[e], (float)den) : 0.f;
-          if (diag_tile && (cbase + e == lrow)) d = 0.f;
+          if (diag_tile && ((int64_t)col0 + cbase + e == gi)) d = 0.f;
           stage[lane][e] = (TO)d;
-          if (!diag_tile && (whole || (gi < p.n && (int64_t)col0 + cbase + e < p.n))) mir0[(int64_t)e * p.ld] = (TO)d;
+          if (mirror && (whole || (gi < p.n && (int64_t)col0 + cbase + e < p.n))) mir0[(int64_t)e * p.ld] = (TO)d;
         }
         __syncwarp();
         TO *dst = D + ((int64_t)row0 + q * 32) * p.ld + col0 + cbase;
         for (int rr = 0; rr < 32; ++rr, dst += p.ld) {
-          if (!whole && (int64_t)row0 + q * 32 + rr >= p.n) break;
+          if (!whole && ((int64_t)row0 + q * 32 + rr >= row_limit || global_row(q * 32 + rr) >= p.n)) break;
 #pragma unroll
           for (int h = 0; h < HALF; h += 32)
             if (whole || (int64_t)col0 + cbase + h + lane < p.n) dst[h + lane] = stage[rr][h + lane];
@@ -465,9 +507,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
                 d = (TO)__double2float_rn(__ddiv_rn(num, (double)den));
               }
             }
-            if (diag_tile && (cb + e == lrow)) d = (TO)0;
+            if (diag_tile && ((int64_t)col0 + cb + e == gi)) d = (TO)0;
             stage[lane][(cb - cbase) + e] = d;
-            if (!diag_tile && (whole || (gi < p.n && (int64_t)col0 + cb + e < p.n))) mir[(int64_t)e * p.ld] = d;
+            if (mirror && (whole || (gi < p.n && (int64_t)col0 + cb + e < p.n))) mir[(int64_t)e * p.ld] = d;
           }
         }
         if (part + HALF == 64) {
@@ -479,7 +521,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) whd_gemm_kernel(const __grid_
         // direct rows: lane l writes columns l (+32) of each of the warp's 32 rows
         TO *dst = D + ((int64_t)row0 + q * 32) * p.ld + col0 + cbase;
         for (int rr = 0; rr < 32; ++rr, dst += p.ld) {
-          if (!whole && (int64_t)row0 + q * 32 + rr >= p.n) break;
+          if (!whole && ((int64_t)row0 + q * 32 + rr >= row_limit || global_row(q * 32 + rr) >= p.n)) break;
 #pragma unroll
           for (int h = 0; h < HALF; h += 32)
             if (whole || (int64_t)col0 + cbase + h + lane < p.n) dst[h + lane] = stage[rr][h + lane];
@@ -1048,15 +1090,19 @@ size_t whd_gemm_workspace_bytes(int64_t n, int32_t m, int32_t n_states, int32_t 
   return c.used();
 }
 
+// world > 1: D is rank `rank`'s shard of the block-cyclic layout (sharded.cu: 64-row blocks r, r + G, ...), filled
+// by the single-SM kernel in shard mode (every column of the rank's rows, no mirroring); world = 1: the whole map.
 int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const double *w, int32_t n_states,
                  void *D, int64_t ld, int32_t dtype, int64_t row0, int64_t row1, void *workspace,
-                 size_t workspace_bytes, cudaStream_t stream) {
+                 size_t workspace_bytes, cudaStream_t stream, int world, int rank) {
   const bool weighted = (w != nullptr);
   const int S = n_states > 0 ? n_states : 1;
+  const bool shard = world > 1;
   if (!(row0 == 0 && row1 == n)) {
-    set_error("CAS_MAP_TENSOR computes the whole map only (use CAS_MAP_EXACT for row blocks)");
+    set_error("CAS_MAP_TENSOR computes the whole map or a block-cyclic shard (use CAS_MAP_EXACT for row blocks)");
     return CAS_ERR_UNSUPPORTED;
   }
+  CAS_REQUIRE(!shard || (rank >= 0 && rank < world), "bad rank %d of %d", rank, world);
   CAS_REQUIRE(m <= 64 * MAXPW, "CAS_MAP_TENSOR supports at most %d characters (m=%d)", 64 * MAXPW, m);
   CAS_REQUIRE(workspace_bytes >= whd_gemm_workspace_bytes(n, m, n_states, weighted), "workspace too small");
   GemmLayout L = layout_of(m, S);
@@ -1077,6 +1123,21 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
   CAS_LAUNCH_CHECK();
   p.pw = pw; p.pmask = pmask;
   p.ntile_rows = (int)((n + GT - 1) / GT);
+  if (shard) {
+    // rows of this rank: 64-row blocks r, r + G, ... below n (the last block may be partial)
+    const int64_t nblocks = (n + 63) / 64;
+    int64_t rows = 0;
+    for (int64_t b = rank; b < nblocks; b += world) rows += (b * 64 + 64 <= n) ? 64 : (n - b * 64);
+    p.shard_world = world; p.shard_rank = rank;
+    p.nloc_rows = (int)rows;
+    p.nloc_tiles = (int)((rows + GT - 1) / GT);
+    p.ncol_tiles = (int)((n + GT - 1) / GT);
+    if (rows == 0) return CAS_OK;  // fewer 64-row blocks than ranks: this rank holds nothing
+  }
+  // shard mode loads the row-side operand as two 64-row boxes
+  auto half_map = [&](int i, void *base, int64_t kcols, int esz) -> int {
+    return shard ? make_map(&p.maps_half[i], base, n, kcols, esz, 64) : CAS_OK;
+  };
   if (!weighted) {
     int8_t *A = carve.take<int8_t>((size_t)n * L.Kp);
     int8_t *B = carve.take<int8_t>((size_t)n * L.Kp);
@@ -1087,6 +1148,10 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     int rc = make_map(&p.maps[0], A, n, L.Kp, 1);
     if (rc != CAS_OK) return rc;
     rc = make_map(&p.maps[1], B, n, L.Kp, 1);
+    if (rc != CAS_OK) return rc;
+    rc = half_map(0, A, L.Kp, 1);
+    if (rc != CAS_OK) return rc;
+    rc = half_map(1, B, L.Kp, 1);
     if (rc != CAS_OK) return rc;
     map_bases[0] = A; map_bases[1] = B;
     p.chunks = (int)(L.Kp / CHUNK_BYTES);
@@ -1111,16 +1176,24 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
       if (rc != CAS_OK) return rc;
       rc = make_map(&p.maps[5 + i], Up + (size_t)i * n * Km, n, Km, 1);
       if (rc != CAS_OK) return rc;
+      rc = half_map(i, Xp + (size_t)i * n * Kx8, Kx8, 1);
+      if (rc != CAS_OK) return rc;
+      rc = half_map(5 + i, Up + (size_t)i * n * Km, Km, 1);
+      if (rc != CAS_OK) return rc;
     }
     int rc = make_map(&p.maps[4], Xm2, n, Kx8, 1);
     if (rc != CAS_OK) return rc;
     rc = make_map(&p.maps[9], Pm, n, Km, 1);
     if (rc != CAS_OK) return rc;
+    rc = half_map(4, Xm2, Kx8, 1);
+    if (rc != CAS_OK) return rc;
+    rc = half_map(9, Pm, Km, 1);
+    if (rc != CAS_OK) return rc;
     p.head_chunks = (int)(Km / CHUNK_BYTES);
     p.chunks = 2 * p.head_chunks + (int)(Kx8 / CHUNK_BYTES);
     p.scale = scale;
     const int64_t tiles8 = (n + GT - 1) / GT;
-    const int64_t ntiles8 = tiles8 * (tiles8 + 1) / 2;
+    const int64_t ntiles8 = shard ? (int64_t)p.nloc_tiles * p.ncol_tiles : tiles8 * (tiles8 + 1) / 2;
     CAS_REQUIRE(ntiles8 < 2147483647LL, "too many tiles");
 #define LAUNCH_W8(TO, PWV)                                                                         \
   do {                                                                                             \
@@ -1156,11 +1229,17 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     }
     int rc = make_map(&p.maps[3], Y, n, L.Kx, 2);
     if (rc != CAS_OK) return rc;
+    for (int i = 0; i < 3; ++i) {
+      rc = half_map(i, XW[i], L.Kx, 2);
+      if (rc != CAS_OK) return rc;
+    }
+    rc = half_map(3, Y, L.Kx, 2);
+    if (rc != CAS_OK) return rc;
     for (int i = 0; i < 3; ++i) map_bases[i] = XW[i];
     map_bases[3] = Y;
     p.chunks = (int)(L.Kx / (CHUNK_BYTES / 2));
   }
-  if (gemm_cta_group(weighted) == 2) {
+  if (!shard && gemm_cta_group(weighted) == 2) {
     // 2-SM kernel: 256-row tiles, N2 = 256 (int8) / 128 (bf16) columns, clusters of two CTAs
     Gemm2Params q;
     memset(&q, 0, sizeof(q));
@@ -1221,7 +1300,7 @@ int whd_gemm_map(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const
     return CAS_OK;
   }
   const int64_t tiles = (n + GT - 1) / GT;
-  const int64_t ntiles = tiles * (tiles + 1) / 2;
+  const int64_t ntiles = shard ? (int64_t)p.nloc_tiles * p.ncol_tiles : tiles * (tiles + 1) / 2;
   CAS_REQUIRE(ntiles < 2147483647LL, "too many tiles");
 #define LAUNCH_GEMM(I8, TO, PWV)                                                                   \
   do {                                                                                             \

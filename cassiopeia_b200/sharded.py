@@ -24,7 +24,8 @@ from typing import Optional
 import numpy as np
 
 from . import _lib, engine
-from ._lib import CAS_ALGO_NJ, CAS_ALGO_UPGMA, CAS_F32, CAS_F64, CAS_MAP_EXACT, CAS_MODE_EXACT, CAS_MODE_FAST
+from ._lib import (CAS_ALGO_NJ, CAS_ALGO_UPGMA, CAS_F32, CAS_F64, CAS_MAP_EXACT, CAS_MAP_TENSOR, CAS_MODE_EXACT,
+                   CAS_MODE_FAST)
 
 _MODE = {"fast": CAS_MODE_FAST, "exact": CAS_MODE_EXACT}
 
@@ -74,8 +75,13 @@ def shard_rows(n: int, rank: int, world: int) -> np.ndarray:
 
 
 # ---- device side ----------------------------------------------------------------------------
-def build_shard(cm_dev, missing: int, table, n_states: int, rank: int, world: int, dtype: str = "f32"):
-    """This rank's rows of the map, [local_capacity, ld], from the replicated character matrix."""
+def build_shard(cm_dev, missing: int, table, n_states: int, rank: int, world: int, dtype: str = "f32",
+                method: str = "exact"):
+    """This rank's rows of the map, [local_capacity, ld], from the replicated character matrix.
+
+    ``method="tensor"``: the tcgen05 kernel in shard mode (bit-exact for unweighted data, fixed point <= 1e-6
+    relative for prior-weighted data); ``"auto"``: tensor for unweighted data, exact otherwise (the exact mode of the
+    loop needs the reference's float64 distances, which only the unweighted tensor path reproduces)."""
     torch = engine._torch()
     L = _lib.load()
     n, m = int(cm_dev.shape[0]), int(cm_dev.shape[1])
@@ -84,18 +90,28 @@ def build_shard(cm_dev, missing: int, table, n_states: int, rank: int, world: in
     tdtype = torch.float64 if dtype == "f64" else torch.float32
     D = torch.zeros((cap, ld), dtype=tdtype, device="cuda")
     w_t = torch.from_numpy(np.ascontiguousarray(table, dtype=np.float64)).cuda() if table is not None else None
-    ws_bytes = int(L.cas_whd_workspace_bytes(n, m, int(n_states), 1 if w_t is not None else 0, CAS_MAP_EXACT))
+    if method == "auto":
+        method = "tensor" if (w_t is None and m <= 512 and m * (int(n_states) + 2) <= 16384) else "exact"
+    code = CAS_MAP_TENSOR if method == "tensor" else CAS_MAP_EXACT
+    ws_bytes = int(L.cas_whd_workspace_bytes(n, m, int(n_states), 1 if w_t is not None else 0, code))
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda")
     rc = L.cas_whd_map_cyclic(cm_dev.data_ptr(), n, m, int(missing), w_t.data_ptr() if w_t is not None else None,
                               int(n_states), D.data_ptr(), ld, CAS_F64 if dtype == "f64" else CAS_F32,
-                              int(rank), int(world), CAS_MAP_EXACT, ws.data_ptr(), ws_bytes,
+                              int(rank), int(world), code, ws.data_ptr(), ws_bytes,
                               engine._stream_ptr(torch))
     _lib.check(rc, "cas_whd_map_cyclic")
+    if code == CAS_MAP_TENSOR:
+        # the encode passes flag states outside [0, n_states] in the first word of the workspace
+        flag = int(ws[:4].view(torch.int32)[0].item())
+        if flag != 0:
+            raise _lib.B200LibraryError("character matrix holds a state outside [0, n_states] that is not the missing "
+                                        "indicator")
     return D
 
 
 def emulated_solve(codes: np.ndarray, missing: int, table, n_states: int, algo: str, world: int,
-                   dtype: str = "f32", max_iters: int = -1, p2p: bool = False, mode: str = "fast"):
+                   dtype: str = "f32", max_iters: int = -1, p2p: bool = False, mode: str = "fast",
+                   map_method: str = "exact"):
     """All `world` virtual ranks in this process on the current GPU (no collective): the same
     kernels as the multi-process path, used to check that sharding does not change the joins."""
     torch = engine._torch()
@@ -104,7 +120,7 @@ def emulated_solve(codes: np.ndarray, missing: int, table, n_states: int, algo: 
     n = int(cm_dev.shape[0])
     ld = engine.padded_ld(n)
     code = CAS_F64 if dtype == "f64" else CAS_F32
-    shards = [build_shard(cm_dev, missing, table, n_states, r, world, dtype) for r in range(world)]
+    shards = [build_shard(cm_dev, missing, table, n_states, r, world, dtype, map_method) for r in range(world)]
     ws_bytes = int(L.cas_sharded_workspace_bytes(n, world, code))
     wss = [torch.empty(ws_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
     njoin = max(n - 2, 0)
@@ -381,11 +397,15 @@ def bench_entry(args, B):
         D = (torch.zeros((n, ld), dtype=torch.float32 if dt == "f32" else torch.float64, device="cuda")
              if rank == 0 else None)
     method = "exact"
+    # shards: the tcgen05 kernel in shard mode where it reproduces the map the mode needs -- unweighted data (bit-exact),
+    # or prior-weighted data in fast mode (fixed point, <= 1e-6 relative); the exact CUDA-core kernel otherwise
+    small_k = codes.shape[1] <= 512 and codes.shape[1] * (int(n_states) + 2) <= 16384
+    shard_method = "tensor" if small_k and (table is None or (mode == "fast" and int(n_states) <= 64)) else "exact"
 
     def step(cm):
         mid = torch.cuda.Event(enable_timing=True)
         if sharded_loop:
-            shard = build_shard(cm, missing_code, table, n_states, rank, world, dt)
+            shard = build_shard(cm, missing_code, table, n_states, rank, world, dt, shard_method)
             launches[0] += engine.last_launch_count()
             mid.record()
             joins, last2 = solve_fn(shard, n, args.algo, group, mode=mode)
@@ -462,6 +482,9 @@ def bench_entry(args, B):
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak * loop_gpus, "unit": "GB/s",
                     "frac": achieved / (peak * loop_gpus), "peak_source": peak_src + f" x {loop_gpus} GPU(s) running the loop",
                     "loop_ms": loop_ms, "map_and_gather_ms": ms_per_step - loop_ms,
+                    "map_kernel": (("whd_gemm_kernel in shard mode (tcgen05)" if shard_method == "tensor" else
+                                    "whd_exact_kernel, block-cyclic rows") if sharded_loop else
+                                   "whd_exact_kernel, one row block per rank"),
                     "traffic": scanned * esz / n_scans if scanned else 1.0005 * b_alg / n_scans,
                     "algorithmic_bytes_per_launch_mean": b_alg / n_scans,
                     "latency_model": {"us_per_iteration": 1e3 * loop_ms / n_scans,

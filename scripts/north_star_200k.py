@@ -24,6 +24,10 @@ ap.add_argument("--chars", type=int, default=40)
 ap.add_argument("--states", type=int, default=50)
 ap.add_argument("--missing", type=float, default=0.1)
 ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+ap.add_argument("--no-priors", action="store_true", help="plain Hamming distances (unweighted)")
+ap.add_argument("--map", default="auto", choices=["auto", "exact", "tensor"],
+                help="kernel that builds the shards; auto = tensor cores where they reproduce the map the mode needs "
+                     "(unweighted data: bit-exact; prior-weighted data in fast mode: fixed point), else CUDA cores")
 ap.add_argument("--compare-single", action="store_true",
                 help="rank 0 also runs the single-GPU loop in the same mode (the map must fit one GPU) and compares")
 a = ap.parse_args()
@@ -32,7 +36,7 @@ lr = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 args = argparse.Namespace(cells=a.cells, chars=a.chars, states=a.states, missing=a.missing, mutation_rate=0.1, seed=0,
-                          algo="nj", priors=True)
+                          algo="nj", priors=not a.no_priors)
 codes, missing_code, table, n_states = bench.make_workload(args)
 n = codes.shape[0]
 dt = "f32" if a.mode == "fast" else "f64"
@@ -41,7 +45,10 @@ cm_dev = torch.from_numpy(codes).cuda()
 peers = sharded.PeerGroup(n, dt)
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.perf_counter()
-shard = sharded.build_shard(cm_dev, missing_code, table, n_states, rank, world, dt)
+map_method = a.map
+if map_method == "auto":
+    map_method = "tensor" if (table is None or (a.mode == "fast" and n_states <= 64)) else "exact"
+shard = sharded.build_shard(cm_dev, missing_code, table, n_states, rank, world, dt, map_method)
 torch.cuda.synchronize(); dist.barrier()
 t1 = time.perf_counter()
 # sampled rows of this rank's shard vs the CPU oracle (reference algorithm), before the loop destroys the map
@@ -52,7 +59,10 @@ ok_map = True
 for local, g in zip(pick.tolist(), got):
     r = int(rows[local])
     want = po.whd_map(codes.astype(np.int64), missing_code, table, rows=(r, r + 1), threads=4)[0]
-    ok_map &= bool(np.array_equal(g, want.astype(g.dtype)))
+    if table is None or map_method == "exact":
+        ok_map &= bool(np.array_equal(g, want.astype(g.dtype)))
+    else:  # fixed-point tensor path: 1e-6 relative
+        ok_map &= bool((np.abs(g.astype(np.float64) - want) <= 1e-6 * np.maximum(np.abs(want), 1.0)).all())
 free_b, total_b = torch.cuda.mem_get_info()
 torch.cuda.synchronize(); dist.barrier()
 t2 = time.perf_counter()
@@ -87,7 +97,8 @@ if rank == 0:
     b_alg = bench.scan_bytes(n, esz)
     out = {"config": f"NJ {a.cells} cells x {a.chars} chars x {a.states} states, priors, {int(a.missing * 100)}% missing, "
                      f"implicit root; map and loop row-sharded over {world} B200 (P2P exchange)",
-           "mode": a.mode, "dtype": dt, "n_gpus": world,
+           "mode": a.mode, "dtype": dt, "n_gpus": world, "priors": not a.no_priors,
+           "map_kernel": "whd_gemm_kernel in shard mode (tcgen05)" if map_method == "tensor" else "whd_exact_kernel",
            "map_seconds": t1 - t0, "loop_seconds": t3 - t2, "solve_seconds": (t1 - t0) + (t3 - t2),
            "us_per_iteration": 1e6 * (t3 - t2) / max(n - 2, 1),
            "map_gpairs_per_s": n * (n - 1) / 2 / (t1 - t0) / 1e9,

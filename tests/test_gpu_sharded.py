@@ -106,6 +106,65 @@ def test_cyclic_shards_tile_the_full_map():
         assert seen.all()
 
 
+@pytest.mark.parametrize("weighted_path", ["i8", "bf16"])
+@pytest.mark.parametrize("n,m,S,world", [(5, 3, 2, 2), (130, 7, 3, 2), (257, 20, 9, 3), (700, 33, 17, 8),
+                                         (3000, 40, 50, 4), (4100, 60, 100, 8)])
+def test_tensor_core_shards_tile_the_full_tensor_map(n, m, S, world, weighted_path, monkeypatch):
+    """cas_whd_map_cyclic with CAS_MAP_TENSOR (tcgen05 kernel in shard mode: two 64-row half boxes per row tile, every
+    column of the rank's rows, no mirroring): unweighted shards are bit-identical to the rows of the exact map,
+    prior-weighted shards bit-identical to the rows of the full tensor map (same products, same accumulation order)
+    and within 1e-6 of the exact map."""
+    import torch
+    from cassiopeia_b200 import engine, sharded
+    from cassiopeia_b200.synthetic import simulate_character_matrix
+
+    monkeypatch.setenv("CAS_GEMM_WEIGHTED", weighted_path)
+    monkeypatch.setenv("CAS_GEMM_CTA_GROUP", "1")  # the shard mode lives in the single-SM kernel
+    cm, priors, table = simulate_character_matrix(n, m, S, seed=n, mutation_rate=0.6, missing_fraction=0.15)
+    with np.errstate(invalid="ignore"):
+        w = np.nan_to_num(-np.log(table))
+    cm_dev = torch.from_numpy(np.ascontiguousarray(cm, dtype=np.int32)).cuda()
+    for weights, dtype in ((None, "f64"), (None, "f32"), (w, "f64"), (w, "f32")):
+        if weights is None and weighted_path == "bf16":
+            continue  # the unweighted path does not depend on the switch
+        exact = engine.whd_map(cm, -1, weights, S, dtype=dtype, method="exact")[:, :n]
+        full = engine.whd_map(cm, -1, weights, S, dtype=dtype, method="tensor")[:, :n]
+        seen = np.zeros(n, dtype=bool)
+        for r in range(world):
+            shard = sharded.build_shard(cm_dev, -1, weights, S, r, world, dtype, method="tensor")[:, :n]
+            rows = sharded.shard_rows(n, r, world)
+            got = shard[: len(rows)]
+            if len(rows) == 0:
+                assert float(shard.abs().max()) == 0.0  # fewer 64-row blocks than ranks: an empty shard
+                continue
+            idx = torch.from_numpy(np.asarray(rows, dtype=np.int64)).cuda()
+            if weights is None:
+                assert torch.equal(got, exact[idx]), (dtype, r)
+            else:
+                assert torch.equal(got, full[idx]), (dtype, r)
+                rel = ((got.double() - exact[idx].double()).abs() / exact[idx].double().abs().clamp(min=1.0)).max().item()
+                assert rel <= 1e-6
+            assert float(shard[len(rows):].abs().max()) == 0.0 if shard.shape[0] > len(rows) else True
+            seen[rows] = True
+        assert seen.all()
+
+
+def test_sharded_solve_on_tensor_core_shards_equals_single_gpu():
+    """Unweighted data: shards built by the tensor kernel are the exact map, so the sharded exact-mode loop on them
+    gives the single-GPU exact-mode join list."""
+    import torch
+    from cassiopeia_b200 import engine, sharded
+    from cassiopeia_b200.synthetic import simulate_character_matrix
+
+    n, m, S, world = 2500, 40, 50, 4
+    cm, _, _ = simulate_character_matrix(n, m, S, seed=3, mutation_rate=0.3, missing_fraction=0.1)
+    D = engine.whd_map(cm, -1, None, S, dtype="f64", method="tensor")
+    want, want_last = engine.agglomerate(D, n, "nj", "exact")
+    got, got_last = sharded.emulated_solve(cm, -1, None, S, "nj", world, dtype="f64", p2p=True, mode="exact",
+                                           map_method="tensor")
+    assert np.array_equal(got, want) and np.array_equal(got_last, want_last)
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("name", ["sim64_s0_nj_priors", "sim256_s1_nj_plain", "sim1024_s0_nj_priors",
                                   "ties120_nj_plain", "ties120_nj_priors"])
