@@ -159,7 +159,8 @@ CAS_API int cas_smj_solve(const int32_t *cm_dev, int64_t n, int32_t m, int32_t m
 
 /* ---- row-sharded loop (n^2 map larger than one GPU; no reference counterpart) ----------
  * Slots are dealt to ranks in 64-row blocks, block-cyclically; a rank stores its rows in local
- * order, [cas_sharded_local_capacity(n, world), ld].  cas_whd_map_cyclic fills such a shard
+ * order, [cas_sharded_local_capacity(n, world), ld].  cas_whd_map_cyclic (method = CAS_MAP_EXACT, or
+ * CAS_MAP_TENSOR: the tcgen05 kernel in shard mode, workspace = cas_whd_workspace_bytes(..., CAS_MAP_TENSOR)) fills such a shard
  * (every rank needs only the replicated character matrix: no exchange).  cas_sharded_solve runs
  * the fast-mode loop with one NCCL all-gather of the ranks' candidates and one of the rows
  * (lo, hi, last) per iteration; every rank receives the full, identical join list.
