@@ -21,7 +21,8 @@ from __future__ import annotations
 import abc
 import gc
 import itertools
-from typing import Callable, List, Optional, Tuple
+import threading
+from typing import Callable, Dict, List, Optional, Tuple
 
 import networkx as nx
 import numpy as np
@@ -166,16 +167,54 @@ class DistanceSolver(abc.ABC):
               logfile: str = "stdout.log") -> None:
         names, D = self._device_map(cassiopeia_tree, layer)
         n = len(names)
-        joins, last2 = engine.agglomerate(D, n, self._algo, self.precision)
+        # the parts of the host tail that do not depend on the join list are computed by a worker thread while the
+        # GPU loop runs (the C call that enqueues the loop and the wait for its result both release the GIL)
+        pre: Dict[str, object] = {}
+        worker = None
+        if self.fast_tail and self._fast_tail_applicable(cassiopeia_tree, names, layer):
+            worker = threading.Thread(target=self._tail_precompute, name="cas-b200-tail",
+                                      args=(pre, cassiopeia_tree, names, layer, collapse_mutationless_edges))
+            worker.start()
+        try:
+            joins, last2 = engine.agglomerate(D, n, self._algo, self.precision)
+        finally:
+            if worker is not None:
+                worker.join()
         del D
         self.last_join_list = (joins, last2, names)
-        self.finish_tree(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges)
+        self.finish_tree(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges,
+                         precomputed=pre if pre.get("ok") else None)
+
+    def _tail_precompute(self, out: Dict[str, object], cassiopeia_tree, names, layer, collapse_mutationless_edges) -> None:
+        """Join-independent inputs of `_finish_tree_arrays` (no mutation of the tree object): internal node names, the
+        character matrix without the root sample, the leaves' state rows in map order.  Any failure leaves `out`
+        without the "ok" mark and the tail computes everything itself."""
+        try:
+            n_joins = max(len(names) - 2, 0)
+            out["internal_names"] = list(itertools.islice(solver_utilities.node_name_generator(), n_joins))
+            cm = cassiopeia_tree.character_matrix
+            root = cassiopeia_tree.root_sample_name
+            dropped = cm.drop(index=root) if (cm is not None and root in cm.index) else None
+            out["dropped"] = dropped
+            leaf_states = None
+            if collapse_mutationless_edges:
+                character_matrix = (cassiopeia_tree.layers[layer] if layer is not None
+                                    else (dropped if dropped is not None else cm))
+                values = character_matrix.to_numpy()
+                pos = character_matrix.index.get_indexer(list(names))
+                leaf_states = np.zeros((len(names), values.shape[1]), dtype=values.dtype)
+                leaf_states[pos >= 0] = values[pos[pos >= 0]]
+            out["leaf_states"] = leaf_states
+            out["ok"] = True
+        except Exception:  # pragma: no cover - the inline path reports the real error
+            out.clear()
 
     #: use the array-based tail (cassiopeia_b200/tree_tail.py) when the stock ``root_tree`` is in place
     fast_tail = True
 
     def finish_tree(self, cassiopeia_tree, names: List[str], joins: np.ndarray, last2: np.ndarray,
-                    layer: Optional[str] = None, collapse_mutationless_edges: bool = False) -> None:
+                    layer: Optional[str] = None, collapse_mutationless_edges: bool = False,
+                    precomputed: Optional[Dict[str, object]] = None) -> None:
         """Host tail of `solve`: turns an id-space join list (leaf at map row p has id p, the
         t-th join creates id n+t) into the rooted, populated tree of reference :181-231.
 
@@ -189,7 +228,8 @@ class DistanceSolver(abc.ABC):
             gc_was_enabled = gc.isenabled()
             gc.disable()
             try:
-                self._finish_tree_arrays(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges)
+                self._finish_tree_arrays(cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges,
+                                         precomputed)
             finally:
                 if gc_was_enabled:
                     gc.enable()
@@ -208,17 +248,27 @@ class DistanceSolver(abc.ABC):
             return True
         return all(np.issubdtype(dt, np.integer) for dt in character_matrix.dtypes)
 
-    def _finish_tree_arrays(self, cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges) -> None:
+    def _finish_tree_arrays(self, cassiopeia_tree, names, joins, last2, layer, collapse_mutationless_edges,
+                            precomputed: Optional[Dict[str, object]] = None) -> None:
         from .. import tree_tail
 
-        node_name_generator = solver_utilities.node_name_generator()
-        internal_names = list(itertools.islice(node_name_generator, len(joins)))
+        pre = precomputed if (precomputed and len(precomputed.get("internal_names", ())) == len(joins)) else None
+        if pre is not None:
+            internal_names = pre["internal_names"]
+        else:
+            node_name_generator = solver_utilities.node_name_generator()
+            internal_names = list(itertools.islice(node_name_generator, len(joins)))
         # remove root from character matrix before populating tree (:214-222)
-        if cassiopeia_tree.root_sample_name in cassiopeia_tree.character_matrix.index:
+        if pre is not None:
+            if pre["dropped"] is not None:
+                cassiopeia_tree.character_matrix = pre["dropped"]
+        elif cassiopeia_tree.root_sample_name in cassiopeia_tree.character_matrix.index:
             cassiopeia_tree.character_matrix = cassiopeia_tree.character_matrix.drop(
                 index=cassiopeia_tree.root_sample_name)
         leaf_states = None
-        if collapse_mutationless_edges:
+        if pre is not None:
+            leaf_states = pre["leaf_states"]
+        elif collapse_mutationless_edges:
             character_matrix = (cassiopeia_tree.layers[layer] if layer is not None
                                 else cassiopeia_tree.character_matrix)
             values = character_matrix.to_numpy()
