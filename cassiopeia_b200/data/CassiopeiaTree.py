@@ -149,8 +149,12 @@ class CassiopeiaTree:
             # node, `length` on every edge -- exactly what the passes below would leave behind
             self._network = tree
             character_matrix = self.layers[layer] if layer else self.character_matrix
+            prepared = self.__dict__.pop("_prepared_leaf_rows", None)
             if character_matrix is not None:
-                self.set_character_states_at_leaves(layer=layer)
+                if prepared is not None and len(prepared[0]) == character_matrix.shape[0]:
+                    self._set_leaf_rows(*prepared)
+                else:
+                    self.set_character_states_at_leaves(layer=layer)
             return
         if any(not isinstance(n, str) for n in tree.nodes):
             tree = nx.relabel_nodes(tree, {n: str(n) for n in tree.nodes})
@@ -191,6 +195,18 @@ class CassiopeiaTree:
         if set(leaves) != set(index):
             raise CassiopeiaTreeError("Character matrix index does not match set of leaves.")
         rows = character_matrix.to_numpy().tolist()
+        self._set_leaf_rows(index, rows, leaves)
+
+    def accept_prepared_leaf_rows(self, index: List[str], rows: List[List[int]]) -> None:
+        """`index` / `rows` = ``character_matrix.index.tolist()`` / ``character_matrix.to_numpy().tolist()`` of the
+        matrix (or layer) the NEXT ``populate_tree`` call of a prepared graph will read: the B200 solvers compute
+        them while the GPU loop runs."""
+        self._prepared_leaf_rows = (index, rows)
+
+    def _set_leaf_rows(self, index, rows, leaves=None) -> None:
+        leaves = self.leaves if leaves is None else leaves
+        if len(leaves) != len(index) or set(leaves) != set(index):
+            raise CassiopeiaTreeError("Character matrix index does not match set of leaves.")
         by_name = dict(zip(index, rows))
         node_attrs = self._network._node
         for n in leaves:

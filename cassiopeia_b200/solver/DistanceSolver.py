@@ -205,6 +205,11 @@ class DistanceSolver(abc.ABC):
                 leaf_states = np.zeros((len(names), values.shape[1]), dtype=values.dtype)
                 leaf_states[pos >= 0] = values[pos[pos >= 0]]
             out["leaf_states"] = leaf_states
+            # the per-leaf state lists populate_tree will attach (our tree class takes them ready-made)
+            if hasattr(cassiopeia_tree, "accept_prepared_leaf_rows"):
+                frame = cassiopeia_tree.layers[layer] if layer is not None else (dropped if dropped is not None else cm)
+                if frame is not None:
+                    out["leaf_rows"] = (frame.index.tolist(), frame.to_numpy().tolist())
             out["ok"] = True
         except Exception:  # pragma: no cover - the inline path reports the real error
             out.clear()
@@ -278,7 +283,12 @@ class DistanceSolver(abc.ABC):
         tree, internal_states = tree_tail.build_final_tree(
             names, internal_names, joins, last2, self._algo, cassiopeia_tree.root_sample_name, leaf_states,
             cassiopeia_tree.missing_state_indicator, collapse_mutationless_edges)
-        cassiopeia_tree.populate_tree(tree, layer=layer)
+        if pre is not None and pre.get("leaf_rows") is not None:
+            cassiopeia_tree.accept_prepared_leaf_rows(*pre["leaf_rows"])
+        try:
+            cassiopeia_tree.populate_tree(tree, layer=layer)
+        finally:
+            getattr(cassiopeia_tree, "__dict__", {}).pop("_prepared_leaf_rows", None)  # never outlives this call
         if internal_states:
             bulk = getattr(cassiopeia_tree, "set_internal_character_states", None)
             if bulk is not None:
