@@ -21,6 +21,7 @@ from __future__ import annotations
 import abc
 import gc
 import itertools
+import os
 import threading
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -171,7 +172,8 @@ class DistanceSolver(abc.ABC):
         # GPU loop runs (the C call that enqueues the loop and the wait for its result both release the GIL)
         pre: Dict[str, object] = {}
         worker = None
-        if self.fast_tail and self._fast_tail_applicable(cassiopeia_tree, names, layer):
+        if (self.fast_tail and self.overlap_tail and os.environ.get("CAS_TAIL_THREAD", "1") != "0"
+                and self._fast_tail_applicable(cassiopeia_tree, names, layer)):
             worker = threading.Thread(target=self._tail_precompute, name="cas-b200-tail",
                                       args=(pre, cassiopeia_tree, names, layer, collapse_mutationless_edges))
             worker.start()
@@ -216,6 +218,8 @@ class DistanceSolver(abc.ABC):
 
     #: use the array-based tail (cassiopeia_b200/tree_tail.py) when the stock ``root_tree`` is in place
     fast_tail = True
+    #: compute the join-independent inputs of that tail in a worker thread while the GPU loop runs
+    overlap_tail = True
 
     def finish_tree(self, cassiopeia_tree, names: List[str], joins: np.ndarray, last2: np.ndarray,
                     layer: Optional[str] = None, collapse_mutationless_edges: bool = False,
