@@ -429,9 +429,14 @@ def run_b200(args):
                 "launch_floor_us_per_iteration": floor_us, "floor_over_measured": floor_us / per_iter_us,
                 "floor": "the same three programmatically chained launches (grids of row test, pruned scan and merge "
                          "at full size) with empty kernels, measured live (cas_loop_launch_floor)",
-                "dependent_round_trips": "row test 3, scan 7 (work list, bounds, map, exact re-evaluation, CTA "
-                                         "reduction, grid reduction, publish), merge 5 (selection, rows, partial "
-                                         "sums, grid reduction, warm start): ~15 x 0.6-1 us of L2 / HBM latency",
+                "dependent_round_trips": ("row test 3, scan 7 (work list, bounds, map, exact re-evaluation, CTA "
+                                          "reduction, grid reduction, publish), merge 5 (selection, rows, partial "
+                                          "sums, grid reduction, warm start): ~15 x 0.6-1 us of L2 / HBM latency"
+                                          if args.algo == "nj" else
+                                          "row test 3 (+ one warp per row listed in the previous iteration: its "
+                                          "row-level bound rebuilt from the sub-segment bounds), scan 7 (work list, "
+                                          "bounds + partner ids, map + column ids, CTA reduction, grid reduction, "
+                                          "publish), merge 4 (selection, rows, grid sync, warm start)"),
                 "bytes_read_per_iteration": scanned * esz / n_scans}})
         roofline["dense_scan"] = dense_scan_sample(args, engine, torch, cm_dev, missing_code, table, n_states, D, dt,
                                                    method, esz, peak)
