@@ -122,6 +122,8 @@ __device__ __forceinline__ void exact_resolve(const ScanArgs &a, const PruneArgs
 
 template <typename T, bool NJ>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_kernel(ScanArgs a) {
+  pdl_wait();  // no-ops unless launched with programmatic stream serialization (the latency-bound small-k iterations)
+  pdl_launch_dependents();
   __shared__ __align__(16) float sU[NJ ? TC : 4];
   __shared__ Cand sCand[SCAN_WARPS];
   __shared__ bool sLast;
@@ -1263,7 +1265,8 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
       grid = sms * 2;  // few units per iteration in steady state: a small grid keeps the launch + tail short
       CAS_CUDA_TRY(launch_pdl(scan_pruned_kernel<T, NJ>, (unsigned)grid, (unsigned)SCAN_THREADS, stream, sa, pa));
     } else {
-      scan_kernel<T, NJ><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+      // dense scan: launch-bound once the map is L2-resident (every solve ends there; small inputs never leave it)
+      CAS_CUDA_TRY(launch_pdl(scan_kernel<T, NJ>, (unsigned)grid, (unsigned)SCAN_THREADS, stream, sa));
     }
     CAS_LAUNCH_CHECK();
 
@@ -1284,12 +1287,8 @@ static int agglom_run(void *D, int64_t n, int64_t ld, int mode, int64_t max_iter
     ma.newcol = w.newcol; ma.newcol_stride = n;
     ma.pmax = w.pmax; ma.pufup = w.pufup;
     ma.keyed = (prune_it && keyed) ? 1 : 0; ma.gstart = w.gstart;
-    if (prune_it) {
-      CAS_CUDA_TRY(launch_pdl(merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
-                              (unsigned)MERGE_THREADS, stream, ma));
-    } else {
-      merge_kernel<T, NJ><<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ma);
-    }
+    CAS_CUDA_TRY(launch_pdl(merge_kernel<T, NJ>, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
+                            (unsigned)MERGE_THREADS, stream, ma));
     CAS_LAUNCH_CHECK();
   }
   last2_kernel<<<1, 32, 0, stream>>>(w.ids, (int)(k_final < 2 ? k_final : 2), last2, (const int *)(w.counters + 6));
