@@ -1119,7 +1119,7 @@ static inline void plan_scan(int k, int target_ctas, int &tr, int &nrb, int &ncb
 // live size below which the loop switches (one way) to the dense scan; CAS_PRUNE_MIN_K overrides (tests use 0)
 int prune_min_k() {
   const char *e = getenv("CAS_PRUNE_MIN_K");
-  return e ? atoi(e) : 3072;
+  return e ? atoi(e) : 2048;
 }
 
 template <typename T, bool NJ>

@@ -1,5 +1,5 @@
 """NJ solve seconds @ n cells on one B200 (BASELINE.json metric (i)): map + complete loop, fast mode (float32 map),
-default scan policy (pruned above 3072 live nodes), with the dense scan beside it where that takes seconds.
+default scan policy (pruned above 2048 live nodes), with the dense scan beside it where that takes seconds.
 60 characters, 100 states, priors, 20 % missing, implicit root.  Prints a markdown table."""
 import os, sys, time
 import numpy as np, torch

@@ -4,7 +4,7 @@ import argparse, os, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 sys.path.insert(0, "scripts")
-os.environ["PRUNE_CHECK_DEFAULT_MIN_K"] = "1"  # keep the default switch to the dense scan below 3072 live nodes
+os.environ["PRUNE_CHECK_DEFAULT_MIN_K"] = "1"  # keep the default switch to the dense scan below 2048 live nodes
 from prune_check import build_map, run
 
 ap = argparse.ArgumentParser()

@@ -127,7 +127,7 @@ def test_upgma_keyed_bounds_on_arbitrary_symmetric_maps(n, kind, monkeypatch):
 
 
 def test_default_policy_switches_to_dense_at_small_sizes(monkeypatch):
-    """Default: NJ prunes above 3072 live nodes and finishes with the dense scan; same joins either way."""
+    """Default: NJ prunes above 2048 live nodes and finishes with the dense scan; same joins either way."""
     from cassiopeia_b200 import engine
 
     D, nn = _map(9000, 30, 10, "f32", 0.4, 0.2, True, seed=4)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(params=["pruned", "pruned-upgma-too", "dense"], autouse=True)
 def scan_policy(request, monkeypatch):
     """Every sharded test runs with the pruned scan kept down to the last iteration (the default policy
-    switches to the dense scan below 3072 live nodes, which these fixtures never exceed), with pruning forced
+    switches to the dense scan below 2048 live nodes, which these fixtures never exceed), with pruning forced
     for UPGMA as well, and with the dense scan."""
     monkeypatch.setenv("CAS_PRUNE_MIN_K", "0")
     if request.param == "dense":
