@@ -33,6 +33,7 @@ EXPORTS = (
     "cas_upgma_solve",
     "cas_last_launch_count",
     "cas_solve_host",
+    "cas_solve_host_release",
     "cas_nj_q",
     "cas_update_map",
     "cas_agglom_stats",
@@ -162,6 +163,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.cas_sharded_solve_emulated_p2p.argtypes = [vp, i64, i64, i32, i32, i32, i64, i32, vp, u64, vp, vp, vp, sz, vp]
     L.cas_sharded_exact_stats.restype = ctypes.c_int
     L.cas_sharded_exact_stats.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.cas_solve_host_release.restype = ctypes.c_int
+    L.cas_solve_host_release.argtypes = []
     L.cas_solve_host.restype = ctypes.c_int
     L.cas_solve_host.argtypes = [vp, i64, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]
 

@@ -1,4 +1,5 @@
 // C-ABI entry points of libcas_b200.so (declared in include/cas_b200.h).
+#include <mutex>
 #include <stdarg.h>
 #include <string.h>
 
@@ -240,11 +241,30 @@ int cas_upgma_solve(void *D, int64_t n, int64_t ld, int32_t dtype, int32_t mode,
 }
 
 // RAII device buffer for the host-buffer entry point
+// Device buffers of cas_solve_host are kept between calls (a cudaMalloc / cudaFree pair of a 20 GB map was measured
+// at anything between 10 and 400 ms): a call re-uses a cached buffer that is large enough, cas_solve_host_release()
+// frees them.  One call at a time (the cache is guarded by a mutex held for the whole call).
 struct DevBuf {
   void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  size_t cap = 0;
+  cudaError_t alloc(size_t bytes) {
+    bytes = bytes ? bytes : 1;
+    if (p && cap >= bytes) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes; else p = nullptr;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+static DevBuf g_host_bufs[7];
+static std::mutex g_host_mu;
+
+int cas_solve_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  for (auto &b : g_host_bufs) b.release();
+  return CAS_OK;
+}
 
 int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t missing,
                    const double *w_host, int32_t n_states, int32_t algo, int32_t mode,
@@ -266,7 +286,9 @@ int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t missing
   for (auto &e : ev) CAS_CUDA_TRY(cudaEventCreate(&e));
   struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); } } eg{ev};
 
-  DevBuf cm_d, w_d, D_d, ws_map, ws_loop, joins_d, last2_d;
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  DevBuf &cm_d = g_host_bufs[0], &w_d = g_host_bufs[1], &D_d = g_host_bufs[2], &ws_map = g_host_bufs[3],
+         &ws_loop = g_host_bufs[4], &joins_d = g_host_bufs[5], &last2_d = g_host_bufs[6];
   const size_t njoin = n > 2 ? (size_t)(n - 2) : 0;
   CAS_CUDA_TRY(cm_d.alloc((size_t)n * m * sizeof(int32_t)));
   if (weighted) CAS_CUDA_TRY(w_d.alloc((size_t)m * (n_states + 1) * sizeof(double)));
@@ -287,10 +309,10 @@ int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t missing
   CAS_CUDA_TRY(cudaEventRecord(ev[1], stream));
   int rc;
   if (map_method == CAS_MAP_TENSOR)
-    rc = whd_gemm_map((const int32_t *)cm_d.p, n, m, missing, (const double *)w_d.p, n_states, D_d.p,
+    rc = whd_gemm_map((const int32_t *)cm_d.p, n, m, missing, (const double *)(weighted ? w_d.p : nullptr), n_states, D_d.p,
                       ld, dtype, 0, n, ws_map.p, wsm, stream);
   else
-    rc = whd_exact_map((const int32_t *)cm_d.p, n, m, missing, (const double *)w_d.p, n_states,
+    rc = whd_exact_map((const int32_t *)cm_d.p, n, m, missing, (const double *)(weighted ? w_d.p : nullptr), n_states,
                        D_d.p, ld, dtype, 0, n, ws_map.p, wsm, stream);
   if (rc != CAS_OK) return rc;
   CAS_CUDA_TRY(cudaEventRecord(ev[2], stream));

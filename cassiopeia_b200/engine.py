@@ -270,6 +270,11 @@ def solve_host(cm: np.ndarray, missing: int, weights: Optional[np.ndarray], n_st
     return joins[: max(n - 2, 0)], last2, tm
 
 
+def solve_host_release() -> None:
+    """Frees the device buffers ``cas_solve_host`` keeps between calls."""
+    _lib.check(_lib.load().cas_solve_host_release(), "cas_solve_host_release")
+
+
 def nj_q(D: np.ndarray) -> np.ndarray:
     """Q-criterion matrix of a float64 [n, n] map (single-step hook, ``cas_nj_q``)."""
     torch = _torch()

@@ -304,6 +304,9 @@ CAS_API int cas_solve_host(const int32_t *cm_host, int64_t n, int32_t m, int32_t
                    const double *w_host, int32_t n_states, int32_t algo, int32_t mode,
                    int32_t map_method, int32_t *joins_host, int32_t *last2_host,
                    double *timings_ms);
+/* cas_solve_host keeps its device buffers (character matrix, map, workspaces, join list) between calls and re-uses
+ * them when they are large enough; this frees them. */
+CAS_API int cas_solve_host_release(void);
 
 #ifdef __cplusplus
 }

@@ -85,3 +85,27 @@ def test_solve_host_matches_device_path():
         joins, last2, tm = engine.solve_host(cm, g.missing, w, S, "nj", mode, "exact")
         assert np.array_equal(joins, g.joins)
         assert (tm >= 0).all()
+
+
+def test_solve_host_reuses_its_device_buffers_across_different_calls():
+    """cas_solve_host keeps its device buffers between calls: weighted after unweighted, smaller after larger, UPGMA
+    after NJ must all equal the device path (no stale weight table, no stale workspace), before and after a release."""
+    from cassiopeia_b200 import engine
+
+    big = Golden("sim1024_s0_nj_priors")
+    small = Golden("sim64_s0_nj_priors")
+    plain = Golden("sim256_s1_nj_plain")
+
+    def device(g, w, S, algo):
+        D = engine.whd_map(g.ordered_cm.astype(np.int32), g.missing, w, S, dtype="f64", method="exact")
+        return engine.agglomerate(D, g.ordered_cm.shape[0], algo, "exact")
+
+    for round_ in range(2):
+        for g, algo in ((big, "nj"), (plain, "nj"), (small, "nj"), (plain, "upgma"), (big, "upgma"), (small, "nj")):
+            w, S = _table(g)
+            S = max(S, 1)
+            cm = g.ordered_cm.astype(np.int32)
+            joins, last2, _ = engine.solve_host(cm, g.missing, w, S, algo, "exact", "exact")
+            dj, dl = device(g, w, S, algo)
+            assert np.array_equal(joins, dj) and np.array_equal(last2, dl), (round_, algo)
+        engine.solve_host_release()
