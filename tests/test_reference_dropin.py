@@ -14,6 +14,8 @@ import importlib.util
 import os
 import unittest
 
+import re
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -189,3 +191,32 @@ def test_tree_level_map_with_duplicate_cells_equals_reference_for_every_pair_fun
     want, got = want_tree.get_dissimilarity_map(), got_tree.get_dissimilarity_map()
     assert list(want.index) == list(got.index)
     np.testing.assert_array_equal(want.to_numpy(), got.to_numpy())
+
+
+@pytest.mark.parametrize("algo", ["nj", "upgma"])
+@pytest.mark.parametrize("collapse", [False, True])
+def test_tail_worker_thread_does_not_change_the_tree(algo, collapse, monkeypatch):
+    """solve() computes the join-independent inputs of the host tail in a worker thread while the loop runs
+    (DistanceSolver._tail_precompute); with the thread switched off (CAS_TAIL_THREAD=0) the tree must be the same:
+    nodes in the same order, the same edges with the same lengths, times and character states."""
+    import fake_engine
+    import cassiopeia_b200 as cb
+    from cassiopeia_b200.synthetic import simulate_character_matrix
+
+    fake_engine.install(monkeypatch)
+    cm, priors, _ = simulate_character_matrix(120, 12, 5, seed=4, mutation_rate=0.4, missing_fraction=0.15)
+    cm = np.vstack([cm, cm[:15]])  # duplicated cells
+    names = [f"c{i}" for i in range(cm.shape[0])]
+    trees = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("CAS_TAIL_THREAD", flag)
+        tree = cb.CassiopeiaTree(character_matrix=pd.DataFrame(cm, index=names), priors=priors)
+        solver = cb.NeighborJoiningSolver(add_root=True) if algo == "nj" else cb.UPGMASolver()
+        solver.solve(tree, collapse_mutationless_edges=collapse)
+        g = tree.get_tree_topology()
+        # internal node names carry a per-solve random prefix (unique, not reproducible): keep the counter only
+        norm = lambda name: re.sub(r"^cassiopeia_internal_node[0-9a-f]{12}", "internal_", name)
+        trees[flag] = ([norm(x) for x in g.nodes], [(norm(u), norm(v), d.get("length")) for u, v, d in g.edges(data=True)],
+                       {norm(x): tree.get_character_states(x) for x in g.nodes},
+                       {norm(x): tree.get_time(x) for x in g.nodes}, tree.character_matrix.index.tolist())
+    assert trees["1"] == trees["0"]
