@@ -170,3 +170,39 @@ def test_all_nan_map_raises_instead_of_indexing_with_minus_one():
     for algo, mode in (("nj", "fast"), ("nj", "exact"), ("upgma", "strict")):
         with pytest.raises(B200LibraryError):
             engine.agglomerate(_upload(D), n, algo, mode)
+
+
+def test_fast_mode_tree_against_exact_mode_at_20k_cells():
+    """The float32 fast mode promises the reference's tree only absent near-ties; at size, on the bench-like workload,
+    its unrooted Robinson-Foulds distance to the exact mode's (= the reference's) tree is measured 0 of 19 998 splits
+    (profiles/r2_exact_time.md).  Bound: 0.1 % of the splits."""
+    from cassiopeia_b200 import engine
+    from cassiopeia_b200.synthetic import simulate_character_matrix
+
+    n, m, S = 20000, 60, 100
+    cm, priors, table = simulate_character_matrix(n, m, S, seed=0, mutation_rate=0.1, missing_fraction=0.2)
+    cm = np.vstack([cm, np.zeros((1, m), dtype=cm.dtype)])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        w = np.nan_to_num(-np.log(table), nan=0.0, posinf=0.0)
+    nn = n + 1
+    je, le = engine.agglomerate(engine.whd_map(cm, -1, w, S, dtype="f64", method="exact"), nn, "nj", "exact")
+    jf, lf = engine.agglomerate(engine.whd_map(cm, -1, w, S, dtype="f32", method="exact"), nn, "nj", "fast")
+
+    rng = np.random.default_rng(12345)
+    key = rng.integers(1, 2 ** 62, size=nn, dtype=np.int64)
+    total = int(np.bitwise_xor.reduce(key))
+
+    def splits(joins):
+        h = np.zeros(2 * nn, dtype=np.int64)
+        h[:nn] = key
+        out = set()
+        for t, (a, b) in enumerate(joins.tolist()):
+            h[nn + t] = h[a] ^ h[b]
+            v = int(h[nn + t])
+            out.add(min(v, v ^ total))
+        return out
+
+    se, sf = splits(je), splits(jf)
+    rf = len(se ^ sf)
+    print(f"RF(fast, exact) at {nn} leaves: {rf} of {len(se)} splits")
+    assert rf <= len(se) // 1000
