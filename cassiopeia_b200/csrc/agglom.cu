@@ -1340,6 +1340,8 @@ __global__ void smj_negate_kernel(double *D, int64_t count) {
 
 // LCA row of the joined pair: all missing -> missing; one missing -> the other; equal -> that; else 0
 __global__ void smj_lca_kernel(SmjArgs a) {
+  pdl_wait();  // the SMJ loop's three kernels are launched with programmatic stream serialization, like the NJ loop's
+  pdl_launch_dependents();
   const Sel s = *a.sel;
   if (s.lo < 0) return;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.m; c += gridDim.x * blockDim.x) {
@@ -1383,6 +1385,8 @@ __device__ __forceinline__ double smj_pair(const SmjArgs &a, int v) {
 }
 
 __global__ void __launch_bounds__(MERGE_THREADS) smj_update_kernel(SmjArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const Sel s = *a.sel;
   if (s.lo < 0) return;
   const int lo = s.lo, hi = s.hi, k = a.k, last = k - 1;
@@ -1464,14 +1468,15 @@ int smj_solve(const int32_t *cm, int64_t n, int32_t m, int32_t missing, const do
     int grid = sa.ntiles < target_ctas ? sa.ntiles : target_ctas;
     if (grid > MAX_SCAN_CTAS) grid = MAX_SCAN_CTAS;
     if (grid < 1) grid = 1;
-    scan_kernel<double, false><<<grid, SCAN_THREADS, 0, stream>>>(sa);
+    CAS_CUDA_TRY(launch_pdl(scan_kernel<double, false>, (unsigned)grid, (unsigned)SCAN_THREADS, stream, sa));
     CAS_LAUNCH_CHECK();
     SmjArgs ua;
     ua.D = D; ua.ld = ld; ua.k = k; ua.sel = wk.sel; ua.ids = wk.ids; ua.new_id = (int)(n + t);
     ua.chars = chars; ua.cap = n; ua.m = m; ua.missing = missing; ua.w = w; ua.S = n_states; ua.fn = fn; ua.lca = lca;
-    smj_lca_kernel<<<(unsigned)((m + 127) / 128), 128, 0, stream>>>(ua);
+    CAS_CUDA_TRY(launch_pdl(smj_lca_kernel, (unsigned)((m + 127) / 128), 128u, stream, ua));
     CAS_LAUNCH_CHECK();
-    smj_update_kernel<<<(unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS), MERGE_THREADS, 0, stream>>>(ua);
+    CAS_CUDA_TRY(launch_pdl(smj_update_kernel, (unsigned)((k + MERGE_THREADS - 1) / MERGE_THREADS),
+                            (unsigned)MERGE_THREADS, stream, ua));
     CAS_LAUNCH_CHECK();
   }
   last2_kernel<<<1, 32, 0, stream>>>(wk.ids, (int)(k_final < 2 ? k_final : 2), last2, (const int *)(wk.counters + 6));
