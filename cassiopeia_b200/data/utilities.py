@@ -68,9 +68,9 @@ def dissimilarity_map_frame_inputs(character_matrix, priors, missing_state_indic
     if priors:
         weights = solver_utilities.transform_priors(priors, prior_transformation)
     cm = host_prep.as_int_matrix(character_matrix)
-    order = host_prep.reference_row_order(cm)
+    order, first = host_prep.reference_row_order(cm, return_first=True)
     names = np.asarray(character_matrix.index, dtype=object)[order].tolist()  # one gather, not n __getitem__ calls
-    n_unique, rep = host_prep.duplicate_groups(cm, order)
+    n_unique, rep = host_prep.duplicate_groups(cm, order, first=first if cm.shape[1] else None)
     D = device_map(cm[order], missing_state_indicator, weights, dtype=dtype, method=method, function=function,
                    count_rows=n_unique)
     if n_unique < cm.shape[0] and function not in ("weighted_hamming_distance", "hamming_distance"):

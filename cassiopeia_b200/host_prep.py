@@ -66,26 +66,28 @@ def _first_occurrence(cm: np.ndarray) -> np.ndarray:
     return first
 
 
-def duplicate_groups(cm: np.ndarray, order: np.ndarray):
+def duplicate_groups(cm: np.ndarray, order: np.ndarray, first: Optional[np.ndarray] = None):
     """(n_unique, rep) for the matrix permuted by `order` = reference_row_order(cm): the first n_unique rows are
     the distinct rows; rep[p] = position (in the permuted matrix) of the distinct row that row p duplicates
-    (rep[p] == p for the distinct rows)."""
+    (rep[p] == p for the distinct rows).  `first`: the first-occurrence vector `reference_row_order(cm,
+    return_first=True)` already computed for the same matrix."""
     cm = np.ascontiguousarray(cm)
     n = cm.shape[0]
     if n == 0 or cm.shape[1] == 0:
         return (min(n, 1), np.zeros(n, dtype=np.int64))
-    first = _first_occurrence(cm)
+    if first is None:
+        first = _first_occurrence(cm)
     pos_of = np.empty(n, dtype=np.int64)
     pos_of[order] = np.arange(n, dtype=np.int64)
     n_unique = int((first == np.arange(n)).sum())
     return n_unique, pos_of[first[order]]
 
 
-def reference_row_order(cm: np.ndarray) -> np.ndarray:
+def reference_row_order(cm: np.ndarray, return_first: bool = False):
     cm = np.ascontiguousarray(cm)
     n = cm.shape[0]
     if n == 0:
-        return np.zeros(0, dtype=np.int64)
+        return (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)) if return_first else np.zeros(0, dtype=np.int64)
     if cm.shape[1] == 0:
         first = np.zeros(n, dtype=np.int64)
     else:
@@ -96,7 +98,8 @@ def reference_row_order(cm: np.ndarray) -> np.ndarray:
     dups = idx[~is_first]
     # duplicates grouped by their unique row's first index (== unique-row order), then by own index
     dups = dups[np.lexsort((dups, first[dups]))]
-    return np.concatenate([uniq, dups])
+    order = np.concatenate([uniq, dups])
+    return (order, first) if return_first else order
 
 
 def compact_states(cm: np.ndarray, missing: int, weights: Optional[Dict[int, Dict[int, float]]],
